@@ -1,0 +1,167 @@
+/*
+ * revealer_b200.h -- C ABI of the B200-native REVEALER conditional-mutual-information search.
+ *
+ * The reference (genepattern/REVEALER, REVEALER_library.v5C.R, "LIB" below; live copy-B line
+ * numbers) has NO native interface: its hot path is three R-level seams inside REVEALER.v1.
+ * Every entry point here states which seam it replaces, so that an R maintainer can bind it
+ * with one .Call shim (revealer_b200/r/r_shim.c).
+ *
+ *   scoring loop      for (k in 1:nrow(m.2)) cmi[k,iter] <- cond.assoc(target, m.2[k,], seed, "IC")
+ *                                                                              LIB:1849-1856
+ *   rank              order(cmi[,iter], decreasing = (target.match != "negative"))[1]
+ *                                                                              LIB:1858-1864
+ *   seed update       seed <- apply(rbind(seed, m.2[top,]), 2, "max");
+ *                     cmi.seed[iter] <- assoc(target, seed, "IC")              LIB:2167-2171
+ *   seed baseline     cmi.seed.iter0 <- assoc(target, seed, "IC")              LIB:1833
+ *   permutation null  cmi.rand[k,j] <- cond.assoc(target.rand[j,], y, seed, "IC")   LIB:1853-1855
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types; no exception crosses the ABI;
+ *   - every function returns 0 on success, a negative rvl_status otherwise;
+ *     rvl_last_error(ctx) returns a message owned by ctx (valid until the next call on ctx);
+ *   - host input buffers are read-only and not retained after the call returns;
+ *   - one rvl_ctx == one GPU == one feature-row shard; a ctx is not re-entrant;
+ *   - there is NO CPU fallback: without a CUDA device rvl_create fails with RVL_ERR_CUDA.
+ *
+ * Row-index convention: rows are 0-based here; the R shim adds 1.
+ */
+#ifndef REVEALER_B200_H
+#define REVEALER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVL_ABI_VERSION 1
+#define RVL_MAX_GRID 32
+
+typedef struct rvl_ctx rvl_ctx;
+
+typedef enum {
+    RVL_OK = 0,
+    RVL_ERR_CUDA = -1,       /* no device / CUDA runtime error (message has the CUDA string) */
+    RVL_ERR_ARG = -2,        /* bad argument: NULL, size mismatch, n < 2, n_grid out of range ... */
+    RVL_ERR_NOT_BINARY = -3, /* a feature or seed entry is not exactly 0 or 1 (or is NA/NaN) */
+    RVL_ERR_STATE = -4,      /* call order: matrix / targets / seed not set yet */
+    RVL_ERR_NONFINITE = -5   /* NA/NaN/Inf in a target */
+} rvl_status;
+
+/* Numeric constants the reference buries in calls (SURVEY section 5, config tier 4). */
+typedef struct {
+    int32_t n_grid;           /* n.grid = 25                      LIB:2497,2511,2517 */
+    int32_t negative;         /* target.match == "negative"       LIB:1858 */
+    double bandwidth_mult;    /* 0.25 in cond.mutual.inf's delta  LIB:2564 */
+    double bandwidth_shrink;  /* -0.75 in delta*(1 + (-0.75)*rho) LIB:2532,2573 */
+} rvl_opts;
+
+/* Outputs of rvl_search; every pointer is caller-allocated (R: allocVector) or NULL to skip.
+ * These are the objects REVEALER.v1 allocates at LIB:1837-1842. */
+typedef struct {
+    double *cmi;        /* [n_targets][iters][F_local]  unsorted scores, local row order (cmi[,iter] before LIB:1863) */
+    int64_t *top;       /* [n_targets][iters]           GLOBAL row index of each iteration's winner (cmi.names[1,iter]) */
+    double *top_score;  /* [n_targets][iters]           the winner's score */
+    uint8_t *seed_iter; /* [n_targets][iters][n]        seed after each merge (seed.iter[iter,])   LIB:2169 */
+    double *cmi_seed;   /* [n_targets][iters]           assoc(target, seed) after each merge       LIB:2170 */
+    double *ic_seed0;   /* [n_targets]                  assoc(target, initial seed)                LIB:1833 */
+} rvl_result;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+int rvl_abi_version(void);
+
+/* Bind a context to CUDA device `device`.  Fails (RVL_ERR_CUDA) when no such device exists. */
+int rvl_create(rvl_ctx **out, int device);
+void rvl_destroy(rvl_ctx *ctx);
+const char *rvl_last_error(const rvl_ctx *ctx);
+
+/* Run all work of this ctx on an existing CUDA stream (a cudaStream_t passed as void*), e.g.
+ * torch's current stream so that a following torch.distributed collective is ordered after it. */
+int rvl_set_stream(rvl_ctx *ctx, void *cuda_stream);
+int rvl_set_options(rvl_ctx *ctx, const rvl_opts *opts);
+int rvl_default_options(rvl_opts *opts);
+
+/* Feature-row sharding: this ctx holds global rows [row_offset, row_offset+F_local)
+ * of a matrix of F_global rows, as rank `rank` of `world`.  Default: rank 0 of 1, offset 0. */
+int rvl_set_shard(rvl_ctx *ctx, int rank, int world, int64_t row_offset, int64_t F_global);
+
+/* ---- inputs (replace the R objects m.2 / target / seed handed to the loop at LIB:1849) --- */
+
+/* m.2 as R holds it: F x n doubles, column-major (m2[k + ld*s]); every entry must be 0 or 1.
+ * Bit-packed on the device into uint64[F][words], sample s -> bit s%64 of word s/64. */
+int rvl_load_matrix_f64_colmajor(rvl_ctx *ctx, const double *m2, int64_t F, int64_t n, int64_t ld);
+/* Same matrix as one byte per entry, row-major (m2[k*n + s]). */
+int rvl_load_matrix_u8_rowmajor(rvl_ctx *ctx, const uint8_t *m2, int64_t F, int64_t n);
+/* Already bit-packed rows, `words` uint64 per row (words >= ceil(n/64)); padding bits must be 0. */
+int rvl_load_matrix_bits(rvl_ctx *ctx, const uint64_t *bits, int64_t F, int64_t n, int64_t words);
+/* As rvl_load_matrix_bits, but `bits` is a DEVICE pointer on this ctx's device (no H2D). */
+int rvl_load_matrix_bits_device(rvl_ctx *ctx, const void *dev_bits, int64_t F, int64_t n, int64_t words);
+
+/* n_targets target profiles, row-major [n_targets][n].  Computes, on the device, per target:
+ * mean, range, bcv(target) (MASS::bcv; pair histogram + Brent), and the (n-1)-entry table of
+ * bcv() for binary vectors.  n_targets > 1 = a batch of independent searches (config C5), or,
+ * with rvl_set_null_targets, the reference's permuted targets (LIB:1843-1844). */
+int rvl_set_targets(rvl_ctx *ctx, const double *targets, int64_t n, int64_t n_targets);
+/* Targets [first_null, n_targets) are permutation-null targets: scored against target 0's
+ * seed, excluded from the winner selection.  first_null <= 0 disables. */
+int rvl_set_null_targets(rvl_ctx *ctx, int64_t first_null);
+
+/* Initial seed(s): one byte per sample, 0 or 1 (all zero == "NULLSEED", LIB:1691).
+ * per_target == 0: one seed [n] shared by all targets; else [n_targets][n]. */
+int rvl_set_seed(rvl_ctx *ctx, const uint8_t *seed, int64_t n, int per_target);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+
+/* One scoring pass with the current seed: out[t*F_local + k] = cond.assoc(target_t, m.2[k,], seed_t, "IC").
+ * Replaces the loop body LIB:1849-1856 for all rows (and all targets) at once. */
+int rvl_score_once(rvl_ctx *ctx, double *out_scores);
+
+/* The whole search, single shard: iters x (score, rank, merge, seed IC).  LIB:1846-2171. */
+int rvl_search(rvl_ctx *ctx, int iters, rvl_result *out);
+
+/* Split-phase form for feature-sharded runs (one ctx per rank).  Per iteration:
+ *   rvl_iter_score  : score local rows + local best per target -> candidate records in the send buffer
+ *   (caller all-gathers send -> recv across ranks: NCCL via torch.distributed, stream-ordered)
+ *   rvl_iter_merge  : every rank resolves the same global winner from `world` records
+ *                     (max score, ties -> lowest GLOBAL row, NaN never wins), ORs its row into
+ *                     the seed, recomputes assoc(target, seed) and the per-iteration tables.
+ * rvl_search_begin resets the iteration state (and computes ic_seed0); rvl_search_fetch copies results out.
+ * The exchange buffers are DEVICE memory owned by the caller (so a torch tensor can back them):
+ * send: rvl_candidate_bytes(ctx) bytes; recv: world * that. */
+int rvl_search_begin(rvl_ctx *ctx, int iters);
+size_t rvl_candidate_bytes(const rvl_ctx *ctx);
+int rvl_set_exchange_buffers(rvl_ctx *ctx, void *dev_send, void *dev_recv);
+int rvl_iter_score(rvl_ctx *ctx, int iter);
+int rvl_iter_merge(rvl_ctx *ctx, int iter);
+int rvl_search_fetch(rvl_ctx *ctx, rvl_result *out);
+int rvl_synchronize(rvl_ctx *ctx);
+
+/* assoc(x, y, "IC") for target t and an arbitrary 0/1 vector y (LIB:2491-2501): seed baselines
+ * at LIB:1820-1833 and REVEALER_assess_features' per-feature IC. */
+int rvl_assoc(rvl_ctx *ctx, int64_t target_index, const uint8_t *y, int64_t n, double *out_ic);
+
+/* Permutation p-values, LIB:1868-1869: pval[i] = #(cmi_rand > cmi[i]) / n_rand, on the device
+ * (sort + binary search instead of the O(F^2 n.perm) scan). */
+int rvl_pvalues(rvl_ctx *ctx, const double *cmi, int64_t F, const double *cmi_rand, int64_t n_rand,
+                double *out_pval);
+
+/* ---- introspection (parity tests, INTEGRATION checks) ----------------------------------- */
+
+/* bcv(target_t) as computed on the device. */
+int rvl_get_target_bandwidth(rvl_ctx *ctx, int64_t target_index, double *out_bcv);
+/* bcv() of a binary vector of length n with n1 ones, n1 = 0..n (entries 0 and n are 0). out[n+1]. */
+int rvl_get_binary_bandwidth_table(rvl_ctx *ctx, double *out_table);
+/* Row popcounts (rowSums(m.2), LIB:1656) of the local shard. out[F_local]. */
+int rvl_get_row_counts(rvl_ctx *ctx, int32_t *out_counts);
+/* Kernel launches issued by this ctx since creation (bench.py's gpu_launches claim). */
+int64_t rvl_launch_count(const rvl_ctx *ctx);
+/* Device time of the dominant score kernel, summed over launches since the last reset (ms),
+ * measured with CUDA events on the ctx stream; and the number of launches it covers. */
+int rvl_score_kernel_time(rvl_ctx *ctx, double *out_ms, int64_t *out_launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REVEALER_B200_H */

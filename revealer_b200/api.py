@@ -1,0 +1,468 @@
+"""Host-side mirror of the reference's R interface for the CMI-search path.
+
+Names, argument meaning and error behaviour follow REVEALER_library.v5C.R ("LIB", copy-B lines):
+
+    assoc(x, y, metric)                 LIB:2491-2501
+    cond_assoc(x, y, z, metric)         LIB:2503-2522
+    revealer_search(...)                the iteration section of REVEALER.v1, LIB:1837-1864 + 2167-2171
+    REVEALER_v1(...)                    REVEALER.v1's formals LIB:1504-1516 and its preprocessing
+                                        LIB:1575-1707 (host-side, numpy; no plots, no PDF)
+
+Everything numerical is done by librevealer_b200.so through its C ABI (include/revealer_b200.h).
+This module never computes a score itself and has no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import rvl_opts, rvl_result
+
+
+class RevealerError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("rvl error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def pack_bits(m):
+    """0/1 matrix (F x n, any integer/bool/float dtype) -> (uint64[F][words], words), sample s at
+    bit s%64 of word s/64, rows padded to an even number of words (16-byte rows)."""
+    m = np.asarray(m)
+    if m.ndim == 1:
+        m = m[None, :]
+    F, n = m.shape
+    if not np.all((m == 0) | (m == 1)):
+        raise RevealerError(_lib.RVL_ERR_NOT_BINARY, "matrix has an entry that is not 0 or 1")
+    words = ((n + 63) // 64 + 1) & ~1
+    by = np.packbits(m.astype(np.uint8), axis=1, bitorder="little")
+    out = np.zeros((F, words * 8), dtype=np.uint8)
+    out[:, : by.shape[1]] = by
+    return out.view("<u8").reshape(F, words), words
+
+
+def shard_rows(F, world, rank):
+    """Contiguous row block of rank `rank`: [rank*F/world, (rank+1)*F/world)  (SURVEY 8e)."""
+    lo = (rank * F) // world
+    hi = ((rank + 1) * F) // world
+    return lo, hi - lo
+
+
+def resolve_winner(scores, rows, negative=False):
+    """The deterministic rule every rank applies to the gathered candidates: R's stable
+    order(decreasing = !negative)[1] -- best score, ties -> lowest global row, NaN never ahead of a
+    number (LIB:1858-1862).  rows < 0 mark empty shards.  Returns the index into the candidate list."""
+    best = -1
+    for i, (v, r) in enumerate(zip(scores, rows)):
+        if r < 0:
+            continue
+        if best < 0:
+            best = i
+            continue
+        bv, br = scores[best], rows[best]
+        vn, bn = np.isnan(v), np.isnan(bv)
+        if vn or bn:
+            ahead = (r < br) if (vn and bn) else bool(bn)
+        elif v != bv:
+            ahead = (v < bv) if negative else (v > bv)
+        else:
+            ahead = r < br
+        if ahead:
+            best = i
+    return best
+
+
+class RevealerContext:
+    """One GPU, one feature-row shard.  Thin object wrapper over rvl_ctx."""
+
+    def __init__(self, device=0, n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75, negative=False):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._lib.rvl_create(C.byref(self._h), int(device))
+        if rc != 0:
+            self._h = None
+            raise RevealerError(rc, "rvl_create failed: no usable CUDA device %d (there is no CPU fallback)" % device)
+        self.device = device
+        self.F = None
+        self.n = None
+        self.T = 0
+        self.world, self.rank, self.row_offset = 1, 0, 0
+        self._keep = []
+        self.set_options(n_grid=n_grid, bandwidth_mult=bandwidth_mult, bandwidth_shrink=bandwidth_shrink,
+                         negative=negative)
+
+    # -- plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise RevealerError(rc, self._lib.rvl_last_error(self._h).decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rvl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_options(self, n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75, negative=False):
+        o = rvl_opts(int(n_grid), int(bool(negative)), float(bandwidth_mult), float(bandwidth_shrink))
+        self._ck(self._lib.rvl_set_options(self._h, C.byref(o)))
+        self.opts = o
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._lib.rvl_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr))))
+
+    def set_shard(self, rank, world, row_offset, F_global):
+        self._ck(self._lib.rvl_set_shard(self._h, rank, world, row_offset, F_global))
+        self.rank, self.world, self.row_offset = rank, world, row_offset
+
+    # -- inputs
+    def load_matrix(self, m2):
+        """m2: F x n.  float64 -> the R layout path (column-major doubles, validated and packed on the
+        device); uint8/bool -> row-major bytes; uint64 -> already bit-packed rows."""
+        m2 = np.asarray(m2)
+        if m2.ndim != 2:
+            raise RevealerError(_lib.RVL_ERR_ARG, "feature matrix must be 2-D (F x n)")
+        F, n = m2.shape
+        if m2.dtype == np.float64:
+            a = np.asfortranarray(m2)
+            self._ck(self._lib.rvl_load_matrix_f64_colmajor(self._h, _dp(a), F, n, max(F, 1)))
+        elif m2.dtype in (np.uint8, np.bool_):
+            a = np.ascontiguousarray(m2).view(np.uint8)
+            self._ck(self._lib.rvl_load_matrix_u8_rowmajor(self._h, a.ctypes.data_as(C.POINTER(C.c_uint8)), F, n))
+        else:
+            raise RevealerError(_lib.RVL_ERR_ARG, "feature matrix dtype must be float64, uint8 or bool")
+        self.F, self.n = F, n
+
+    def load_matrix_bits(self, bits, n):
+        bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        F, words = bits.shape
+        self._ck(self._lib.rvl_load_matrix_bits(self._h, bits.ctypes.data_as(C.POINTER(C.c_uint64)), F, n, words))
+        self.F, self.n = F, n
+
+    def load_matrix_bits_device(self, dev_ptr, F, n, words):
+        self._ck(self._lib.rvl_load_matrix_bits_device(self._h, C.c_void_p(int(dev_ptr)), F, n, words))
+        self.F, self.n = F, n
+
+    def set_targets(self, targets, first_null=0):
+        t = np.ascontiguousarray(np.atleast_2d(np.asarray(targets, dtype=np.float64)))
+        T, n = t.shape
+        self._ck(self._lib.rvl_set_targets(self._h, _dp(t), n, T))
+        self.T, self.n = T, n
+        if first_null and first_null > 0:
+            self._ck(self._lib.rvl_set_null_targets(self._h, first_null))
+
+    def set_seed(self, seed):
+        s = np.asarray(seed)
+        if not np.all((s == 0) | (s == 1)):
+            raise RevealerError(_lib.RVL_ERR_NOT_BINARY, "seed has an entry that is not 0 or 1")
+        s = np.ascontiguousarray(s.astype(np.uint8))
+        per_target = 1 if s.ndim == 2 else 0
+        n = s.shape[-1]
+        self._ck(self._lib.rvl_set_seed(self._h, s.ctypes.data_as(C.POINTER(C.c_uint8)), n, per_target))
+
+    # -- hot path
+    def score_once(self):
+        out = np.empty((self.T, self.F), dtype=np.float64)
+        self._ck(self._lib.rvl_score_once(self._h, _dp(out)))
+        return out
+
+    def _alloc_result(self, iters, want_cmi=True):
+        T, F, n = self.T, self.F, self.n
+        res = dict(
+            cmi=np.empty((T, iters, F), dtype=np.float64) if want_cmi else None,
+            top=np.empty((T, iters), dtype=np.int64),
+            top_score=np.empty((T, iters), dtype=np.float64),
+            seed_iter=np.empty((T, iters, n), dtype=np.uint8),
+            cmi_seed=np.empty((T, iters), dtype=np.float64),
+            ic_seed0=np.empty((T,), dtype=np.float64),
+        )
+        r = rvl_result()
+        r.cmi = _dp(res["cmi"]) if want_cmi else None
+        r.top = res["top"].ctypes.data_as(C.POINTER(C.c_int64))
+        r.top_score = _dp(res["top_score"])
+        r.seed_iter = res["seed_iter"].ctypes.data_as(C.POINTER(C.c_uint8))
+        r.cmi_seed = _dp(res["cmi_seed"])
+        r.ic_seed0 = _dp(res["ic_seed0"])
+        return res, r
+
+    def search(self, iters, want_cmi=True, fetch=True):
+        """iters x (score all rows, rank, OR-merge the winner into the seed, assoc(target, seed))."""
+        if not fetch:
+            self._ck(self._lib.rvl_search(self._h, int(iters), None))
+            return None
+        res, r = self._alloc_result(iters, want_cmi)
+        self._ck(self._lib.rvl_search(self._h, int(iters), C.byref(r)))
+        return res
+
+    # split-phase (sharded) form
+    def search_begin(self, iters):
+        self._ck(self._lib.rvl_search_begin(self._h, int(iters)))
+
+    def candidate_bytes(self):
+        return int(self._lib.rvl_candidate_bytes(self._h))
+
+    def set_exchange_buffers(self, send_ptr, recv_ptr):
+        self._ck(self._lib.rvl_set_exchange_buffers(self._h, C.c_void_p(int(send_ptr)), C.c_void_p(int(recv_ptr))))
+
+    def iter_score(self, it):
+        self._ck(self._lib.rvl_iter_score(self._h, int(it)))
+
+    def iter_merge(self, it):
+        self._ck(self._lib.rvl_iter_merge(self._h, int(it)))
+
+    def search_fetch(self, iters, want_cmi=True):
+        res, r = self._alloc_result(iters, want_cmi)
+        self._ck(self._lib.rvl_search_fetch(self._h, C.byref(r)))
+        return res
+
+    def synchronize(self):
+        self._ck(self._lib.rvl_synchronize(self._h))
+
+    def assoc(self, y, target_index=0):
+        y = np.asarray(y)
+        if not np.all((y == 0) | (y == 1)):
+            raise RevealerError(_lib.RVL_ERR_NOT_BINARY, "y has an entry that is not 0 or 1")
+        y = np.ascontiguousarray(y.astype(np.uint8))
+        out = C.c_double()
+        self._ck(self._lib.rvl_assoc(self._h, int(target_index), y.ctypes.data_as(C.POINTER(C.c_uint8)), len(y),
+                                     C.byref(out)))
+        return out.value
+
+    def pvalues(self, cmi, cmi_rand):
+        c = np.ascontiguousarray(cmi, dtype=np.float64)
+        r = np.ascontiguousarray(np.ravel(cmi_rand), dtype=np.float64)
+        out = np.empty(len(c), dtype=np.float64)
+        self._ck(self._lib.rvl_pvalues(self._h, _dp(c), len(c), _dp(r), len(r), _dp(out)))
+        return out
+
+    # -- introspection
+    def target_bandwidth(self, t=0):
+        out = C.c_double()
+        self._ck(self._lib.rvl_get_target_bandwidth(self._h, int(t), C.byref(out)))
+        return out.value
+
+    def binary_bandwidth_table(self):
+        out = np.empty(self.n + 1, dtype=np.float64)
+        self._ck(self._lib.rvl_get_binary_bandwidth_table(self._h, _dp(out)))
+        return out
+
+    def row_counts(self):
+        out = np.empty(self.F, dtype=np.int32)
+        self._ck(self._lib.rvl_get_row_counts(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def launch_count(self):
+        return int(self._lib.rvl_launch_count(self._h))
+
+    def score_kernel_time(self, reset=False):
+        ms, nl = C.c_double(), C.c_int64()
+        self._ck(self._lib.rvl_score_kernel_time(self._h, C.byref(ms), C.byref(nl), int(reset)))
+        return ms.value, nl.value
+
+
+# ---------------------------------------------------------------------------------------------
+# Reference-shaped functions
+# ---------------------------------------------------------------------------------------------
+
+def _unique_is_one(v):
+    v = np.asarray(v)
+    return v.size > 0 and bool(np.all(v == v.flat[0]))
+
+
+def assoc(x, y, metric="IC", device=0, n_grid=25):
+    """assoc(x, y, metric), LIB:2491-2501.  y must be a 0/1 vector (binary features only)."""
+    if metric != "IC":
+        raise RevealerError(_lib.RVL_ERR_ARG, 'only metric="IC" is implemented (assoc.metric is hard-coded to "IC", LIB:1522)')
+    with RevealerContext(device, n_grid=n_grid) as ctx:
+        ctx.set_targets(x)
+        return ctx.assoc(y, 0)
+
+
+def cond_assoc(x, y, z, metric="IC", device=0, n_grid=25):
+    """cond.assoc(x, y, z, metric), LIB:2503-2522: 0 for constant x or y; IC(x,y) for constant z;
+    CIC(x,y|z) otherwise.  y and z must be 0/1 vectors."""
+    if metric != "IC":
+        raise RevealerError(_lib.RVL_ERR_ARG, 'only metric="IC" is implemented (assoc.metric is hard-coded to "IC", LIB:1522)')
+    with RevealerContext(device, n_grid=n_grid) as ctx:
+        ctx.load_matrix(np.asarray(y, dtype=np.float64)[None, :])
+        ctx.set_targets(x)
+        ctx.set_seed(z)
+        return float(ctx.score_once()[0, 0])
+
+
+def revealer_search(target, m2, seed=None, max_n_iter=5, target_match="positive", n_grid=25,
+                    bandwidth_mult=0.25, bandwidth_shrink=-0.75, target_rand=None, n_markers=30, device=0,
+                    ctx=None):
+    """The iteration section of REVEALER.v1 (LIB:1837-1864, 2167-2171) on in-memory inputs.
+
+    target        double[n]  (already ordered as REVEALER.v1 orders samples, LIB:1626-1633)
+    m2            F x n 0/1 matrix (seed rows already removed, LIB:1703-1705)
+    seed          0/1 [n] or None == "NULLSEED" (all zero, LIB:1691)
+    target_rand   optional n.perm x n permuted targets (LIB:1843-1844); adds the null scores and the
+                  per-iteration permutation p-values of LIB:1868-1869
+    Returns the objects REVEALER.v1 builds: cmi (F x iters, UNSORTED), order (iters x F, R's order()),
+    top (0-based winner per iteration), seed_iter, cmi_seed, ic_seed0, and with target_rand also
+    cmi_rand (iters x F x n.perm) and p_val (iters x F, aligned with cmi rows).
+    """
+    if target_match not in ("positive", "negative"):
+        raise RevealerError(_lib.RVL_ERR_ARG, 'target.match must be "positive" or "negative"')
+    negative = target_match == "negative"
+    target = np.asarray(target, dtype=np.float64)
+    n = target.shape[-1]
+    own = ctx is None
+    if own:
+        ctx = RevealerContext(device, n_grid=n_grid, bandwidth_mult=bandwidth_mult,
+                              bandwidth_shrink=bandwidth_shrink, negative=negative)
+    try:
+        if own or m2 is not None:
+            ctx.load_matrix(m2)
+        targets = target[None, :]
+        first_null = 0
+        if target_rand is not None:
+            targets = np.vstack([targets, np.asarray(target_rand, dtype=np.float64)])
+            first_null = 1
+        ctx.set_targets(targets, first_null=first_null)
+        ctx.set_seed(np.zeros(n, dtype=np.uint8) if seed is None else seed)
+        res = ctx.search(max_n_iter)
+        cmi = res["cmi"][0].T.copy()  # F x iters like R
+        out = dict(cmi=cmi, top=res["top"][0], top_score=res["top_score"][0], seed_iter=res["seed_iter"][0],
+                   cmi_seed=res["cmi_seed"][0], ic_seed0=float(res["ic_seed0"][0]))
+        # display-side ranking (R's order(); stable, NaN last)
+        key = np.where(np.isnan(cmi), np.inf, cmi if negative else -cmi)
+        out["order"] = np.stack([np.argsort(key[:, it], kind="stable") for it in range(max_n_iter)])
+        out["top_markers"] = out["order"][:, :n_markers]
+        if target_rand is not None:
+            out["cmi_rand"] = np.transpose(res["cmi"][1:], (1, 2, 0)).copy()  # iters x F x n.perm
+            out["p_val"] = np.stack([ctx.pvalues(cmi[:, it], out["cmi_rand"][it]) for it in range(max_n_iter)])
+        return out
+    finally:
+        if own:
+            ctx.close()
+
+
+def read_gct(path):
+    """MSIG.Gct2Frame, LIB:2616-2626: skip 2 lines, first column row names, second descriptions."""
+    with open(path) as fh:
+        fh.readline()
+        fh.readline()
+        header = fh.readline().rstrip("\n").split("\t")
+        names = header[2:]
+        rows, descs, data = [], [], []
+        for line in fh:
+            if not line.strip():
+                continue
+            p = line.rstrip("\n").split("\t")
+            rows.append(p[0])
+            descs.append(p[1])
+            data.append([float(v) if v not in ("", "NA") else np.nan for v in p[2:]])
+    return dict(ds=np.asarray(data, dtype=np.float64), row_names=rows, descs=descs, names=names)
+
+
+def REVEALER_v1(ds1, target_name, target_match="positive", ds2=None, seed_names=None, exclude_features=None,
+                max_n_iter=5, pdf_output_file=None, count_thres_low=None, count_thres_high=None, n_markers=30,
+                locs_table_file=None, n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75, n_perm=0,
+                r_seed=34578, device=0):
+    """REVEALER.v1 with its 12 formals (LIB:1504-1516) plus the optional grid/bandwidth arguments.
+    ds1 / ds2: GCT path or dict(ds, row_names, names) as MSIG.Gct2Frame returns.  Preprocessing
+    mirrors LIB:1575-1707: drop NA-target samples, intersect samples, sort by target, drop the target
+    row from the features, count filter (seeds always kept), build the seed as the column-wise max of
+    the seed rows and remove those rows.  No plots/PDF (pdf_output_file and locs_table_file are accepted
+    and ignored).  n_perm > 0 adds the permutation null with numpy's PCG64(r_seed) (R's sample() stream is
+    not reproduced)."""
+    d1 = read_gct(ds1) if isinstance(ds1, str) else ds1
+    d2 = read_gct(ds2) if isinstance(ds2, str) else ds2
+    m1 = np.asarray(d1["ds"], dtype=np.float64)
+    names1 = list(d1["names"])
+    rows1 = list(d1["row_names"])
+    if target_name not in rows1:
+        raise RevealerError(_lib.RVL_ERR_ARG, "target %r not found in ds1" % target_name)
+    tgt = m1[rows1.index(target_name)]
+    keep = ~np.isnan(tgt)                                   # LIB:1589-1594
+    m1, names1 = m1[:, keep], [s for s, k in zip(names1, keep) if k]
+    m2 = np.asarray(d2["ds"], dtype=np.float64)
+    names2 = list(d2["names"])
+    rows2 = list(d2["row_names"])
+    pos2 = {s: i for i, s in enumerate(names2)}             # LIB:1596-1601 intersect
+    overlap = [s for s in names1 if s in pos2]
+    i1 = [names1.index(s) for s in overlap]
+    i2 = [pos2[s] for s in overlap]
+    m1, m2 = m1[:, i1], m2[:, i2]
+    target = m1[rows1.index(target_name)]
+    negative = target_match == "negative"                   # LIB:1626-1633
+    ind = np.argsort(target if negative else -target, kind="stable")
+    target, m2 = target[ind], m2[:, ind]
+    sample_names = [overlap[i] for i in ind]
+    if target_name in rows2:                                # LIB:1635-1638
+        loc = rows2.index(target_name)
+        m2 = np.delete(m2, loc, axis=0)
+        rows2 = rows2[:loc] + rows2[loc + 1:]
+    if seed_names is None or (isinstance(seed_names, str) and seed_names in ("NULL", "NULLSEED")):
+        seed_list = []
+    elif isinstance(seed_names, str):
+        seed_list = [seed_names]
+    else:
+        seed_list = list(seed_names)
+    if count_thres_low is not None and count_thres_high is not None:   # LIB:1655-1671
+        sums = m2.sum(axis=1)
+        retain = (sums >= count_thres_low) & (sums <= count_thres_high)
+        for s in seed_list:
+            if s in rows2:
+                retain[rows2.index(s)] = True
+        m2 = m2[retain]
+        rows2 = [r for r, k in zip(rows2, retain) if k]
+    if seed_list:                                           # LIB:1690-1707
+        missing = [s for s in seed_list if s not in rows2]
+        if missing:
+            raise RevealerError(_lib.RVL_ERR_ARG, "seed(s) not found in ds2: %s" % ", ".join(missing))
+        locs = [rows2.index(s) for s in seed_list]
+        seed_vectors = m2[locs]
+        seed = seed_vectors.max(axis=0)
+        m2 = np.delete(m2, locs, axis=0)
+        rows2 = [r for i, r in enumerate(rows2) if i not in set(locs)]
+    else:
+        seed = np.zeros(m2.shape[1])
+        seed_vectors = seed[None, :]
+    if exclude_features is not None:                        # LIB:1716-1720
+        ex = {rows2.index(s) for s in exclude_features if s in rows2}
+        m2 = np.delete(m2, sorted(ex), axis=0)
+        rows2 = [r for i, r in enumerate(rows2) if i not in ex]
+    target_rand = None
+    if n_perm > 0:                                          # LIB:1843-1844
+        rng = np.random.Generator(np.random.PCG64(r_seed))
+        target_rand = np.stack([rng.permutation(target) for _ in range(n_perm)])
+    out = revealer_search(target, m2, seed, max_n_iter=max_n_iter, target_match=target_match, n_grid=n_grid,
+                          bandwidth_mult=bandwidth_mult, bandwidth_shrink=bandwidth_shrink,
+                          target_rand=target_rand, n_markers=n_markers, device=device)
+    out["feature_names"] = rows2
+    out["sample_names"] = sample_names
+    out["target"] = target
+    out["seed_names_iter"] = [rows2[i] for i in out["top"]]       # seed.names.iter  LIB:2167
+    med = np.median(target)                                         # LIB:1810-1815
+    locs_t = (target <= med) if negative else (target > med)
+    out["pct_explained_seed"] = out["seed_iter"][:, locs_t].sum(axis=1) / max(1, locs_t.sum())  # LIB:2171
+    # seed baselines LIB:1817-1833 (one assoc per seed row and per cumulative OR)
+    if seed_list:
+        with RevealerContext(device, n_grid=n_grid, bandwidth_mult=bandwidth_mult,
+                             bandwidth_shrink=bandwidth_shrink) as c2:
+            c2.set_targets(target)
+            cum = np.zeros_like(seed)
+            out["cmi_orig_seed"], out["cmi_orig_seed_cum"] = [], []
+            for v in seed_vectors:
+                out["cmi_orig_seed"].append(c2.assoc(v))
+                cum = np.maximum(cum, v)
+                out["cmi_orig_seed_cum"].append(c2.assoc(cum))
+    return out

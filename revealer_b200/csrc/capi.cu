@@ -1,0 +1,778 @@
+// capi.cu -- the C ABI declared in include/revealer_b200.h: context, uploads, the search driver.
+// Host code here is plumbing only (allocation, copies, launch order); all arithmetic of the path
+// runs in the kernels of score.cu / bandwidth.cu.  There is no CPU fallback.
+#include "../../include/revealer_b200.h"
+#include "rvl_common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/partition.h>
+#include <thrust/sort.h>
+
+// launchers (score.cu, bandwidth.cu)
+extern "C" {
+void rvl_launch_bcv_binary_table(int n, double *table, cudaStream_t st);
+void rvl_launch_target_setup(const double *x_all, int n, int T, int G, RvlTarget *tg, double *u_all, double *xc_all,
+                             int *bin_all, int *cnt_all, int *nonfinite, cudaStream_t st);
+size_t rvl_score_smem_bytes(int n, int words);
+cudaError_t rvl_score_configure(size_t smem);
+void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits, const double *u_all,
+                      const double *xc_all, const RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
+                      double *scores, cudaStream_t st);
+void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
+                          cudaStream_t st);
+void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of, const double *u_all,
+                      const double *xc_all, const uint64_t *y_all, const double *bcvtab, double *out,
+                      cudaStream_t st);
+void rvl_launch_argmax(const RvlParams *P, const double *scores, const uint64_t *bits, unsigned char *send,
+                       size_t rec_bytes, cudaStream_t st);
+void rvl_launch_merge(const RvlParams *P, int iter, int iters, int first_null, const unsigned char *recv,
+                      size_t rec_bytes, RvlTarget *tg, uint64_t *seeds, const double *u_all, const double *xc_all,
+                      const double *bcvtab, int64_t *top, double *top_score, uint64_t *seed_iter, double *cmi_seed,
+                      cudaStream_t st);
+void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols, int words,
+                                  uint64_t *bits, int *flag, cudaStream_t st);
+void rvl_launch_pack_u8_rowmajor(const uint8_t *m, int64_t F0, int64_t Fc, int n, int words, uint64_t *bits,
+                                 int *flag, cudaStream_t st);
+void rvl_launch_check_padding(const uint64_t *bits, int64_t F, int n, int words, int *flag, cudaStream_t st);
+void rvl_launch_row_counts(const uint64_t *bits, int64_t F, int words, int32_t *out, cudaStream_t st);
+void rvl_launch_pvalues(const double *cmi, int64_t F, const double *rand_sorted, int64_t n_valid, int64_t n_rand,
+                        double *pval, cudaStream_t st);
+}
+
+struct rvl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    rvl_opts opts;
+
+    // shard
+    int rank = 0, world = 1;
+    int64_t row_offset = 0, F_global = -1;
+
+    // matrix
+    int64_t F = -1;
+    int n = 0, words = 0;
+    uint64_t *d_bits = nullptr;
+    bool own_bits = true;
+
+    // targets
+    int T = 0;
+    int first_null = 0;
+    int G_targets = 0; // n_grid the target tables were built for
+    double *d_x = nullptr, *d_u = nullptr, *d_xc = nullptr, *d_bcvtab = nullptr;
+    int *d_bin = nullptr, *d_cnt = nullptr, *d_flag = nullptr;
+    RvlTarget *d_tg = nullptr;
+
+    // seeds
+    uint64_t *d_seed0 = nullptr; // initial seeds [T][words]
+    uint64_t *d_seed = nullptr;  // working seeds  [T][words]
+    bool have_seed = false;
+
+    // search state
+    int iters = 0;
+    double *d_scores = nullptr; // [iters][T][F]  (rvl_score_once uses slot 0)
+    size_t scores_cap = 0;
+    int64_t *d_top = nullptr;
+    double *d_top_score = nullptr, *d_cmi_seed = nullptr, *d_ic0 = nullptr;
+    uint64_t *d_seed_iter = nullptr;
+    int res_cap_T = 0, res_cap_iters = 0, res_cap_words = 0;
+    unsigned char *d_send = nullptr, *d_recv = nullptr; // exchange buffers
+    unsigned char *d_own_xchg = nullptr;                // owned fallback (world == 1)
+    size_t own_xchg_bytes = 0;
+
+    // instrumentation
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_events;
+    size_t score_events_used = 0;
+    double score_ms = 0.0;
+    int64_t score_launches = 0;
+};
+
+static int fail(rvl_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, RVL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define GUARD()                                                                  \
+    if (!ctx) return RVL_ERR_ARG;                                                \
+    {                                                                            \
+        cudaError_t e_ = cudaSetDevice(ctx->device);                             \
+        if (e_ != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e_)); \
+    }
+
+template <class T> static cudaError_t dalloc(T **p, size_t count)
+{
+    *p = nullptr;
+    return cudaMalloc((void **)p, sizeof(T) * (count ? count : 1));
+}
+template <class T> static void dfree(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static RvlParams make_params(const rvl_ctx *c)
+{
+    RvlParams P;
+    P.n = c->n; P.words = c->words; P.G = c->opts.n_grid; P.negative = c->opts.negative;
+    P.bw_mult = c->opts.bandwidth_mult; P.bw_shrink = c->opts.bandwidth_shrink;
+    P.F = c->F; P.row_offset = c->row_offset; P.T = c->T; P.world = c->world; P.rank = c->rank;
+    return P;
+}
+
+extern "C" int rvl_abi_version(void) { return RVL_ABI_VERSION; }
+
+extern "C" int rvl_default_options(rvl_opts *o)
+{
+    if (!o) return RVL_ERR_ARG;
+    o->n_grid = 25; o->negative = 0; o->bandwidth_mult = 0.25; o->bandwidth_shrink = -0.75;
+    return RVL_OK;
+}
+
+extern "C" int rvl_create(rvl_ctx **out, int device)
+{
+    if (!out) return RVL_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return RVL_ERR_CUDA;
+    rvl_ctx *ctx = new (std::nothrow) rvl_ctx();
+    if (!ctx) return RVL_ERR_ARG;
+    ctx->device = device;
+    rvl_default_options(&ctx->opts);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return RVL_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+    *out = ctx;
+    return RVL_OK;
+}
+
+static void free_matrix(rvl_ctx *c)
+{
+    if (c->own_bits) dfree(c->d_bits);
+    c->d_bits = nullptr;
+    c->own_bits = true;
+    c->F = -1;
+}
+static void free_targets(rvl_ctx *c)
+{
+    dfree(c->d_x); dfree(c->d_u); dfree(c->d_xc); dfree(c->d_bcvtab); dfree(c->d_bin); dfree(c->d_cnt);
+    dfree(c->d_tg); dfree(c->d_seed0); dfree(c->d_seed);
+    c->T = 0; c->have_seed = false;
+}
+static void free_results(rvl_ctx *c)
+{
+    dfree(c->d_scores); c->scores_cap = 0;
+    dfree(c->d_top); dfree(c->d_top_score); dfree(c->d_cmi_seed); dfree(c->d_ic0); dfree(c->d_seed_iter);
+    c->res_cap_T = c->res_cap_iters = c->res_cap_words = 0;
+    dfree(c->d_own_xchg); c->own_xchg_bytes = 0;
+}
+
+extern "C" void rvl_destroy(rvl_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_matrix(ctx); free_targets(ctx); free_results(ctx);
+    dfree(ctx->d_flag);
+    for (auto &p : ctx->score_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *rvl_last_error(const rvl_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int rvl_set_stream(rvl_ctx *ctx, void *cuda_stream)
+{
+    GUARD();
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return RVL_OK;
+}
+
+extern "C" int rvl_set_options(rvl_ctx *ctx, const rvl_opts *o)
+{
+    GUARD();
+    if (!o) return fail(ctx, RVL_ERR_ARG, "opts is NULL");
+    if (o->n_grid < 2 || o->n_grid > RVL_MAX_GRID) return fail(ctx, RVL_ERR_ARG, "n_grid must be in [2, %d]", RVL_MAX_GRID);
+    if (!(o->bandwidth_mult > 0.0)) return fail(ctx, RVL_ERR_ARG, "bandwidth_mult must be > 0");
+    if (!(o->bandwidth_shrink > -1.0) || !(o->bandwidth_shrink <= 0.0))
+        return fail(ctx, RVL_ERR_ARG, "bandwidth_shrink must be in (-1, 0]");
+    if (ctx->T > 0 && o->n_grid != ctx->G_targets)
+        return fail(ctx, RVL_ERR_STATE, "n_grid must be set before rvl_set_targets");
+    ctx->opts = *o;
+    return RVL_OK;
+}
+
+extern "C" int rvl_set_shard(rvl_ctx *ctx, int rank, int world, int64_t row_offset, int64_t F_global)
+{
+    GUARD();
+    if (world < 1 || rank < 0 || rank >= world || row_offset < 0) return fail(ctx, RVL_ERR_ARG, "bad shard spec");
+    ctx->rank = rank; ctx->world = world; ctx->row_offset = row_offset; ctx->F_global = F_global;
+    return RVL_OK;
+}
+
+// ---- matrix ---------------------------------------------------------------------------------
+
+static int begin_matrix(rvl_ctx *ctx, int64_t F, int64_t n)
+{
+    if (F < 0 || n < 2 || n > (1 << 24)) return fail(ctx, RVL_ERR_ARG, "need F >= 0 and 2 <= n <= 2^24 (F=%lld n=%lld)", (long long)F, (long long)n);
+    if (ctx->T > 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "matrix has n=%lld but targets have n=%d", (long long)n, ctx->n);
+    free_matrix(ctx);
+    ctx->n = (int)n;
+    ctx->words = (int)(((n + 63) / 64 + 1) & ~1ll); // rows padded to 16 B
+    return RVL_OK;
+}
+
+static int check_flag(rvl_ctx *ctx, const char *what)
+{
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h) return fail(ctx, RVL_ERR_NOT_BINARY, "%s", what);
+    return RVL_OK;
+}
+
+extern "C" int rvl_load_matrix_f64_colmajor(rvl_ctx *ctx, const double *m2, int64_t F, int64_t n, int64_t ld)
+{
+    GUARD();
+    if (!m2 && F > 0) return fail(ctx, RVL_ERR_ARG, "m2 is NULL");
+    if (ld < F) return fail(ctx, RVL_ERR_ARG, "ld < F");
+    int rc = begin_matrix(ctx, F, n);
+    if (rc) return rc;
+    CK(dalloc(&ctx->d_bits, (size_t)F * ctx->words));
+    CK(cudaMemsetAsync(ctx->d_bits, 0, sizeof(uint64_t) * (size_t)F * ctx->words, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    ctx->F = F;
+    if (F == 0) return RVL_OK;
+    // column chunks of a multiple of 64 samples, <= ~256 MB staging
+    int64_t cols = (256ll << 20) / (8 * ld);
+    cols = (cols / 64) * 64;
+    if (cols < 64) cols = 64;
+    double *stage = nullptr;
+    int64_t stage_cols = cols < n ? cols : ((n + 63) / 64) * 64;
+    CK(dalloc(&stage, (size_t)ld * stage_cols));
+    for (int64_t s0 = 0; s0 < n; s0 += cols) {
+        int64_t nc = (n - s0 < cols) ? (n - s0) : cols;
+        cudaError_t e = cudaMemcpyAsync(stage, m2 + ld * s0, sizeof(double) * (size_t)ld * nc, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(stage); return fail(ctx, RVL_ERR_CUDA, "H2D: %s", cudaGetErrorString(e)); }
+        rvl_launch_pack_f64_colmajor(stage, F, ld, (int)s0, (int)nc, ctx->words, ctx->d_bits, ctx->d_flag, ctx->stream);
+        ctx->launches++;
+        // the staging buffer is reused by the next chunk: stream order makes that safe
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "pack: %s", cudaGetErrorString(e));
+    rc = check_flag(ctx, "feature matrix has an entry that is not 0 or 1 (binary features only; no fallback)");
+    if (rc) free_matrix(ctx);
+    return rc;
+}
+
+extern "C" int rvl_load_matrix_u8_rowmajor(rvl_ctx *ctx, const uint8_t *m2, int64_t F, int64_t n)
+{
+    GUARD();
+    if (!m2 && F > 0) return fail(ctx, RVL_ERR_ARG, "m2 is NULL");
+    int rc = begin_matrix(ctx, F, n);
+    if (rc) return rc;
+    CK(dalloc(&ctx->d_bits, (size_t)F * ctx->words));
+    CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    ctx->F = F;
+    if (F == 0) return RVL_OK;
+    int64_t rows = (256ll << 20) / n;
+    if (rows < 1) rows = 1;
+    if (rows > F) rows = F;
+    uint8_t *stage = nullptr;
+    CK(dalloc(&stage, (size_t)rows * n));
+    for (int64_t f0 = 0; f0 < F; f0 += rows) {
+        int64_t fc = (F - f0 < rows) ? (F - f0) : rows;
+        cudaError_t e = cudaMemcpyAsync(stage, m2 + (size_t)f0 * n, (size_t)fc * n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(stage); return fail(ctx, RVL_ERR_CUDA, "H2D: %s", cudaGetErrorString(e)); }
+        rvl_launch_pack_u8_rowmajor(stage, f0, fc, (int)n, ctx->words, ctx->d_bits, ctx->d_flag, ctx->stream);
+        ctx->launches++;
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "pack: %s", cudaGetErrorString(e));
+    rc = check_flag(ctx, "feature matrix has an entry that is not 0 or 1 (binary features only; no fallback)");
+    if (rc) free_matrix(ctx);
+    return rc;
+}
+
+static int load_bits_common(rvl_ctx *ctx, const void *src, bool src_device, int64_t F, int64_t n, int64_t words)
+{
+    if (!src && F > 0) return fail(ctx, RVL_ERR_ARG, "bits is NULL");
+    int rc = begin_matrix(ctx, F, n);
+    if (rc) return rc;
+    if (words < (n + 63) / 64) return fail(ctx, RVL_ERR_ARG, "words < ceil(n/64)");
+    CK(dalloc(&ctx->d_bits, (size_t)F * ctx->words));
+    CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    ctx->F = F;
+    if (F == 0) return RVL_OK;
+    cudaMemcpyKind kind = src_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    int64_t cw = words < ctx->words ? words : ctx->words;
+    if (cw < ctx->words) CK(cudaMemsetAsync(ctx->d_bits, 0, sizeof(uint64_t) * (size_t)F * ctx->words, ctx->stream));
+    CK(cudaMemcpy2DAsync(ctx->d_bits, sizeof(uint64_t) * ctx->words, src, sizeof(uint64_t) * words,
+                         sizeof(uint64_t) * cw, (size_t)F, kind, ctx->stream));
+    rvl_launch_check_padding(ctx->d_bits, F, (int)n, ctx->words, ctx->d_flag, ctx->stream);
+    ctx->launches++;
+    rc = check_flag(ctx, "bit-packed matrix has non-zero padding bits beyond sample n");
+    if (rc) free_matrix(ctx);
+    return rc;
+}
+
+extern "C" int rvl_load_matrix_bits(rvl_ctx *ctx, const uint64_t *bits, int64_t F, int64_t n, int64_t words)
+{
+    GUARD();
+    return load_bits_common(ctx, bits, false, F, n, words);
+}
+
+extern "C" int rvl_load_matrix_bits_device(rvl_ctx *ctx, const void *dev_bits, int64_t F, int64_t n, int64_t words)
+{
+    GUARD();
+    return load_bits_common(ctx, dev_bits, true, F, n, words);
+}
+
+// ---- targets and seeds -----------------------------------------------------------------------
+
+extern "C" int rvl_set_targets(rvl_ctx *ctx, const double *targets, int64_t n, int64_t n_targets)
+{
+    GUARD();
+    if (!targets || n < 2 || n_targets < 1 || n_targets > 65535) return fail(ctx, RVL_ERR_ARG, "bad targets (n=%lld, n_targets=%lld; need n >= 2, 1 <= n_targets <= 65535)", (long long)n, (long long)n_targets);
+    if (ctx->F >= 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "targets have n=%lld but matrix has n=%d", (long long)n, ctx->n);
+    free_targets(ctx);
+    if (ctx->F < 0) { ctx->n = (int)n; ctx->words = (int)(((n + 63) / 64 + 1) & ~1ll); }
+    int T = (int)n_targets;
+    CK(dalloc(&ctx->d_x, (size_t)T * n));
+    CK(dalloc(&ctx->d_u, (size_t)T * n));
+    CK(dalloc(&ctx->d_xc, (size_t)T * n));
+    CK(dalloc(&ctx->d_bin, (size_t)T * n));
+    CK(dalloc(&ctx->d_cnt, (size_t)T * 1000));
+    CK(dalloc(&ctx->d_bcvtab, (size_t)n + 1));
+    CK(dalloc(&ctx->d_tg, (size_t)T));
+    CK(dalloc(&ctx->d_seed0, (size_t)T * ctx->words));
+    CK(dalloc(&ctx->d_seed, (size_t)T * ctx->words));
+    CK(cudaMemsetAsync(ctx->d_tg, 0, sizeof(RvlTarget) * T, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_x, targets, sizeof(double) * (size_t)T * n, cudaMemcpyHostToDevice, ctx->stream));
+    rvl_launch_bcv_binary_table((int)n, ctx->d_bcvtab, ctx->stream);
+    rvl_launch_target_setup(ctx->d_x, (int)n, T, ctx->opts.n_grid, ctx->d_tg, ctx->d_u, ctx->d_xc, ctx->d_bin,
+                            ctx->d_cnt, ctx->d_flag, ctx->stream);
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    ctx->T = T;
+    ctx->G_targets = ctx->opts.n_grid;
+    ctx->first_null = 0;
+    ctx->have_seed = false;
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h) { free_targets(ctx); return fail(ctx, RVL_ERR_NONFINITE, "target has NA/NaN/Inf values"); }
+    // seed_of defaults to self
+    std::vector<RvlTarget> tg(T);
+    CK(cudaMemcpy(tg.data(), ctx->d_tg, sizeof(RvlTarget) * T, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < T; t++) tg[t].seed_of = t;
+    CK(cudaMemcpy(ctx->d_tg, tg.data(), sizeof(RvlTarget) * T, cudaMemcpyHostToDevice));
+    return RVL_OK;
+}
+
+extern "C" int rvl_set_null_targets(rvl_ctx *ctx, int64_t first_null)
+{
+    GUARD();
+    if (ctx->T <= 0) return fail(ctx, RVL_ERR_STATE, "set targets first");
+    if (first_null >= ctx->T) return fail(ctx, RVL_ERR_ARG, "first_null >= n_targets");
+    int fn = first_null > 0 ? (int)first_null : 0;
+    if (fn > 1) return fail(ctx, RVL_ERR_ARG, "null targets are scored against target 0's seed: first_null must be 1 (or <= 0 to disable)");
+    std::vector<RvlTarget> tg(ctx->T);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(tg.data(), ctx->d_tg, sizeof(RvlTarget) * ctx->T, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < ctx->T; t++) tg[t].seed_of = (fn > 0 && t >= fn) ? 0 : t;
+    CK(cudaMemcpy(ctx->d_tg, tg.data(), sizeof(RvlTarget) * ctx->T, cudaMemcpyHostToDevice));
+    ctx->first_null = fn;
+    return RVL_OK;
+}
+
+extern "C" int rvl_set_seed(rvl_ctx *ctx, const uint8_t *seed, int64_t n, int per_target)
+{
+    GUARD();
+    if (ctx->T <= 0) return fail(ctx, RVL_ERR_STATE, "set targets before the seed");
+    if (!seed || n != ctx->n) return fail(ctx, RVL_ERR_ARG, "seed length %lld != n %d", (long long)n, ctx->n);
+    int T = ctx->T, words = ctx->words;
+    std::vector<uint64_t> packed((size_t)T * words, 0ull);
+    for (int t = 0; t < T; t++) {
+        const uint8_t *s = per_target ? seed + (size_t)t * n : seed;
+        for (int64_t i = 0; i < n; i++) {
+            if (s[i] == 1) packed[(size_t)t * words + (i >> 6)] |= (1ull << (i & 63));
+            else if (s[i] != 0) return fail(ctx, RVL_ERR_NOT_BINARY, "seed entry %lld is not 0 or 1", (long long)i);
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->d_seed0, packed.data(), sizeof(uint64_t) * packed.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_seed = true;
+    return RVL_OK;
+}
+
+// ---- search ------------------------------------------------------------------------------------
+
+static int ready(rvl_ctx *ctx)
+{
+    if (ctx->F < 0) return fail(ctx, RVL_ERR_STATE, "feature matrix not loaded");
+    if (ctx->T <= 0) return fail(ctx, RVL_ERR_STATE, "targets not set");
+    if (!ctx->have_seed) return fail(ctx, RVL_ERR_STATE, "seed not set");
+    if (ctx->opts.n_grid != ctx->G_targets) return fail(ctx, RVL_ERR_STATE, "n_grid changed after rvl_set_targets");
+    return RVL_OK;
+}
+
+extern "C" size_t rvl_candidate_bytes(const rvl_ctx *ctx)
+{
+    if (!ctx || ctx->T <= 0) return 0;
+    return (size_t)ctx->T * (sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words);
+}
+
+extern "C" int rvl_set_exchange_buffers(rvl_ctx *ctx, void *dev_send, void *dev_recv)
+{
+    GUARD();
+    ctx->d_send = (unsigned char *)dev_send;
+    ctx->d_recv = (unsigned char *)dev_recv;
+    return RVL_OK;
+}
+
+static int ensure_results(rvl_ctx *ctx, int iters)
+{
+    int T = ctx->T;
+    size_t need = (size_t)T * iters * (size_t)(ctx->F > 0 ? ctx->F : 1);
+    if (need > ctx->scores_cap) {
+        dfree(ctx->d_scores);
+        CK(dalloc(&ctx->d_scores, need));
+        ctx->scores_cap = need;
+    }
+    if (T > ctx->res_cap_T || iters > ctx->res_cap_iters || ctx->words > ctx->res_cap_words) {
+        dfree(ctx->d_top); dfree(ctx->d_top_score); dfree(ctx->d_cmi_seed); dfree(ctx->d_ic0); dfree(ctx->d_seed_iter);
+        CK(dalloc(&ctx->d_top, (size_t)T * iters));
+        CK(dalloc(&ctx->d_top_score, (size_t)T * iters));
+        CK(dalloc(&ctx->d_cmi_seed, (size_t)T * iters));
+        CK(dalloc(&ctx->d_ic0, (size_t)T));
+        CK(dalloc(&ctx->d_seed_iter, (size_t)T * iters * ctx->words));
+        ctx->res_cap_T = T; ctx->res_cap_iters = iters; ctx->res_cap_words = ctx->words;
+    }
+    return RVL_OK;
+}
+
+// Device score layout is [iters][T][F]; `base` is one iteration's [T][F] slot.
+static int launch_score(rvl_ctx *ctx, double *base)
+{
+    RvlParams P = make_params(ctx);
+    size_t smem = rvl_score_smem_bytes(ctx->n, ctx->words);
+    if (smem > 227 * 1024) return fail(ctx, RVL_ERR_ARG, "n=%d needs %zu B of shared memory per block (> 227 KB)", ctx->n, smem);
+    CK(rvl_score_configure(smem));
+    if (ctx->F == 0) return RVL_OK;
+    int64_t per_block = 8 * 4; // RVL_SCORE_WARPS warps x 4 rows each: the hardware block scheduler balances the tail
+    int64_t gx = (ctx->F + per_block - 1) / per_block;
+    if (gx > 65535 * 16) gx = 65535 * 16;
+    if (ctx->score_events_used == ctx->score_events.size()) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        ctx->score_events.push_back({a, b});
+    }
+    auto &ev = ctx->score_events[ctx->score_events_used++];
+    CK(cudaEventRecord(ev.first, ctx->stream));
+    rvl_launch_score(&P, (int)gx, smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab,
+                     base, ctx->stream);
+    CK(cudaEventRecord(ev.second, ctx->stream));
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return RVL_OK;
+}
+
+static int drain_score_events(rvl_ctx *ctx)
+{
+    for (size_t i = 0; i < ctx->score_events_used; i++) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, ctx->score_events[i].first, ctx->score_events[i].second);
+        if (e == cudaSuccess) { ctx->score_ms += ms; ctx->score_launches++; }
+    }
+    ctx->score_events_used = 0;
+    return RVL_OK;
+}
+
+extern "C" int rvl_search_begin(rvl_ctx *ctx, int iters)
+{
+    GUARD();
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (iters < 1) return fail(ctx, RVL_ERR_ARG, "iters < 1");
+    rc = ensure_results(ctx, iters);
+    if (rc) return rc;
+    ctx->iters = iters;
+    size_t cb = rvl_candidate_bytes(ctx);
+    if (ctx->world == 1 && (!ctx->d_send || !ctx->d_recv)) {
+        if (ctx->own_xchg_bytes < cb) {
+            dfree(ctx->d_own_xchg);
+            CK(dalloc(&ctx->d_own_xchg, cb));
+            ctx->own_xchg_bytes = cb;
+        }
+        ctx->d_send = ctx->d_recv = ctx->d_own_xchg; // world of one: the record is its own gather
+    }
+    if (!ctx->d_send || !ctx->d_recv) return fail(ctx, RVL_ERR_STATE, "world > 1 needs rvl_set_exchange_buffers");
+    RvlParams P = make_params(ctx);
+    CK(cudaMemcpyAsync(ctx->d_seed, ctx->d_seed0, sizeof(uint64_t) * (size_t)ctx->T * ctx->words, cudaMemcpyDeviceToDevice, ctx->stream));
+    rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->stream);
+    // cmi.seed.iter0 <- assoc(target, seed)  LIB:1833
+    rvl_launch_assoc(&P, ctx->T, ctx->d_tg, nullptr, ctx->d_u, ctx->d_xc, ctx->d_seed, ctx->d_bcvtab, ctx->d_ic0, ctx->stream);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return RVL_OK;
+}
+
+extern "C" int rvl_iter_score(rvl_ctx *ctx, int iter)
+{
+    GUARD();
+    if (iter < 0 || iter >= ctx->iters) return fail(ctx, RVL_ERR_ARG, "iter out of range");
+    int rc = launch_score(ctx, ctx->d_scores + (size_t)iter * ctx->T * ctx->F);
+    if (rc) return rc;
+    RvlParams P2 = make_params(ctx);
+    rvl_launch_argmax(&P2, ctx->d_scores + (size_t)iter * ctx->T * ctx->F, ctx->d_bits, ctx->d_send,
+                      sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return RVL_OK;
+}
+
+extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
+{
+    GUARD();
+    if (iter < 0 || iter >= ctx->iters) return fail(ctx, RVL_ERR_ARG, "iter out of range");
+    RvlParams P = make_params(ctx);
+    rvl_launch_merge(&P, iter, ctx->iters, ctx->first_null, ctx->d_recv,
+                     sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, ctx->d_tg, ctx->d_seed, ctx->d_u,
+                     ctx->d_xc, ctx->d_bcvtab, ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, ctx->d_cmi_seed,
+                     ctx->stream);
+    rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->stream);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return RVL_OK;
+}
+
+extern "C" int rvl_synchronize(rvl_ctx *ctx)
+{
+    GUARD();
+    CK(cudaStreamSynchronize(ctx->stream));
+    drain_score_events(ctx);
+    return RVL_OK;
+}
+
+extern "C" int rvl_search_fetch(rvl_ctx *ctx, rvl_result *out)
+{
+    GUARD();
+    if (!out) return fail(ctx, RVL_ERR_ARG, "result is NULL");
+    int T = ctx->T, iters = ctx->iters, words = ctx->words, n = ctx->n;
+    if (iters < 1) return fail(ctx, RVL_ERR_STATE, "no search has run");
+    CK(cudaStreamSynchronize(ctx->stream));
+    drain_score_events(ctx);
+    if (out->cmi && ctx->F > 0) {
+        // device layout [iters][T][F] -> caller layout [T][iters][F]
+        for (int t = 0; t < T; t++)
+            CK(cudaMemcpy2DAsync(out->cmi + (size_t)t * iters * ctx->F, sizeof(double) * (size_t)ctx->F,
+                                 ctx->d_scores + (size_t)t * ctx->F, sizeof(double) * (size_t)T * ctx->F,
+                                 sizeof(double) * (size_t)ctx->F, (size_t)iters, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (out->top) CK(cudaMemcpyAsync(out->top, ctx->d_top, sizeof(int64_t) * (size_t)T * iters, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->top_score) CK(cudaMemcpyAsync(out->top_score, ctx->d_top_score, sizeof(double) * (size_t)T * iters, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->cmi_seed) CK(cudaMemcpyAsync(out->cmi_seed, ctx->d_cmi_seed, sizeof(double) * (size_t)T * iters, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->ic_seed0) CK(cudaMemcpyAsync(out->ic_seed0, ctx->d_ic0, sizeof(double) * (size_t)T, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint64_t> sb;
+    if (out->seed_iter) {
+        sb.resize((size_t)T * iters * words);
+        CK(cudaMemcpyAsync(sb.data(), ctx->d_seed_iter, sizeof(uint64_t) * sb.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (out->seed_iter) {
+        for (size_t r = 0; r < (size_t)T * iters; r++)
+            for (int s = 0; s < n; s++) out->seed_iter[r * n + s] = (uint8_t)((sb[r * words + (s >> 6)] >> (s & 63)) & 1ull);
+    }
+    return RVL_OK;
+}
+
+extern "C" int rvl_search(rvl_ctx *ctx, int iters, rvl_result *out)
+{
+    GUARD();
+    if (ctx->world != 1) return fail(ctx, RVL_ERR_STATE, "rvl_search is the single-shard driver; use the split-phase calls when world > 1");
+    int rc = rvl_search_begin(ctx, iters);
+    if (rc) return rc;
+    for (int it = 0; it < iters; it++) { // enqueued back to back: no host round-trip inside the loop
+        rc = rvl_iter_score(ctx, it);
+        if (rc) return rc;
+        rc = rvl_iter_merge(ctx, it);
+        if (rc) return rc;
+    }
+    if (out) return rvl_search_fetch(ctx, out);
+    return rvl_synchronize(ctx);
+}
+
+extern "C" int rvl_score_once(rvl_ctx *ctx, double *out_scores)
+{
+    GUARD();
+    int rc = ready(ctx);
+    if (rc) return rc;
+    rc = ensure_results(ctx, 1);
+    if (rc) return rc;
+    RvlParams P = make_params(ctx);
+    CK(cudaMemcpyAsync(ctx->d_seed, ctx->d_seed0, sizeof(uint64_t) * (size_t)ctx->T * ctx->words, cudaMemcpyDeviceToDevice, ctx->stream));
+    rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->stream);
+    ctx->launches++;
+    rc = launch_score(ctx, ctx->d_scores);
+    if (rc) return rc;
+    if (out_scores && ctx->F > 0)
+        CK(cudaMemcpyAsync(out_scores, ctx->d_scores, sizeof(double) * (size_t)ctx->T * ctx->F, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    drain_score_events(ctx);
+    return RVL_OK;
+}
+
+extern "C" int rvl_assoc(rvl_ctx *ctx, int64_t target_index, const uint8_t *y, int64_t n, double *out_ic)
+{
+    GUARD();
+    if (ctx->T <= 0) return fail(ctx, RVL_ERR_STATE, "targets not set");
+    if (!y || !out_ic || n != ctx->n || target_index < 0 || target_index >= ctx->T) return fail(ctx, RVL_ERR_ARG, "bad rvl_assoc arguments");
+    std::vector<uint64_t> packed(ctx->words, 0ull);
+    for (int64_t i = 0; i < n; i++) {
+        if (y[i] == 1) packed[i >> 6] |= (1ull << (i & 63));
+        else if (y[i] != 0) return fail(ctx, RVL_ERR_NOT_BINARY, "y entry %lld is not 0 or 1", (long long)i);
+    }
+    uint64_t *d_y = nullptr;
+    double *d_o = nullptr;
+    int *d_t = nullptr;
+    CK(dalloc(&d_y, (size_t)ctx->words));
+    CK(dalloc(&d_o, 1));
+    CK(dalloc(&d_t, 1));
+    int ti = (int)target_index;
+    RvlParams P = make_params(ctx);
+    cudaMemcpyAsync(d_y, packed.data(), sizeof(uint64_t) * ctx->words, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_t, &ti, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    rvl_launch_assoc(&P, 1, ctx->d_tg, d_t, ctx->d_u, ctx->d_xc, d_y, ctx->d_bcvtab, d_o, ctx->stream);
+    ctx->launches++;
+    cudaMemcpyAsync(out_ic, d_o, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_y); cudaFree(d_o); cudaFree(d_t);
+    if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "rvl_assoc: %s", cudaGetErrorString(e));
+    return RVL_OK;
+}
+
+struct rvl_not_nan {
+    __host__ __device__ bool operator()(double v) const { return v == v; }
+};
+
+extern "C" int rvl_pvalues(rvl_ctx *ctx, const double *cmi, int64_t F, const double *cmi_rand, int64_t n_rand, double *out_pval)
+{
+    GUARD();
+    if (!cmi || !cmi_rand || !out_pval || F < 1 || n_rand < 1) return fail(ctx, RVL_ERR_ARG, "bad rvl_pvalues arguments");
+    double *d_c = nullptr, *d_r = nullptr, *d_p = nullptr;
+    CK(dalloc(&d_c, (size_t)F));
+    CK(dalloc(&d_r, (size_t)n_rand));
+    CK(dalloc(&d_p, (size_t)F));
+    cudaMemcpyAsync(d_c, cmi, sizeof(double) * F, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_r, cmi_rand, sizeof(double) * n_rand, cudaMemcpyHostToDevice, ctx->stream);
+    int64_t n_valid = 0;
+    try {
+        auto pol = thrust::cuda::par.on(ctx->stream);
+        thrust::device_ptr<double> r(d_r);
+        auto mid = thrust::partition(pol, r, r + n_rand, rvl_not_nan());
+        n_valid = mid - r;
+        thrust::sort(pol, r, r + n_valid);
+    } catch (...) {
+        cudaFree(d_c); cudaFree(d_r); cudaFree(d_p);
+        return fail(ctx, RVL_ERR_CUDA, "device sort failed");
+    }
+    rvl_launch_pvalues(d_c, F, d_r, n_valid, n_rand, d_p, ctx->stream);
+    ctx->launches += 3;
+    cudaMemcpyAsync(out_pval, d_p, sizeof(double) * F, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_c); cudaFree(d_r); cudaFree(d_p);
+    if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "rvl_pvalues: %s", cudaGetErrorString(e));
+    return RVL_OK;
+}
+
+// ---- introspection ------------------------------------------------------------------------------
+
+extern "C" int rvl_get_target_bandwidth(rvl_ctx *ctx, int64_t t, double *out)
+{
+    GUARD();
+    if (ctx->T <= 0) return fail(ctx, RVL_ERR_STATE, "targets not set");
+    if (!out || t < 0 || t >= ctx->T) return fail(ctx, RVL_ERR_ARG, "bad target index");
+    RvlTarget tg;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(&tg, ctx->d_tg + t, sizeof(RvlTarget), cudaMemcpyDeviceToHost));
+    *out = tg.bcv;
+    return RVL_OK;
+}
+
+extern "C" int rvl_get_binary_bandwidth_table(rvl_ctx *ctx, double *out)
+{
+    GUARD();
+    if (ctx->T <= 0) return fail(ctx, RVL_ERR_STATE, "targets not set");
+    if (!out) return fail(ctx, RVL_ERR_ARG, "out is NULL");
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, ctx->d_bcvtab, sizeof(double) * ((size_t)ctx->n + 1), cudaMemcpyDeviceToHost));
+    return RVL_OK;
+}
+
+extern "C" int rvl_get_row_counts(rvl_ctx *ctx, int32_t *out)
+{
+    GUARD();
+    if (ctx->F < 0) return fail(ctx, RVL_ERR_STATE, "feature matrix not loaded");
+    if (!out) return fail(ctx, RVL_ERR_ARG, "out is NULL");
+    if (ctx->F == 0) return RVL_OK;
+    int32_t *d = nullptr;
+    CK(dalloc(&d, (size_t)ctx->F));
+    rvl_launch_row_counts(ctx->d_bits, ctx->F, ctx->words, d, ctx->stream);
+    ctx->launches++;
+    cudaMemcpyAsync(out, d, sizeof(int32_t) * ctx->F, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "row counts: %s", cudaGetErrorString(e));
+    return RVL_OK;
+}
+
+extern "C" int64_t rvl_launch_count(const rvl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int rvl_score_kernel_time(rvl_ctx *ctx, double *out_ms, int64_t *out_launches, int reset)
+{
+    GUARD();
+    CK(cudaStreamSynchronize(ctx->stream));
+    drain_score_events(ctx);
+    if (out_ms) *out_ms = ctx->score_ms;
+    if (out_launches) *out_launches = ctx->score_launches;
+    if (reset) { ctx->score_ms = 0.0; ctx->score_launches = 0; }
+    return RVL_OK;
+}

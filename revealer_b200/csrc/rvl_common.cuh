@@ -1,0 +1,73 @@
+// rvl_common.cuh -- shared device-side structures of the REVEALER CMI-search core.
+//
+// Vocabulary follows the reference (REVEALER_library.v5C.R, "LIB", copy-B line numbers):
+//   target  x  : double[n]            (LIB:1626 `target`)
+//   feature y  : one bit-row of m.2   (LIB:1851 `m.2[k,]`)
+//   seed    z  : bit vector           (LIB:1691-1700 `seed`)
+//   n_grid  G  : KDE grid points per axis (25)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define RVL_MAXG 32
+
+// Per-target constants (computed once by rvl_set_targets) and per-iteration seed state.
+struct RvlTarget {
+    // --- constant per target
+    double mean;      // mean(x)
+    double sxx;       // sum((x-mean)^2)
+    double xmin, xmax;
+    double bcv;       // MASS::bcv(x)                        LIB:2524 / 2564 default args
+    int32_t is_const; // length(unique(x)) == 1              LIB:2495 / 2507
+    int32_t seed_of;  // index of the target whose seed this target is scored against
+                      // (itself, or 0 for permutation-null targets LIB:1853-1855)
+    // --- per iteration (written by k_seed_prep)
+    int32_t nz;       // popcount(seed)
+    int32_t mode;     // RVL_MODE_*
+    double bcv_z;     // bcv(seed) from the binary table
+};
+
+enum { RVL_MODE_ZERO = 0,  // constant target: every score is 0          LIB:2507
+       RVL_MODE_IC = 1,    // constant seed: mutual.inf.v2(x,y)$IC       LIB:2509-2511
+       RVL_MODE_CIC = 2 }; // cond.mutual.inf(x,y,z)$CIC                 LIB:2517
+
+// One candidate record per (rank, target) exchanged each iteration.
+// Layout in bytes: [score f64][global row i64][bits: words * u64]
+struct RvlCandHead {
+    double score;
+    int64_t row;
+};
+
+struct RvlParams {
+    int32_t n;        // samples
+    int32_t words;    // uint64 per bit row (row stride)
+    int32_t G;        // n_grid
+    int32_t negative; // target.match == "negative"
+    double bw_mult;   // 0.25
+    double bw_shrink; // -0.75
+    int64_t F;        // local rows
+    int64_t row_offset;
+    int32_t T;        // targets
+    int32_t world, rank;
+};
+
+#define RVL_DBL_EPS 2.220446049250313e-16
+
+__device__ __forceinline__ double rvl_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double rvl_warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int rvl_warp_sum_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

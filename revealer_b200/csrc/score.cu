@@ -1,0 +1,650 @@
+// score.cu -- the REVEALER scoring pass and the per-iteration tail, hand-written for sm_100a.
+//
+//   k_score      cmi[k] = cond.assoc(target, m.2[k,], seed, "IC") for every local row k and
+//                every target at once                                  (LIB:1849-1856)
+//   k_argmax     order(cmi, decreasing = !negative)[1] on the shard    (LIB:1858-1862)
+//   k_merge      global winner from `world` candidate records, seed <- max(seed, m.2[top,]),
+//                cmi.seed[iter] <- assoc(target, seed)                 (LIB:2167-2170)
+//   k_seed_prep  per-iteration seed state (popcount, dispatch of cond.assoc LIB:2507-2517)
+//
+// Algebra.  With y, z in {0,1}^n the 25^3 KDE cube of misc3d::kde3d is
+//   d[i,j,k] = kappa * sum_{a,b in {0,1}} A_ab[i] * gy_a[j] * gz_b[k],
+//   A_ab[i]  = sum_{s: y_s=a, z_s=b} exp(-beta (i - u_s)^2),  u_s = (x_s - xmin)/dx,
+//   beta     = dx^2 / (2 hx^2),  gy_a[j] = exp(-(j/(G-1) - a)^2 / (2 hy^2)),  gz_b likewise,
+//   kappa    = 1 / (n (2 pi)^{3/2} hx hy hz).
+// The reference then adds .Machine$double.eps, normalises and takes entropies (LIB:2581-2605);
+// in terms of Q = D + eps/kappa (D = d/kappa) and S = sum Q the cell-volume factors cancel:
+//   CMI = HXZ + HYZ - HXYZ - HZ = ( L(Q_ijk) - L(Q_ik) - L(Q_jk) + L(Q_k) ) / S,  L(.) = sum q log q,
+// with the marginals Q_ik, Q_jk, Q_k and S available in closed form from the rank-4 structure.
+// Columns (j,k) whose density cannot change fl(D + eps') (D < eps' * 2^-55 for every i) contribute
+// exactly G * eps' log eps' and are not visited.
+//
+// One warp owns one (target, feature) evaluation: no block barrier inside an evaluation, all
+// reductions are fixed-order warp shuffles, so identical rows give bit-identical scores whatever
+// their index, block or GPU -- which is what makes "lowest row index wins ties" reproducible.
+#include "rvl_common.cuh"
+#include <cfloat>
+#include <cmath>
+
+#define RVL_SCORE_WARPS 8
+#define RVL_TWO_PI 6.283185307179586476925286766559
+
+// ---- per-warp scratch in shared memory ----------------------------------------------------
+struct __align__(16) RvlWarpScratch {
+    double A[RVL_MAXG][4];     // A[i][a*2+b]
+    double gy[2][RVL_MAXG];    // gy[a][j]
+    double gz[2][RVL_MAXG];    // gz[b][k]
+    uint16_t live[RVL_MAXG * RVL_MAXG];
+};
+
+__device__ __forceinline__ double rvl_xlogx(double q) { return q * log(q); }
+
+// Accumulate the class-masked Gaussian sums for grid point `lane` over samples [s_begin, s_end)
+// with stride s_step.  yrow / zrow are bit rows (zrow may be NULL: single z class).
+__device__ __forceinline__ void rvl_accumulate_dense(const double *__restrict__ u, const uint64_t *__restrict__ yrow,
+                                                     const uint64_t *__restrict__ zrow, int s_begin, int s_end,
+                                                     int s_step, double gi, double beta, double acc[4])
+{
+    for (int s = s_begin; s < s_end; s += s_step) {
+        double t = gi - u[s];
+        double e = exp(-beta * t * t);
+        int yb = (int)((yrow[s >> 6] >> (s & 63)) & 1ull);
+        int zb = zrow ? (int)((zrow[s >> 6] >> (s & 63)) & 1ull) : 0;
+        if (yb) { if (zb) acc[3] += e; else acc[2] += e; }
+        else    { if (zb) acc[1] += e; else acc[0] += e; }
+    }
+}
+
+// 3-D epilogue: CMI from A (in scratch), axis kernels gy/gz, eps' = eps/kappa.  Whole warp.
+__device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    // per-class totals and maxima over the x grid
+    double sa[4], amax[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        double v = (lane < G) ? S.A[lane][c] : 0.0;
+        sa[c] = rvl_warp_sum(v);
+        amax[c] = rvl_warp_max(v);
+    }
+    double gyv = (lane < G) ? S.gy[0][lane] : 0.0;
+    double gzv = (lane < G) ? S.gz[0][lane] : 0.0;
+    double Gy = rvl_warp_sum(gyv); // = sum_j gy_1[j] as well (mirror image)
+    double Gz = rvl_warp_sum(gzv);
+
+    // live (j,k) columns
+    const double dead_thr = epsq * 0x1p-55;
+    int GG = G * G, nlive = 0;
+    for (int p0 = 0; p0 < GG; p0 += 32) {
+        int p = p0 + lane;
+        bool live = false;
+        if (p < GG) {
+            int j = p / G, k = p - j * G;
+            double dmax = amax[0] * S.gy[0][j] * S.gz[0][k] + amax[1] * S.gy[0][j] * S.gz[1][k] +
+                          amax[2] * S.gy[1][j] * S.gz[0][k] + amax[3] * S.gy[1][j] * S.gz[1][k];
+            live = dmax >= dead_thr;
+        }
+        unsigned m = __ballot_sync(FULL, live);
+        if (live) S.live[nlive + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
+        nlive += __popc(m);
+    }
+    __syncwarp();
+
+    // L3 = sum over all cells of Q log Q
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int idx = lane; idx < nlive; idx += 32) {
+        int p = S.live[idx];
+        int j = p / G, k = p - j * G;
+        double w00 = S.gy[0][j] * S.gz[0][k], w01 = S.gy[0][j] * S.gz[1][k];
+        double w10 = S.gy[1][j] * S.gz[0][k], w11 = S.gy[1][j] * S.gz[1][k];
+        int i = 0;
+        for (; i + 1 < G; i += 2) {
+            double q0 = fma(S.A[i][0], w00, fma(S.A[i][1], w01, fma(S.A[i][2], w10, fma(S.A[i][3], w11, epsq))));
+            double q1 = fma(S.A[i + 1][0], w00,
+                            fma(S.A[i + 1][1], w01, fma(S.A[i + 1][2], w10, fma(S.A[i + 1][3], w11, epsq))));
+            acc0 = fma(q0, log(q0), acc0);
+            acc1 = fma(q1, log(q1), acc1);
+        }
+        if (i < G) {
+            double q0 = fma(S.A[i][0], w00, fma(S.A[i][1], w01, fma(S.A[i][2], w10, fma(S.A[i][3], w11, epsq))));
+            acc0 = fma(q0, log(q0), acc0);
+        }
+    }
+    double L3 = rvl_warp_sum(acc0 + acc1) + (double)(GG - nlive) * (double)G * rvl_xlogx(epsq);
+
+    // marginals: Q_ik (XZ), Q_jk (YZ), Q_k (Z)
+    double accxz = 0.0, accyz = 0.0;
+    double gE = (double)G * epsq;
+    for (int p = lane; p < GG; p += 32) {
+        int a = p / G, k = p - a * G; // a is i for XZ, j for YZ
+        double qxz = fma((S.A[a][0] + S.A[a][2]) * Gy, S.gz[0][k], fma((S.A[a][1] + S.A[a][3]) * Gy, S.gz[1][k], gE));
+        double qyz = fma(sa[0] * S.gy[0][a], S.gz[0][k],
+                         fma(sa[1] * S.gy[0][a], S.gz[1][k],
+                             fma(sa[2] * S.gy[1][a], S.gz[0][k], fma(sa[3] * S.gy[1][a], S.gz[1][k], gE))));
+        accxz += rvl_xlogx(qxz);
+        accyz += rvl_xlogx(qyz);
+    }
+    double accz = 0.0;
+    if (lane < G) {
+        double qz = fma((sa[0] + sa[2]) * Gy, S.gz[0][lane], fma((sa[1] + sa[3]) * Gy, S.gz[1][lane], (double)GG * epsq));
+        accz = rvl_xlogx(qz);
+    }
+    double Lxz = rvl_warp_sum(accxz), Lyz = rvl_warp_sum(accyz), Lz = rvl_warp_sum(accz);
+    double Stot = (sa[0] + sa[1] + sa[2] + sa[3]) * Gy * Gz + (double)GG * (double)G * epsq;
+    return (L3 - Lxz - Lyz + Lz) / Stot;
+}
+
+// 2-D epilogue (mutual.inf.v2, LIB:2536-2550): MI from B_a[i] = A[i][a*2] and gy.  Whole warp.
+__device__ double rvl_mi_epilogue(RvlWarpScratch &S, int G, double epsq, int lane)
+{
+    double b0 = (lane < G) ? S.A[lane][0] : 0.0, b1 = (lane < G) ? S.A[lane][2] : 0.0;
+    double sb0 = rvl_warp_sum(b0), sb1 = rvl_warp_sum(b1);
+    double gyv = (lane < G) ? S.gy[0][lane] : 0.0;
+    double Gy = rvl_warp_sum(gyv);
+    int GG = G * G;
+    double gE = (double)G * epsq;
+    double acc = 0.0;
+    for (int p = lane; p < GG; p += 32) {
+        int i = p / G, j = p - i * G;
+        double q = fma(S.A[i][0], S.gy[0][j], fma(S.A[i][2], S.gy[1][j], epsq));
+        acc += rvl_xlogx(q);
+    }
+    double accx = 0.0, accy = 0.0;
+    if (lane < G) {
+        double qx = fma(b0 + b1, Gy, gE);
+        double qy = fma(sb0, S.gy[0][lane], fma(sb1, S.gy[1][lane], gE));
+        accx = rvl_xlogx(qx);
+        accy = rvl_xlogx(qy);
+    }
+    double L2 = rvl_warp_sum(acc), Lx = rvl_warp_sum(accx), Ly = rvl_warp_sum(accy);
+    double Stot = (sb0 + sb1) * Gy + (double)GG * epsq;
+    return (L2 - Lx - Ly) / Stot + log(Stot);
+}
+
+__device__ __forceinline__ double rvl_sign(double r) { return (double)((r > 0.0) - (r < 0.0)); }
+
+// Fill the axis kernel of a non-constant binary variable: g[0][j] = exp(-(j/(G-1))^2/(2h^2)),
+// g[1][j] = g[0][G-1-j].
+__device__ __forceinline__ void rvl_fill_axis(double g[2][RVL_MAXG], int G, double h, int lane)
+{
+    if (lane < G) {
+        double t = (double)lane / (double)(G - 1) / h;
+        double v = exp(-0.5 * t * t);
+        g[0][lane] = v;
+        g[1][G - 1 - lane] = v;
+    }
+}
+
+// Pearson correlation of x with a 0/1 vector having n1 ones, s1c = sum_{y=1}(x - mean).
+__device__ __forceinline__ double rvl_rho(double s1c, int n1, int n, double sxx)
+{
+    double r = s1c / sqrt(sxx * ((double)n1 * (double)(n - n1) / (double)n));
+    return fmin(1.0, fmax(-1.0, r));
+}
+
+// Finish one evaluation once A (dense sums) is in scratch.  Returns IC or CIC.
+// mode: RVL_MODE_IC (2-D) or RVL_MODE_CIC (3-D).  c is the bandwidth shrink factor already applied
+// to hx (beta); here it is applied to hy / hz.
+__device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, double rho, double c, double hx,
+                             double bcv_y, double bcv_z, int lane)
+{
+    int G = P.G;
+    double dn = (double)P.n;
+    if (mode == RVL_MODE_IC) {
+        double hy = bcv_y * c / 4; // kde2d: h <- h/4
+        rvl_fill_axis(S.gy, G, hy, lane);
+        __syncwarp();
+        double epsq = RVL_DBL_EPS * (RVL_TWO_PI * dn * hx * hy);
+        double mi = rvl_mi_epilogue(S, G, epsq, lane);
+        return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * mi));
+    }
+    double hy = P.bw_mult * bcv_y * c, hz = P.bw_mult * bcv_z * c;
+    rvl_fill_axis(S.gy, G, hy, lane);
+    rvl_fill_axis(S.gz, G, hz, lane);
+    __syncwarp();
+    double epsq = RVL_DBL_EPS * (dn * RVL_TWO_PI * sqrt(RVL_TWO_PI) * hx * hy * hz);
+    double cmi = rvl_cmi_epilogue(S, G, epsq, lane);
+    return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * cmi));
+}
+
+// ---- k_score --------------------------------------------------------------------------------
+// grid = (feature blocks, targets); block = RVL_SCORE_WARPS warps; each warp walks features
+// blockIdx.x*W + warp, += gridDim.x*W.  Dynamic smem: u[n] doubles, seed bit row, per-warp
+// scratch + bit row.
+__global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
+k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict__ u_all,
+        const double *__restrict__ xc_all, const RvlTarget *__restrict__ tg_all,
+        const uint64_t *__restrict__ seeds, const double *__restrict__ bcvtab, double *__restrict__ scores)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = P.n, words = P.words, G = P.G;
+    const int t = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    double *u = reinterpret_cast<double *>(smem_raw);
+    uint64_t *zrow = reinterpret_cast<uint64_t *>(u + n);
+    RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(zrow + words);
+    uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_SCORE_WARPS);
+    RvlWarpScratch &S = scr[warp];
+    uint64_t *yrow = yrows + (size_t)warp * words;
+
+    const RvlTarget tg = tg_all[t];
+    const double *xc = xc_all + (size_t)t * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) u[i] = u_all[(size_t)t * n + i];
+    for (int i = threadIdx.x; i < words; i += blockDim.x) zrow[i] = seeds[(size_t)tg.seed_of * words + i];
+    __syncthreads();
+
+    const int mode = tg.mode;
+    double *out = scores + (size_t)t * P.F;
+
+    for (int64_t f = (int64_t)blockIdx.x * RVL_SCORE_WARPS + warp; f < P.F; f += (int64_t)gridDim.x * RVL_SCORE_WARPS) {
+        // bit row -> smem, popcount, masked target sum
+        const uint64_t *row = bits + (size_t)f * words;
+        int n1 = 0;
+        double s1c = 0.0;
+        for (int w = lane; w < words; w += 32) {
+            uint64_t v = row[w];
+            yrow[w] = v;
+            n1 += __popcll(v);
+            while (v) {
+                int b = __ffsll((long long)v) - 1;
+                v &= v - 1;
+                s1c += xc[w * 64 + b];
+            }
+        }
+        n1 = rvl_warp_sum_i(n1);
+        s1c = rvl_warp_sum(s1c);
+        __syncwarp();
+        if (mode == RVL_MODE_ZERO || n1 == 0 || n1 == n) { // LIB:2507: constant x or y -> 0
+            if (lane == 0) out[f] = 0.0;
+            continue;
+        }
+        double rho = rvl_rho(s1c, n1, n, tg.sxx);
+        double c, hx;
+        if (mode == RVL_MODE_IC) { // LIB:2530-2532: abs(rho); kde2d divides h by 4
+            c = 1.0 + P.bw_shrink * fabs(rho);
+            hx = tg.bcv * c / 4;
+        } else {                   // LIB:2571-2573: positive part of rho
+            c = 1.0 + P.bw_shrink * (rho < 0.0 ? 0.0 : rho);
+            hx = P.bw_mult * tg.bcv * c;
+        }
+        double dx = (tg.xmax - tg.xmin) / (double)(G - 1);
+        double beta = 0.5 * (dx / hx) * (dx / hx);
+
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (lane < G)
+            rvl_accumulate_dense(u, yrow, mode == RVL_MODE_CIC ? zrow : nullptr, 0, n, 1, (double)lane, beta, acc);
+        if (lane < G) {
+            S.A[lane][0] = acc[0]; S.A[lane][1] = acc[1]; S.A[lane][2] = acc[2]; S.A[lane][3] = acc[3];
+        }
+        __syncwarp();
+        double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, lane);
+        if (lane == 0) out[f] = score;
+        __syncwarp();
+    }
+}
+
+// ---- seed state ------------------------------------------------------------------------------
+
+// One block per target: popcount(seed) and the cond.assoc dispatch (LIB:2507-2517).
+__device__ void rvl_seed_prep_block(const RvlParams &P, RvlTarget *tg_all, const uint64_t *seeds,
+                                    const double *bcvtab, int t, int *sh_i)
+{
+    RvlTarget &tg = tg_all[t];
+    const uint64_t *z = seeds + (size_t)tg.seed_of * P.words;
+    int c = 0;
+    for (int w = threadIdx.x; w < P.words; w += blockDim.x) c += __popcll(z[w]);
+    c = rvl_warp_sum_i(c);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh_i[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nz = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) nz += sh_i[i];
+        tg.nz = nz;
+        tg.bcv_z = bcvtab[nz];
+        tg.mode = tg.is_const ? RVL_MODE_ZERO : ((nz == 0 || nz == P.n) ? RVL_MODE_IC : RVL_MODE_CIC);
+    }
+    __syncthreads();
+}
+
+__global__ void k_seed_prep(RvlParams P, RvlTarget *tg_all, const uint64_t *seeds, const double *bcvtab)
+{
+    __shared__ int sh_i[32];
+    rvl_seed_prep_block(P, tg_all, seeds, bcvtab, blockIdx.x, sh_i);
+}
+
+// assoc(x_t, y, "IC") by one block (8 warps): warps split the samples, lanes own grid points.
+// LIB:2491-2501 -> mutual.inf.v2.  Result written by thread 0.
+struct RvlAssocShared {
+    RvlWarpScratch S;
+    double part[RVL_SCORE_WARPS][RVL_MAXG][2];
+    double red[32];
+    int redi[32];
+};
+
+__device__ double rvl_assoc_block(const RvlParams &P, const RvlTarget &tg, const double *__restrict__ u,
+                                  const double *__restrict__ xc, const uint64_t *__restrict__ y,
+                                  const double *__restrict__ bcvtab, RvlAssocShared &sh)
+{
+    const int n = P.n, G = P.G;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // popcount + masked sum, fixed order: words strided over threads, then block tree
+    int n1 = 0;
+    double s1c = 0.0;
+    for (int w = threadIdx.x; w < P.words; w += blockDim.x) {
+        uint64_t v = y[w];
+        n1 += __popcll(v);
+        while (v) {
+            int b = __ffsll((long long)v) - 1;
+            v &= v - 1;
+            s1c += xc[w * 64 + b];
+        }
+    }
+    n1 = rvl_warp_sum_i(n1);
+    s1c = rvl_warp_sum(s1c);
+    __syncthreads();
+    if (lane == 0) { sh.red[warp] = s1c; sh.redi[warp] = n1; }
+    __syncthreads();
+    n1 = 0; s1c = 0.0;
+    for (int i = 0; i < nwarps; i++) { n1 += sh.redi[i]; s1c += sh.red[i]; }
+    if (tg.is_const || n1 == 0 || n1 == n) return 0.0;
+
+    double rho = rvl_rho(s1c, n1, n, tg.sxx);
+    double c = 1.0 + P.bw_shrink * fabs(rho);
+    double hx = tg.bcv * c / 4;
+    double dx = (tg.xmax - tg.xmin) / (double)(G - 1);
+    double beta = 0.5 * (dx / hx) * (dx / hx);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (lane < G) rvl_accumulate_dense(u, y, nullptr, warp, n, nwarps, (double)lane, beta, acc);
+    if (lane < G) { sh.part[warp][lane][0] = acc[0]; sh.part[warp][lane][1] = acc[2]; }
+    __syncthreads();
+    double score = 0.0;
+    if (warp == 0) {
+        if (lane < G) {
+            double b0 = 0.0, b1 = 0.0;
+            for (int w = 0; w < nwarps; w++) { b0 += sh.part[w][lane][0]; b1 += sh.part[w][lane][1]; }
+            sh.S.A[lane][0] = b0; sh.S.A[lane][1] = 0.0; sh.S.A[lane][2] = b1; sh.S.A[lane][3] = 0.0;
+        }
+        __syncwarp();
+        score = rvl_finish(sh.S, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, lane);
+    }
+    return score; // valid in warp 0
+}
+
+// grid = number of (target, vector) pairs; y_all holds one bit row per pair.
+__global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
+k_assoc(RvlParams P, const RvlTarget *__restrict__ tg_all, const int *__restrict__ target_of,
+        const double *__restrict__ u_all, const double *__restrict__ xc_all, const uint64_t *__restrict__ y_all,
+        const double *__restrict__ bcvtab, double *__restrict__ out)
+{
+    __shared__ RvlAssocShared sh;
+    int q = blockIdx.x;
+    int t = target_of ? target_of[q] : q;
+    double v = rvl_assoc_block(P, tg_all[t], u_all + (size_t)t * P.n, xc_all + (size_t)t * P.n,
+                               y_all + (size_t)q * P.words, bcvtab, sh);
+    if (threadIdx.x == 0) out[q] = v;
+}
+
+// ---- rank: local best per target ---------------------------------------------------------------
+
+// "a is ahead of b" in R's stable order(decreasing = !negative): NaN last, ties by lower row.
+__device__ __forceinline__ bool rvl_ahead(double va, int64_t ia, double vb, int64_t ib, int negative)
+{
+    if (ib < 0) return ia >= 0;
+    if (ia < 0) return false;
+    bool na = isnan(va), nb = isnan(vb);
+    if (na || nb) {
+        if (na && nb) return ia < ib;
+        return nb;
+    }
+    if (va != vb) return negative ? (va < vb) : (va > vb);
+    return ia < ib;
+}
+
+// One block per target: scan the local scores, write the candidate record
+// [score][global row][bit row] into the send buffer.
+__global__ void k_argmax(RvlParams P, const double *__restrict__ scores, const uint64_t *__restrict__ bits,
+                         unsigned char *__restrict__ send, size_t rec_bytes)
+{
+    __shared__ double shv[32];
+    __shared__ long long shi[32];
+    int t = blockIdx.x;
+    const double *v = scores + (size_t)t * P.F;
+    double bv = 0.0;
+    int64_t bi = -1;
+    for (int64_t k = threadIdx.x; k < P.F; k += blockDim.x) {
+        double x = v[k];
+        if (rvl_ahead(x, k, bv, bi, P.negative)) { bv = x; bi = k; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, (long long)bi, o);
+        if (rvl_ahead(ov, oi, bv, bi, P.negative)) { bv = ov; bi = oi; }
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { shv[w] = bv; shi[w] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int nw = blockDim.x >> 5;
+        bv = (lane < nw) ? shv[lane] : 0.0;
+        bi = (lane < nw) ? shi[lane] : -1;
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            long long oi = __shfl_xor_sync(0xffffffffu, (long long)bi, o);
+            if (rvl_ahead(ov, oi, bv, bi, P.negative)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { shv[0] = bv; shi[0] = bi; }
+    }
+    __syncthreads();
+    bv = shv[0]; bi = shi[0];
+    unsigned char *rec = send + (size_t)t * rec_bytes;
+    RvlCandHead *h = reinterpret_cast<RvlCandHead *>(rec);
+    uint64_t *rb = reinterpret_cast<uint64_t *>(rec + sizeof(RvlCandHead));
+    if (threadIdx.x == 0) { h->score = bv; h->row = (bi < 0) ? -1 : (P.row_offset + bi); }
+    for (int i = threadIdx.x; i < P.words; i += blockDim.x) rb[i] = (bi < 0) ? 0ull : bits[(size_t)bi * P.words + i];
+}
+
+// ---- merge: global winner, seed OR-merge, seed IC, next-iteration seed state ---------------------
+// recv holds `world` blocks of T records.  One block per target.  Every rank runs the same
+// deterministic resolution, so the seeds stay replicated without a second exchange.
+__global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
+k_merge(RvlParams P, int iter, int iters, int first_null, const unsigned char *__restrict__ recv, size_t rec_bytes,
+        RvlTarget *tg_all, uint64_t *seeds, const double *__restrict__ u_all, const double *__restrict__ xc_all,
+        const double *__restrict__ bcvtab, int64_t *__restrict__ top, double *__restrict__ top_score,
+        uint64_t *__restrict__ seed_iter, double *__restrict__ cmi_seed)
+{
+    __shared__ RvlAssocShared sh;
+    __shared__ int sh_i[32];
+    __shared__ int win_rank;
+    int t = blockIdx.x;
+    bool is_null = (first_null > 0 && t >= first_null);
+    if (!is_null) {
+        if (threadIdx.x == 0) {
+            double bv = 0.0;
+            int64_t bi = -1;
+            int br = 0;
+            for (int r = 0; r < P.world; r++) {
+                const RvlCandHead *h =
+                    reinterpret_cast<const RvlCandHead *>(recv + ((size_t)r * P.T + t) * rec_bytes);
+                if (rvl_ahead(h->score, h->row, bv, bi, P.negative)) { bv = h->score; bi = h->row; br = r; }
+            }
+            win_rank = br;
+            top[(size_t)t * iters + iter] = bi;
+            top_score[(size_t)t * iters + iter] = bv;
+        }
+        __syncthreads();
+        const uint64_t *rb = reinterpret_cast<const uint64_t *>(recv + ((size_t)win_rank * P.T + t) * rec_bytes +
+                                                                sizeof(RvlCandHead));
+        uint64_t *z = seeds + (size_t)t * P.words;
+        uint64_t *zi = seed_iter + ((size_t)t * iters + iter) * P.words;
+        for (int i = threadIdx.x; i < P.words; i += blockDim.x) {
+            uint64_t v = z[i] | rb[i]; // apply(rbind(seed, m.2[top,]), 2, "max")  LIB:2168
+            z[i] = v;
+            zi[i] = v;
+        }
+        __syncthreads();
+        double ic = rvl_assoc_block(P, tg_all[t], u_all + (size_t)t * P.n, xc_all + (size_t)t * P.n, z, bcvtab, sh);
+        if (threadIdx.x == 0) cmi_seed[(size_t)t * iters + iter] = ic; // LIB:2170
+        __syncthreads();
+    }
+}
+
+// ---- bit packing ------------------------------------------------------------------------------
+
+// Column-major doubles (R matrix) -> bit rows, for columns [s0, s0 + ncols) where s0 % 64 == 0.
+// chunk[k + ld * (s - s0)].  One thread per (row, word).  Sets *flag on any entry not 0 or 1.
+__global__ void k_pack_f64_colmajor(const double *__restrict__ chunk, int64_t F, int64_t ld, int s0, int ncols,
+                                    int words, uint64_t *__restrict__ bits, int *__restrict__ flag)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int w = blockIdx.y; // word within the chunk
+    if (k >= F) return;
+    uint64_t v = 0;
+    int bad = 0;
+    int base = w * 64;
+    for (int b = 0; b < 64 && base + b < ncols; b++) {
+        double e = chunk[k + ld * (int64_t)(base + b)];
+        if (e == 1.0) v |= (1ull << b);
+        else if (!(e == 0.0)) bad = 1;
+    }
+    bits[(size_t)k * words + (s0 >> 6) + w] = v;
+    if (bad) atomicOr(flag, 1);
+}
+
+// Row-major bytes -> bit rows.  One warp per (row, 32 words) tile; lane = word.
+__global__ void k_pack_u8_rowmajor(const uint8_t *__restrict__ m, int64_t F, int n, int words,
+                                   uint64_t *__restrict__ bits, int *__restrict__ flag)
+{
+    int64_t k = blockIdx.x;
+    int bad = 0;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) {
+        uint64_t v = 0;
+        int base = w * 64;
+        for (int b = 0; b < 64 && base + b < n; b++) {
+            uint8_t e = m[(size_t)k * n + base + b];
+            if (e == 1) v |= (1ull << b);
+            else if (e != 0) bad = 1;
+        }
+        bits[(size_t)k * words + w] = v;
+    }
+    if (bad) atomicOr(flag, 1);
+}
+
+// Padding bits beyond n must be zero in caller-packed rows.
+__global__ void k_check_padding(const uint64_t *__restrict__ bits, int64_t F, int n, int words, int *__restrict__ flag)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F) return;
+    int full = n >> 6, rem = n & 63;
+    int bad = 0;
+    if (rem && (bits[(size_t)k * words + full] >> rem)) bad = 1;
+    for (int w = full + (rem ? 1 : 0); w < words; w++)
+        if (bits[(size_t)k * words + w]) bad = 1;
+    if (bad) atomicOr(flag, 1);
+}
+
+__global__ void k_row_counts(const uint64_t *__restrict__ bits, int64_t F, int words, int32_t *__restrict__ out)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F) return;
+    int c = 0;
+    for (int w = 0; w < words; w++) c += __popcll(bits[(size_t)k * words + w]);
+    out[k] = c;
+}
+
+// Permutation p-values (LIB:1869): pval[i] = #(rand > cmi[i]) / n_rand with `rand` sorted ascending
+// and NaNs removed: count = n_valid - upper_bound(rand, cmi[i]).
+__global__ void k_pvalues(const double *__restrict__ cmi, int64_t F, const double *__restrict__ rand_sorted,
+                          int64_t n_valid, int64_t n_rand, double *__restrict__ pval)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F) return;
+    double v = cmi[i];
+    if (isnan(v)) { pval[i] = 0.0; return; } // (NaN > x) is NA in R; sum() would be NA -- reported as 0 here
+    int64_t lo = 0, hi = n_valid;
+    while (lo < hi) { // first index with rand > v
+        int64_t mid = (lo + hi) >> 1;
+        if (rand_sorted[mid] > v) hi = mid; else lo = mid + 1;
+    }
+    pval[i] = (double)(n_valid - lo) / (double)n_rand;
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+
+extern "C" size_t rvl_score_smem_bytes(int n, int words)
+{
+    return sizeof(double) * (size_t)n + sizeof(uint64_t) * (size_t)words +
+           sizeof(RvlWarpScratch) * RVL_SCORE_WARPS + sizeof(uint64_t) * (size_t)words * RVL_SCORE_WARPS;
+}
+
+extern "C" cudaError_t rvl_score_configure(size_t smem)
+{
+    return cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits,
+                                 const double *u_all, const double *xc_all, const RvlTarget *tg,
+                                 const uint64_t *seeds, const double *bcvtab, double *scores, cudaStream_t st)
+{
+    dim3 grid(grid_x, P->T);
+    k_score<<<grid, RVL_SCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, scores);
+}
+
+extern "C" void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const uint64_t *seeds,
+                                     const double *bcvtab, cudaStream_t st)
+{
+    k_seed_prep<<<P->T, 128, 0, st>>>(*P, tg, seeds, bcvtab);
+}
+
+extern "C" void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of,
+                                 const double *u_all, const double *xc_all, const uint64_t *y_all,
+                                 const double *bcvtab, double *out, cudaStream_t st)
+{
+    k_assoc<<<npairs, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, target_of, u_all, xc_all, y_all, bcvtab, out);
+}
+
+extern "C" void rvl_launch_argmax(const RvlParams *P, const double *scores, const uint64_t *bits,
+                                  unsigned char *send, size_t rec_bytes, cudaStream_t st)
+{
+    k_argmax<<<P->T, 1024, 0, st>>>(*P, scores, bits, send, rec_bytes);
+}
+
+extern "C" void rvl_launch_merge(const RvlParams *P, int iter, int iters, int first_null,
+                                 const unsigned char *recv, size_t rec_bytes, RvlTarget *tg, uint64_t *seeds,
+                                 const double *u_all, const double *xc_all, const double *bcvtab, int64_t *top,
+                                 double *top_score, uint64_t *seed_iter, double *cmi_seed, cudaStream_t st)
+{
+    k_merge<<<P->T, RVL_SCORE_WARPS * 32, 0, st>>>(*P, iter, iters, first_null, recv, rec_bytes, tg, seeds, u_all,
+                                                   xc_all, bcvtab, top, top_score, seed_iter, cmi_seed);
+}
+
+extern "C" void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols,
+                                             int words, uint64_t *bits, int *flag, cudaStream_t st)
+{
+    dim3 grid((unsigned)((F + 255) / 256), (unsigned)((ncols + 63) / 64));
+    k_pack_f64_colmajor<<<grid, 256, 0, st>>>(chunk, F, ld, s0, ncols, words, bits, flag);
+}
+
+extern "C" void rvl_launch_pack_u8_rowmajor(const uint8_t *m, int64_t F0, int64_t Fc, int n, int words,
+                                            uint64_t *bits, int *flag, cudaStream_t st)
+{
+    k_pack_u8_rowmajor<<<(unsigned)Fc, 64, 0, st>>>(m, Fc, n, words, bits + (size_t)F0 * words, flag);
+}
+
+extern "C" void rvl_launch_check_padding(const uint64_t *bits, int64_t F, int n, int words, int *flag,
+                                         cudaStream_t st)
+{
+    k_check_padding<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(bits, F, n, words, flag);
+}
+
+extern "C" void rvl_launch_row_counts(const uint64_t *bits, int64_t F, int words, int32_t *out, cudaStream_t st)
+{
+    k_row_counts<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(bits, F, words, out);
+}
+
+extern "C" void rvl_launch_pvalues(const double *cmi, int64_t F, const double *rand_sorted, int64_t n_valid,
+                                   int64_t n_rand, double *pval, cudaStream_t st)
+{
+    k_pvalues<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(cmi, F, rand_sorted, n_valid, n_rand, pval);
+}

@@ -1,0 +1,188 @@
+"""CPU tests of the oracle (oracle/revealer_oracle.c) -- PARITY UNPINNED against real R (no R, MASS or
+misc3d in this environment; the reference ships no numeric fixtures).  What pins it instead:
+  * an independent numpy/scipy restatement must agree to <= 1e-10 (tests/np_restatement.py);
+  * scipy.optimize.fminbound (same FMM routine as R's optimize) must reproduce the Brent search;
+  * structural identities of the published algorithms (permutation invariance of bcv, closed-form pair
+    histogram of binary vectors, 3-D marginal == 2-D MI);
+  * the reference's own guard semantics (LIB:2495, 2507-2511) and R's order() tie/NaN rules;
+  * regression fixtures in tests/golden/oracle_golden.json (oracle-generated, see tools/make_golden.py);
+  * R-generated fixtures (tools/make_golden.R) when someone with R drops them in tests/golden/.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import np_restatement as NP
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _case(n, p=0.08, pz=0.15, seed=0):
+    rng = np.random.default_rng(seed)
+    x = np.sort(rng.standard_normal(n))[::-1].copy()
+    y = (rng.random(n) < p).astype(float)
+    z = (rng.random(n) < pz).astype(float)
+    y[:2] = 1
+    z[1:3] = 1
+    return x, y, z
+
+
+def test_var_cor_match_numpy(oracle):
+    x, y, _ = _case(157, seed=3)
+    assert abs(oracle.var(x) - np.var(x, ddof=1)) < 1e-14
+    assert abs(oracle.cor(x, y) - np.corrcoef(x, y)[0, 1]) < 1e-14
+
+
+@pytest.mark.parametrize("n,seed", [(50, 1), (82, 2), (200, 3), (333, 4)])
+def test_bcv_matches_scipy_fminbound(oracle, n, seed):
+    x, y, z = _case(n, seed=seed)
+    # scipy hard-codes sqrt_eps = sqrt(2.2e-16) where R uses sqrt(DBL_EPSILON): the minimum-step
+    # size tol1 differs by ~7e-11*|x|, so the two searches agree to ~1e-10, not to the last bit.
+    # A different iteration path would differ by ~tol = 1e-2*hmax.
+    for v in (x, y, z):
+        assert abs(oracle.bcv(v) - NP.bcv_scipy(v)) <= 1e-9 * abs(oracle.bcv(v))
+
+
+def test_bcv_permutation_invariant(oracle):
+    x, _, _ = _case(120, seed=5)
+    rng = np.random.default_rng(0)
+    assert oracle.bcv(x) == oracle.bcv(rng.permutation(x))
+
+
+def test_bcv_binary_depends_only_on_counts(oracle):
+    n = 90
+    rng = np.random.default_rng(1)
+    for n1 in (1, 3, 17, 45, 89):
+        y = np.zeros(n)
+        y[:n1] = 1
+        assert oracle.bcv(y) == oracle.bcv(rng.permutation(y))
+    # mirror image: n1 ones <-> n1 zeros give the same pair histogram and variance
+    y = np.zeros(n)
+    y[:7] = 1
+    assert abs(oracle.bcv(y) - oracle.bcv(1 - y)) < 1e-15
+
+
+@pytest.mark.parametrize("n,seed", [(60, 11), (150, 12), (300, 13)])
+def test_ic_matches_numpy_restatement(oracle, n, seed):
+    x, y, _ = _case(n, seed=seed)
+    delta = [oracle.bcv(x), oracle.bcv(y)]
+    a = oracle.mutual_inf_v2(x, y)
+    b = NP.mutual_inf_v2(x, y, delta)
+    assert abs(a["MI"] - b["MI"]) <= 1e-10 * abs(b["MI"]) + 1e-14
+    assert abs(a["IC"] - b["IC"]) <= 1e-10
+
+
+@pytest.mark.parametrize("n,seed", [(60, 21), (150, 22), (300, 23)])
+def test_cic_matches_numpy_restatement(oracle, n, seed):
+    x, y, z = _case(n, seed=seed)
+    delta = 0.25 * np.array([oracle.bcv(x), oracle.bcv(y), oracle.bcv(z)])
+    a = oracle.cond_mutual_inf(x, y, z)
+    b = NP.cond_mutual_inf(x, y, z, delta)
+    assert abs(a["CMI"] - b["CMI"]) <= 1e-10 * abs(b["CMI"]) + 1e-13
+    assert abs(a["CIC"] - b["CIC"]) <= 1e-9
+
+
+def test_3d_marginal_mi_equals_2d_mi_when_rho_positive(oracle):
+    # kde2d(h = bcv) divides by 4; kde3d gets 0.25*bcv: the XY marginal of the cube is the 2-D density.
+    for seed in range(30, 40):
+        x, y, z = _case(100, seed=seed)
+        if oracle.cor(x, y) > 0:
+            a = oracle.cond_mutual_inf(x, y, z)["MI"]
+            b = oracle.mutual_inf_v2(x, y)["MI"]
+            assert abs(a - b) <= 1e-9 * abs(b) + 1e-12
+
+
+def test_cond_assoc_guards(oracle):
+    x, y, z = _case(80, seed=41)
+    assert oracle.cond_assoc(x, np.zeros(80), z) == 0.0          # constant y   LIB:2507
+    assert oracle.cond_assoc(x, np.ones(80), z) == 0.0
+    assert oracle.cond_assoc(np.full(80, 2.5), y, z) == 0.0      # constant x
+    assert oracle.cond_assoc(x, y, np.zeros(80)) == oracle.assoc(x, y)   # constant z -> IC  LIB:2509
+    assert oracle.cond_assoc(x, y, np.ones(80)) == oracle.assoc(x, y)
+    assert oracle.assoc(x, np.zeros(80)) == 0.0                   # LIB:2495
+
+
+def test_scores_invariant_to_sample_order(oracle):
+    x, y, z = _case(70, seed=42)
+    p = np.random.default_rng(2).permutation(70)
+    a, b = oracle.cond_assoc(x, y, z), oracle.cond_assoc(x[p], y[p], z[p])
+    assert abs(a - b) <= 1e-10 * abs(a)
+
+
+def test_order_rules(oracle):
+    v = np.array([0.3, np.nan, 0.5, 0.5, -0.2, 0.5])
+    assert list(oracle.order(v)) == [2, 3, 5, 0, 4, 1]           # stable, NaN last
+    assert list(oracle.order(v, negative=True)) == [4, 0, 2, 3, 5, 1]
+    assert oracle.top1(v) == 2 and oracle.top1(v, negative=True) == 4
+    assert oracle.top1(np.array([np.nan, np.nan])) == 0
+
+
+def test_hoisted_mode_is_same_arithmetic(oracle):
+    x, y, z = _case(64, seed=43)
+    m = np.stack([y, 1 - y, np.roll(y, 5)])
+    a = oracle.score_rows(x, m, z, hoist=False, nthreads=1)
+    b = oracle.score_rows(x, m, z, hoist=True, nthreads=2)
+    assert np.array_equal(a, b)
+
+
+def test_search_loop_semantics(oracle):
+    # winner row is OR-ed into the seed and stays in the candidate set (LIB:2167-2168)
+    rng = np.random.default_rng(7)
+    n, F = 60, 40
+    x = np.sort(rng.standard_normal(n))[::-1].copy()
+    m = (rng.random((F, n)) < 0.1).astype(float)
+    m[5] = 0
+    m[5, :6] = 1
+    m[6] = m[5]                                                   # exact duplicate: lower index wins
+    seed = np.zeros(n)
+    seed[6:9] = 1
+    r = oracle.search(x, m, seed, 3)
+    s = seed.copy()
+    for it in range(3):
+        col = oracle.score_rows(x, m, s)
+        assert np.array_equal(col, r["cmi"][it])
+        top = oracle.top1(col)
+        assert top == r["top"][it]
+        s = np.maximum(s, m[top])
+        assert np.array_equal(s, r["seed_iter"][it])
+        assert r["cmi_seed"][it] == oracle.assoc(x, s)
+    assert r["top"][0] == 5
+
+
+def test_pvals(oracle):
+    cmi = np.array([0.5, 0.1, -0.2])
+    rand = np.array([[0.4, 0.6], [0.0, 0.2], [-0.3, 0.1]])
+    assert np.allclose(oracle.pvals(cmi, rand), [1 / 6, 3 / 6, 5 / 6])
+
+
+def test_oracle_regression_fixture(oracle):
+    path = os.path.join(HERE, "golden", "oracle_golden.json")
+    g = json.load(open(path))
+    assert g["provenance"].startswith("oracle-generated")
+    for c in g["cases"]:
+        x, y, z = (np.array(c[k]) for k in ("x", "y", "z"))
+        assert abs(oracle.bcv(x) - c["bcv_x"]) <= 1e-13 * c["bcv_x"]
+        assert abs(oracle.bcv(y) - c["bcv_y"]) <= 1e-13 * c["bcv_y"]
+        assert abs(oracle.assoc(x, y) - c["IC"]) <= 1e-11
+        assert abs(oracle.cond_assoc(x, y, z) - c["CIC"]) <= 1e-11
+    s = g["search"]
+    r = oracle.search(np.array(s["target"]), np.array(s["m2"], dtype=float), np.array(s["seed"], dtype=float),
+                      s["iters"])
+    assert list(r["top"]) == s["top"]
+    assert np.allclose(r["cmi_seed"], s["cmi_seed"], rtol=1e-11, atol=0)
+
+
+def test_r_golden_vectors_if_present(oracle):
+    """Real-R fixtures written by tools/make_golden.R; absent in this environment."""
+    path = os.path.join(HERE, "golden", "r_golden.json")
+    if not os.path.exists(path):
+        pytest.skip("no R-generated golden file (tests/golden/r_golden.json): parity with R stays unpinned")
+    g = json.load(open(path))
+    for c in g["cases"]:
+        x, y, z = (np.array(c[k], dtype=float) for k in ("x", "y", "z"))
+        assert abs(oracle.bcv(x) - c["bcv_x"]) <= 1e-9 * c["bcv_x"]
+        assert abs(oracle.bcv(y) - c["bcv_y"]) <= 1e-9 * c["bcv_y"]
+        assert abs(oracle.assoc(x, y) - c["IC"]) <= 1e-6 * abs(c["IC"]) + 1e-7
+        assert abs(oracle.cond_assoc(x, y, z) - c["CIC"]) <= 1e-6 * abs(c["CIC"]) + 1e-7
