@@ -161,6 +161,17 @@ int64_t rvl_launch_count(const rvl_ctx *ctx);
  * measured with CUDA events on the ctx stream; and the number of launches it covers. */
 int rvl_score_kernel_time(rvl_ctx *ctx, double *out_ms, int64_t *out_launches, int reset);
 
+/* Validation switch: on != 0 makes the score kernel recompute the x-axis kernel sums of every
+ * feature over all n samples (the literal form) instead of using the per-iteration
+ * bandwidth-interpolation table + minority-class visit.  Same results to ~1e-12; ~5x slower. */
+int rvl_set_dense_x(rvl_ctx *ctx, int on);
+/* Work counters of the score kernel since the last reset: out4[0] evaluations that ran the KDE path,
+ * out4[1] live (j,k) density columns (n_grid log() each), out4[2] dense-pass exp() evaluations. */
+int rvl_get_counters(rvl_ctx *ctx, uint64_t *out4, int reset);
+/* FP64 FMA peak of this device by a DFMA-chain micro-benchmark (TFLOP/s); the denominator of the
+ * roofline bench.py reports, since the path is FP64-compute-bound. */
+int rvl_measure_fp64_peak(rvl_ctx *ctx, double *out_tflops);
+
 #ifdef __cplusplus
 }
 #endif

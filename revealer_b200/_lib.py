@@ -64,6 +64,9 @@ SIGNATURES = {
     "rvl_get_row_counts": (_i, [_vp, _i32p]),
     "rvl_launch_count": (_i64, [_vp]),
     "rvl_score_kernel_time": (_i, [_vp, _dp, _i64p, _i]),
+    "rvl_set_dense_x": (_i, [_vp, _i]),
+    "rvl_get_counters": (_i, [_vp, _u64p, _i]),
+    "rvl_measure_fp64_peak": (_i, [_vp, _dp]),
 }
 
 _LIB = None

@@ -176,8 +176,8 @@ class RevealerContext:
 
     # -- hot path
     def score_once(self):
-        out = np.empty((self.T, self.F), dtype=np.float64)
-        self._ck(self._lib.rvl_score_once(self._h, _dp(out)))
+        out = np.empty((self.T or 0, self.F or 0), dtype=np.float64)
+        self._ck(self._lib.rvl_score_once(self._h, _dp(out)))  # call order errors come from the core
         return out
 
     def _alloc_result(self, iters, want_cmi=True):
@@ -267,6 +267,20 @@ class RevealerContext:
 
     def launch_count(self):
         return int(self._lib.rvl_launch_count(self._h))
+
+    def set_dense_x(self, on):
+        """Validation mode: literal per-feature x-axis sums over all samples (see rvl_set_dense_x)."""
+        self._ck(self._lib.rvl_set_dense_x(self._h, int(bool(on))))
+
+    def counters(self, reset=False):
+        out = (C.c_uint64 * 4)()
+        self._ck(self._lib.rvl_get_counters(self._h, out, int(reset)))
+        return dict(kde_evaluations=int(out[0]), live_columns=int(out[1]), dense_exps=int(out[2]))
+
+    def measure_fp64_peak(self):
+        out = C.c_double()
+        self._ck(self._lib.rvl_measure_fp64_peak(self._h, C.byref(out)))
+        return out.value
 
     def score_kernel_time(self, reset=False):
         ms, nl = C.c_double(), C.c_int64()

@@ -4,6 +4,7 @@
 #include "../../include/revealer_b200.h"
 #include "rvl_common.cuh"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -25,7 +26,10 @@ size_t rvl_score_smem_bytes(int n, int words);
 cudaError_t rvl_score_configure(size_t smem);
 void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits, const double *u_all,
                       const double *xc_all, const RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
-                      double *scores, cudaStream_t st);
+                      const double *tt, double *scores, unsigned long long *ctr, cudaStream_t st);
+void rvl_launch_ttable(const RvlParams *P, const RvlTarget *tg, const double *u_all, const uint64_t *seeds,
+                       double *tt, cudaStream_t st);
+void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaStream_t st);
 void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
                           cudaStream_t st);
 void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of, const double *u_all,
@@ -72,6 +76,11 @@ struct rvl_ctx {
     int *d_bin = nullptr, *d_cnt = nullptr, *d_flag = nullptr;
     RvlTarget *d_tg = nullptr;
 
+    // per-iteration x-axis table [T][nodes][2][RVL_MAXG] (score.cu, k_ttable)
+    double *d_tt = nullptr;
+    size_t tt_cap = 0;
+    int dense_x = 0;
+
     // seeds
     uint64_t *d_seed0 = nullptr; // initial seeds [T][words]
     uint64_t *d_seed = nullptr;  // working seeds  [T][words]
@@ -90,6 +99,7 @@ struct rvl_ctx {
     size_t own_xchg_bytes = 0;
 
     // instrumentation
+    unsigned long long *d_ctr = nullptr; // [0] KDE evaluations, [1] live (j,k) columns, [2] dense-pass exps
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_events;
@@ -140,6 +150,13 @@ static RvlParams make_params(const rvl_ctx *c)
     P.n = c->n; P.words = c->words; P.G = c->opts.n_grid; P.negative = c->opts.negative;
     P.bw_mult = c->opts.bandwidth_mult; P.bw_shrink = c->opts.bandwidth_shrink;
     P.F = c->F; P.row_offset = c->row_offset; P.T = c->T; P.world = c->world; P.rank = c->rank;
+    // tau = -2 ln c ranges over [0, -2 ln(1 + shrink)]; RVL_TT_PAD nodes beyond each end
+    double tau_max = -2.0 * log(1.0 + c->opts.bandwidth_shrink);
+    P.tt_dt = 1.0 / RVL_TT_INV_DT;
+    P.tt_pad = RVL_TT_PAD;
+    P.tt_nodes = (int)ceil(tau_max / P.tt_dt) + 2 * RVL_TT_PAD + 1;
+    if (P.tt_nodes < RVL_TT_STENCIL) P.tt_nodes = RVL_TT_STENCIL;
+    P.dense_x = c->dense_x;
     return P;
 }
 
@@ -165,6 +182,8 @@ extern "C" int rvl_create(rvl_ctx **out, int device)
     rvl_default_options(&ctx->opts);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->d_ctr, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_ctr, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
         return RVL_ERR_CUDA;
@@ -184,7 +203,8 @@ static void free_matrix(rvl_ctx *c)
 static void free_targets(rvl_ctx *c)
 {
     dfree(c->d_x); dfree(c->d_u); dfree(c->d_xc); dfree(c->d_bcvtab); dfree(c->d_bin); dfree(c->d_cnt);
-    dfree(c->d_tg); dfree(c->d_seed0); dfree(c->d_seed);
+    dfree(c->d_tg); dfree(c->d_seed0); dfree(c->d_seed); dfree(c->d_tt);
+    c->tt_cap = 0;
     c->T = 0; c->have_seed = false;
 }
 static void free_results(rvl_ctx *c)
@@ -202,6 +222,7 @@ extern "C" void rvl_destroy(rvl_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     free_matrix(ctx); free_targets(ctx); free_results(ctx);
     dfree(ctx->d_flag);
+    dfree(ctx->d_ctr);
     for (auto &p : ctx->score_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -444,6 +465,26 @@ extern "C" int rvl_set_seed(rvl_ctx *ctx, const uint8_t *seed, int64_t n, int pe
 
 // ---- search ------------------------------------------------------------------------------------
 
+// Per-iteration seed state + the x-axis table that depends on it.
+static int prep_iteration(rvl_ctx *ctx)
+{
+    RvlParams P = make_params(ctx);
+    size_t need = (size_t)ctx->T * P.tt_nodes * 2 * RVL_MAXG;
+    if (need > ctx->tt_cap) {
+        dfree(ctx->d_tt);
+        CK(dalloc(&ctx->d_tt, need));
+        ctx->tt_cap = need;
+    }
+    rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->stream);
+    ctx->launches++;
+    if (!ctx->dense_x) {
+        rvl_launch_ttable(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_tt, ctx->stream);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    return RVL_OK;
+}
+
 static int ready(rvl_ctx *ctx)
 {
     if (ctx->F < 0) return fail(ctx, RVL_ERR_STATE, "feature matrix not loaded");
@@ -508,7 +549,7 @@ static int launch_score(rvl_ctx *ctx, double *base)
     auto &ev = ctx->score_events[ctx->score_events_used++];
     CK(cudaEventRecord(ev.first, ctx->stream));
     rvl_launch_score(&P, (int)gx, smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab,
-                     base, ctx->stream);
+                     ctx->d_tt, base, ctx->d_ctr, ctx->stream);
     CK(cudaEventRecord(ev.second, ctx->stream));
     ctx->launches++;
     CK(cudaGetLastError());
@@ -547,10 +588,11 @@ extern "C" int rvl_search_begin(rvl_ctx *ctx, int iters)
     if (!ctx->d_send || !ctx->d_recv) return fail(ctx, RVL_ERR_STATE, "world > 1 needs rvl_set_exchange_buffers");
     RvlParams P = make_params(ctx);
     CK(cudaMemcpyAsync(ctx->d_seed, ctx->d_seed0, sizeof(uint64_t) * (size_t)ctx->T * ctx->words, cudaMemcpyDeviceToDevice, ctx->stream));
-    rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->stream);
+    rc = prep_iteration(ctx);
+    if (rc) return rc;
     // cmi.seed.iter0 <- assoc(target, seed)  LIB:1833
     rvl_launch_assoc(&P, ctx->T, ctx->d_tg, nullptr, ctx->d_u, ctx->d_xc, ctx->d_seed, ctx->d_bcvtab, ctx->d_ic0, ctx->stream);
-    ctx->launches += 2;
+    ctx->launches += 1;
     CK(cudaGetLastError());
     return RVL_OK;
 }
@@ -578,10 +620,9 @@ extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
                      sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, ctx->d_tg, ctx->d_seed, ctx->d_u,
                      ctx->d_xc, ctx->d_bcvtab, ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, ctx->d_cmi_seed,
                      ctx->stream);
-    rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->stream);
-    ctx->launches += 2;
+    ctx->launches += 1;
     CK(cudaGetLastError());
-    return RVL_OK;
+    return prep_iteration(ctx);
 }
 
 extern "C" int rvl_synchronize(rvl_ctx *ctx)
@@ -649,8 +690,8 @@ extern "C" int rvl_score_once(rvl_ctx *ctx, double *out_scores)
     if (rc) return rc;
     RvlParams P = make_params(ctx);
     CK(cudaMemcpyAsync(ctx->d_seed, ctx->d_seed0, sizeof(uint64_t) * (size_t)ctx->T * ctx->words, cudaMemcpyDeviceToDevice, ctx->stream));
-    rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->stream);
-    ctx->launches++;
+    rc = prep_iteration(ctx);
+    if (rc) return rc;
     rc = launch_score(ctx, ctx->d_scores);
     if (rc) return rc;
     if (out_scores && ctx->F > 0)
@@ -774,5 +815,50 @@ extern "C" int rvl_score_kernel_time(rvl_ctx *ctx, double *out_ms, int64_t *out_
     if (out_ms) *out_ms = ctx->score_ms;
     if (out_launches) *out_launches = ctx->score_launches;
     if (reset) { ctx->score_ms = 0.0; ctx->score_launches = 0; }
+    return RVL_OK;
+}
+
+extern "C" int rvl_get_counters(rvl_ctx *ctx, uint64_t *out4, int reset)
+{
+    GUARD();
+    if (!out4) return fail(ctx, RVL_ERR_ARG, "out is NULL");
+    CK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long h[4];
+    CK(cudaMemcpy(h, ctx->d_ctr, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; i++) out4[i] = (uint64_t)h[i];
+    if (reset) CK(cudaMemset(ctx->d_ctr, 0, sizeof h));
+    return RVL_OK;
+}
+
+extern "C" int rvl_measure_fp64_peak(rvl_ctx *ctx, double *out_tflops)
+{
+    GUARD();
+    if (!out_tflops) return fail(ctx, RVL_ERR_ARG, "out is NULL");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    double *d = nullptr;
+    CK(dalloc(&d, (size_t)blocks * threads));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        rvl_launch_fp64_peak(blocks, threads, iters, d, ctx->stream);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        double tf = 2.0 * 8.0 * (double)iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+        ctx->launches++;
+    }
+    cudaFree(d);
+    *out_tflops = best;
+    return RVL_OK;
+}
+
+extern "C" int rvl_set_dense_x(rvl_ctx *ctx, int on)
+{
+    GUARD();
+    ctx->dense_x = on ? 1 : 0;
     return RVL_OK;
 }

@@ -49,7 +49,15 @@ struct RvlParams {
     int64_t row_offset;
     int32_t T;        // targets
     int32_t world, rank;
+    // bandwidth-interpolation table (see score.cu, "x-axis sums"): nodes tau_m = (m - tt_pad) * tt_dt
+    int32_t tt_nodes, tt_pad;
+    double tt_dt;
+    int32_t dense_x;  // 1: recompute the x-axis sums per feature over all samples (validation mode)
 };
+
+#define RVL_TT_STENCIL 8   // Lagrange points
+#define RVL_TT_PAD 4       // nodes beyond each end of [0, tau_max]
+#define RVL_TT_INV_DT 128  // nodes per unit of tau = -2 ln c
 
 #define RVL_DBL_EPS 2.220446049250313e-16
 

@@ -56,7 +56,7 @@ __device__ __forceinline__ void rvl_accumulate_dense(const double *__restrict__ 
 }
 
 // 3-D epilogue: CMI from A (in scratch), axis kernels gy/gz, eps' = eps/kappa.  Whole warp.
-__device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int lane)
+__device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int lane, int *nlive_out)
 {
     const unsigned FULL = 0xffffffffu;
     // per-class totals and maxima over the x grid
@@ -89,6 +89,7 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int la
         nlive += __popc(m);
     }
     __syncwarp();
+    *nlive_out = nlive;
 
     // L3 = sum over all cells of Q log Q
     double acc0 = 0.0, acc1 = 0.0;
@@ -186,8 +187,9 @@ __device__ __forceinline__ double rvl_rho(double s1c, int n1, int n, double sxx)
 // mode: RVL_MODE_IC (2-D) or RVL_MODE_CIC (3-D).  c is the bandwidth shrink factor already applied
 // to hx (beta); here it is applied to hy / hz.
 __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, double rho, double c, double hx,
-                             double bcv_y, double bcv_z, int lane)
+                             double bcv_y, double bcv_z, int lane, int *nlive_out)
 {
+    *nlive_out = 0;
     int G = P.G;
     double dn = (double)P.n;
     if (mode == RVL_MODE_IC) {
@@ -203,8 +205,99 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
     rvl_fill_axis(S.gz, G, hz, lane);
     __syncwarp();
     double epsq = RVL_DBL_EPS * (dn * RVL_TWO_PI * sqrt(RVL_TWO_PI) * hx * hy * hz);
-    double cmi = rvl_cmi_epilogue(S, G, epsq, lane);
+    double cmi = rvl_cmi_epilogue(S, G, epsq, lane, nlive_out);
     return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * cmi));
+}
+
+// ---- x-axis sums: the bandwidth-interpolation table ---------------------------------------------
+// The x-axis bandwidth of a feature is hx = hx0 * c with c = 1 + shrink * rho^+ (LIB:2571-2573), so
+//   T_b(c)[i] = sum_{s: z_s = b} exp(-beta0 * t * (i - u_s)^2),   t = 1/c^2,
+// the per-z-class total over ALL samples, depends on the feature only through the scalar t.  As a
+// function of tau = ln t it is a sum of exp(-a_s e^tau): entire, and 8-point Lagrange interpolation
+// on nodes spaced 1/128 in tau reproduces it to ~1e-16 of the class size (checked in
+// tests/test_ttable_interp.py against direct summation).  The table is rebuilt once per
+// (target, iteration) by k_ttable -- M * n * G exps, the cost of ~M dense passes instead of one per
+// feature -- and k_score only visits the minority y-class of each row bit by bit.
+// Node tt_pad is tau = 0 exactly (c = 1: every feature with rho <= 0), so those use it unweighted.
+// Layout: tt[target][node][b][RVL_MAXG].
+
+__global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
+k_ttable(RvlParams P, const RvlTarget *__restrict__ tg_all, const double *__restrict__ u_all,
+         const uint64_t *__restrict__ seeds, double *__restrict__ tt)
+{
+    __shared__ double part[RVL_SCORE_WARPS][2][RVL_MAXG];
+    const int t = blockIdx.y, m = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const RvlTarget tg = tg_all[t];
+    double *out = tt + (((size_t)t * P.tt_nodes + m) * 2) * RVL_MAXG;
+    if (tg.mode == RVL_MODE_ZERO) {
+        if (threadIdx.x < 2 * RVL_MAXG) out[threadIdx.x] = 0.0;
+        return;
+    }
+    const double hx0 = (tg.mode == RVL_MODE_IC) ? tg.bcv / 4 : P.bw_mult * tg.bcv;
+    const double dx = (tg.xmax - tg.xmin) / (double)(P.G - 1);
+    const double beta0 = 0.5 * (dx / hx0) * (dx / hx0);
+    const double tau = (double)(m - P.tt_pad) * P.tt_dt;
+    const double beta = (m == P.tt_pad) ? beta0 : beta0 * exp(tau);
+    const double *u = u_all + (size_t)t * P.n;
+    const uint64_t *z = (tg.mode == RVL_MODE_CIC) ? seeds + (size_t)tg.seed_of * P.words : nullptr;
+    double a0 = 0.0, a1 = 0.0;
+    const double gi = (double)lane;
+    for (int s = warp; s < P.n; s += nwarps) {
+        double d = gi - u[s];
+        double e = exp(-beta * d * d);
+        bool zb = z ? ((z[s >> 6] >> (s & 63)) & 1ull) : false;
+        if (zb) a1 += e; else a0 += e;
+    }
+    part[warp][0][lane] = a0;
+    part[warp][1][lane] = a1;
+    __syncthreads();
+    if (threadIdx.x < 2 * RVL_MAXG) {
+        int b = threadIdx.x >> 5;
+        double s = 0.0;
+        for (int w = 0; w < nwarps; w++) s += part[w][b][lane];
+        out[b * RVL_MAXG + lane] = s;
+    }
+}
+
+// Per-class totals at shrink factor c for grid point `lane`.
+__device__ __forceinline__ void rvl_tt_lookup(const RvlParams &P, const double *__restrict__ tt_t, double c, int lane,
+                                              double &tot0, double &tot1)
+{
+    if (c == 1.0) {
+        const double *nd = tt_t + (size_t)P.tt_pad * 2 * RVL_MAXG;
+        tot0 = nd[lane];
+        tot1 = nd[RVL_MAXG + lane];
+        return;
+    }
+    double pos = -2.0 * log(c) / P.tt_dt;
+    double fl = floor(pos);
+    double x = pos - fl;
+    int m0 = (int)fl + P.tt_pad - (RVL_TT_STENCIL / 2 - 1);
+    m0 = max(0, min(m0, P.tt_nodes - RVL_TT_STENCIL));
+    x = pos - (double)(m0 - P.tt_pad + (RVL_TT_STENCIL / 2 - 1)); // offset of pos from stencil node 3
+    // Lagrange weight of stencil node q = lane (q = 0..7, offsets q-3), then broadcast
+    double wl = 0.0;
+    if (lane < RVL_TT_STENCIL) {
+        double num = 1.0, den = 1.0;
+#pragma unroll
+        for (int r = 0; r < RVL_TT_STENCIL; r++) {
+            if (r != lane) {
+                num *= x - (double)(r - (RVL_TT_STENCIL / 2 - 1));
+                den *= (double)(lane - r);
+            }
+        }
+        wl = num / den;
+    }
+    tot0 = 0.0;
+    tot1 = 0.0;
+    const double *nd = tt_t + (size_t)m0 * 2 * RVL_MAXG;
+#pragma unroll
+    for (int q = 0; q < RVL_TT_STENCIL; q++) {
+        double wq = __shfl_sync(0xffffffffu, wl, q);
+        tot0 = fma(wq, nd[(size_t)q * 2 * RVL_MAXG + lane], tot0);
+        tot1 = fma(wq, nd[(size_t)q * 2 * RVL_MAXG + RVL_MAXG + lane], tot1);
+    }
 }
 
 // ---- k_score --------------------------------------------------------------------------------
@@ -214,17 +307,19 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
 __global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
 k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict__ u_all,
         const double *__restrict__ xc_all, const RvlTarget *__restrict__ tg_all,
-        const uint64_t *__restrict__ seeds, const double *__restrict__ bcvtab, double *__restrict__ scores)
+        const uint64_t *__restrict__ seeds, const double *__restrict__ bcvtab, const double *__restrict__ tt,
+        double *__restrict__ scores, unsigned long long *__restrict__ ctr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n, words = P.words, G = P.G;
     const int t = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    double *u = reinterpret_cast<double *>(smem_raw);
-    uint64_t *zrow = reinterpret_cast<uint64_t *>(u + n);
-    RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(zrow + words);
+    // 16-byte aligned scratch first; the 8-byte arrays follow
+    RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
     uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_SCORE_WARPS);
+    uint64_t *zrow = yrows + (size_t)RVL_SCORE_WARPS * words;
+    double *u = reinterpret_cast<double *>(zrow + words);
     RvlWarpScratch &S = scr[warp];
     uint64_t *yrow = yrows + (size_t)warp * words;
 
@@ -272,14 +367,55 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
         double beta = 0.5 * (dx / hx) * (dx / hx);
 
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        if (lane < G)
-            rvl_accumulate_dense(u, yrow, mode == RVL_MODE_CIC ? zrow : nullptr, 0, n, 1, (double)lane, beta, acc);
+        int nexp;
+        if (P.dense_x) {
+            // validation mode: every sample visited for every feature
+            if (lane < G)
+                rvl_accumulate_dense(u, yrow, mode == RVL_MODE_CIC ? zrow : nullptr, 0, n, 1, (double)lane, beta, acc);
+            nexp = n;
+        } else {
+            // x-axis sums = (per-class totals over ALL samples at this feature's bandwidth, interpolated
+            // from the per-iteration table) - (the minority y-class, visited bit by bit)
+            double tot0, tot1;
+            rvl_tt_lookup(P, tt + (size_t)t * P.tt_nodes * 2 * RVL_MAXG, c, lane, tot0, tot1);
+            const bool flip = n1 > n - n1; // visit the zeros of y instead when they are fewer
+            double m0 = 0.0, m1 = 0.0;     // minority-class sums split by z
+            const double gi = (double)lane;
+            const int last = (n - 1) >> 6;
+            for (int w = 0; w <= last; w++) {
+                uint64_t v = yrow[w];
+                if (flip) {
+                    v = ~v;
+                    if (w == last && (n & 63)) v &= (1ull << (n & 63)) - 1ull;
+                }
+                const uint64_t zw = (mode == RVL_MODE_CIC) ? zrow[w] : 0ull;
+                while (v) { // warp-uniform loop: every lane sees the same word
+                    int b = __ffsll((long long)v) - 1;
+                    v &= v - 1;
+                    double d = gi - u[w * 64 + b];
+                    double e = exp(-beta * d * d);
+                    if ((zw >> b) & 1ull) m1 += e; else m0 += e;
+                }
+            }
+            double r0 = fmax(tot0 - m0, 0.0), r1 = fmax(tot1 - m1, 0.0); // the majority class
+            if (flip) { acc[0] = m0; acc[1] = m1; acc[2] = r0; acc[3] = r1; }
+            else      { acc[0] = r0; acc[1] = r1; acc[2] = m0; acc[3] = m1; }
+            nexp = flip ? n - n1 : n1;
+        }
         if (lane < G) {
             S.A[lane][0] = acc[0]; S.A[lane][1] = acc[1]; S.A[lane][2] = acc[2]; S.A[lane][3] = acc[3];
         }
         __syncwarp();
-        double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, lane);
-        if (lane == 0) out[f] = score;
+        int nlive;
+        double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, lane, &nlive);
+        if (lane == 0) {
+            out[f] = score;
+            if (ctr) { // instrumentation: work actually executed (bench.py's roofline numerator)
+                atomicAdd(&ctr[0], 1ull);                          // evaluations that ran the KDE path
+                atomicAdd(&ctr[1], (unsigned long long)nlive);     // live (j,k) columns -> G logs each
+                atomicAdd(&ctr[2], (unsigned long long)nexp * G);  // x-axis exp() evaluations
+            }
+        }
         __syncwarp();
     }
 }
@@ -367,7 +503,8 @@ __device__ double rvl_assoc_block(const RvlParams &P, const RvlTarget &tg, const
             sh.S.A[lane][0] = b0; sh.S.A[lane][1] = 0.0; sh.S.A[lane][2] = b1; sh.S.A[lane][3] = 0.0;
         }
         __syncwarp();
-        score = rvl_finish(sh.S, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, lane);
+        int nlive;
+        score = rvl_finish(sh.S, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, lane, &nlive);
     }
     return score; // valid in warp 0
 }
@@ -455,7 +592,6 @@ k_merge(RvlParams P, int iter, int iters, int first_null, const unsigned char *_
         uint64_t *__restrict__ seed_iter, double *__restrict__ cmi_seed)
 {
     __shared__ RvlAssocShared sh;
-    __shared__ int sh_i[32];
     __shared__ int win_rank;
     int t = blockIdx.x;
     bool is_null = (first_null > 0 && t >= first_null);
@@ -585,10 +721,37 @@ extern "C" cudaError_t rvl_score_configure(size_t smem)
 
 extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits,
                                  const double *u_all, const double *xc_all, const RvlTarget *tg,
-                                 const uint64_t *seeds, const double *bcvtab, double *scores, cudaStream_t st)
+                                 const uint64_t *seeds, const double *bcvtab, const double *tt, double *scores,
+                                 unsigned long long *ctr, cudaStream_t st)
 {
     dim3 grid(grid_x, P->T);
-    k_score<<<grid, RVL_SCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, scores);
+    k_score<<<grid, RVL_SCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, ctr);
+}
+
+extern "C" void rvl_launch_ttable(const RvlParams *P, const RvlTarget *tg, const double *u_all,
+                                  const uint64_t *seeds, double *tt, cudaStream_t st)
+{
+    dim3 grid(P->tt_nodes, P->T);
+    k_ttable<<<grid, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, u_all, seeds, tt);
+}
+
+// FP64 FMA peak micro-benchmark (MEASURED_PEAKS.json has no FP64 figure): 8 independent DFMA chains
+// per thread.  out[tid] keeps the compiler honest.
+__global__ void k_fp64_peak(int iters, double seedv, double *__restrict__ out)
+{
+    double a0 = seedv, a1 = seedv + 1, a2 = seedv + 2, a3 = seedv + 3, a4 = seedv + 4, a5 = seedv + 5, a6 = seedv + 6,
+           a7 = seedv + 7;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaStream_t st)
+{
+    k_fp64_peak<<<blocks, threads, 0, st>>>(iters, 1.0, out);
 }
 
 extern "C" void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const uint64_t *seeds,

@@ -1,0 +1,142 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/revealer_b200.h declares; host-side helpers (bit packing, sharding, winner resolution); and the
+product path fails loudly without a GPU (no CPU fallback, nothing under oracle/ is imported)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "revealer_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(rvl_[a-z0-9_]+)\s*\(", hdr)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from revealer_b200 import build as rb_build
+    return rb_build.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for s in names:
+        assert hasattr(lib, s), "missing export: " + s
+    lib.rvl_abi_version.restype = ctypes.c_int
+    assert lib.rvl_abi_version() == 1
+
+
+def test_python_binding_covers_the_header(built_lib):
+    from revealer_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+    _lib.load()
+
+
+def test_library_is_sm100a_only(built_lib):
+    out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_gpu_means_error_not_fallback(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    import revealer_b200 as rb
+    with pytest.raises(rb.RevealerError):
+        rb.RevealerContext(0)
+    with pytest.raises(rb.RevealerError):
+        rb.assoc(np.arange(10.0), np.array([0, 1] * 5))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "revealer_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h", ".R")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.lower() or f == "synth.py" and "oracle" not in src.lower(), f
+    code = "import sys; import revealer_b200; assert not any('oracle' in m for m in sys.modules), 'oracle imported'"
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+
+
+def test_pack_bits_layout():
+    import revealer_b200 as rb
+    rng = np.random.default_rng(0)
+    for n in (1, 63, 64, 65, 130, 1000):
+        m = (rng.random((5, n)) < 0.4).astype(np.uint8)
+        bits, words = rb.pack_bits(m)
+        assert words % 2 == 0 and words * 64 >= n and bits.shape == (5, words)
+        for k in range(5):
+            for s in range(n):
+                assert (int(bits[k, s >> 6]) >> (s & 63)) & 1 == m[k, s]
+        assert all(int(bits[k, (n - 1) >> 6]) >> ((n - 1) & 63) >> 1 == 0 for k in range(5)) or n % 64 == 0
+    with pytest.raises(rb.RevealerError):
+        rb.pack_bits(np.array([[0, 2, 1]]))
+
+
+def test_shard_rows_partition():
+    import revealer_b200 as rb
+    for F in (0, 1, 7, 100000, 500001):
+        for world in (1, 2, 4, 8):
+            spans = [rb.shard_rows(F, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == F
+            for (lo, c), (lo2, _) in zip(spans, spans[1:]):
+                assert lo + c == lo2
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_resolve_winner_matches_r_order(oracle):
+    from revealer_b200.api import resolve_winner
+    rng = np.random.default_rng(1)
+    for trial in range(200):
+        k = rng.integers(1, 9)
+        rows = rng.choice(1000, k, replace=False)
+        sc = rng.choice([0.1, 0.5, 0.5, -0.3, np.nan], k)
+        for neg in (False, True):
+            # scatter into a full score vector and ask the oracle's order()
+            full = np.full(1000, np.nan)
+            full[rows] = sc
+            want = oracle.top1(full, negative=neg)
+            got = rows[resolve_winner(sc, rows, neg)]
+            if np.all(np.isnan(sc)):
+                assert got == rows.min()
+            else:
+                assert got == want
+    assert resolve_winner([0.2, 0.9], [-1, -1]) == -1
+    assert resolve_winner([0.2, np.nan, 0.1], [-1, 5, 9]) == 2
+
+
+def test_reference_formals_are_preserved():
+    """REVEALER.v1's 12 formals (LIB:1504-1516), same names (dots -> underscores) and defaults."""
+    import inspect
+    import revealer_b200 as rb
+    sig = inspect.signature(rb.REVEALER_v1)
+    names = list(sig.parameters)[:12]
+    assert names == ["ds1", "target_name", "target_match", "ds2", "seed_names", "exclude_features", "max_n_iter",
+                     "pdf_output_file", "count_thres_low", "count_thres_high", "n_markers", "locs_table_file"]
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert d["target_match"] == "positive" and d["max_n_iter"] == 5 and d["n_markers"] == 30
+    assert d["seed_names"] is None and d["count_thres_low"] is None and d["n_grid"] == 25
+    assert d["bandwidth_mult"] == 0.25 and d["bandwidth_shrink"] == -0.75
+
+
+def test_synthetic_workload_is_deterministic_and_shardable():
+    from revealer_b200 import synth
+    a = synth.make_workload(n=120, F=900)
+    b = synth.make_workload(n=120, F=900, row_lo=200, row_hi=650)
+    assert np.array_equal(a["m2"][200:650], b["m2"]) and np.array_equal(a["seed"], b["seed"])
+    assert np.all(np.diff(a["target"]) <= 0)
+    dup = ((a["m2"][1:] == a["m2"][:-1]).all(axis=1)).mean()
+    assert 0.1 < dup < 0.3
+    cnt = a["m2"].sum(axis=1)
+    assert (cnt == 0).any() and (cnt == 120).any()
