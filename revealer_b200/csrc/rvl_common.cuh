@@ -61,6 +61,42 @@ struct RvlParams {
 
 #define RVL_DBL_EPS 2.220446049250313e-16
 
+// log(q) for a positive, finite, NORMAL double (callers guarantee the range once per evaluation).
+// Branch-free: mantissa folded to [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1) by a MUFU reciprocal seed
+// + two Newton steps, log m = 2 atanh(s) as a 9-term odd series (|s| <= 0.1716), k*ln2 added last.
+// <= 2 ulp against a correctly rounded log over [1e-18, 1e5] (emulated in tests/test_fastlog.py);
+// 21 FP64-pipe instructions, no special-case branches, coefficients stay in registers across a loop.
+__device__ __forceinline__ double rvl_log_pos(double q)
+{
+    int hi = __double2hiint(q);
+    const int lo = __double2loint(q);
+    hi += 0x3ff00000 - 0x3fe6a09e;
+    const int k = (hi >> 20) - 0x3ff;
+    hi = (hi & 0x000fffff) + 0x3fe6a09e;
+    const double m = __hiloint2double(hi, lo);
+    const double f = m - 1.0, t = m + 1.0;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(t));
+    double e = fma(-t, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-t, r, 1.0);
+    r = fma(r, e, r);
+    const double s = f * r;
+    const double z = s * s;
+    double p = 1.0 / 19.0;
+    p = fma(p, z, 1.0 / 17.0);
+    p = fma(p, z, 1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0);
+    p = fma(p, z, 1.0 / 11.0);
+    p = fma(p, z, 1.0 / 9.0);
+    p = fma(p, z, 1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0);
+    p = fma(p, z, 1.0 / 3.0);
+    const double s2 = s + s;
+    const double lm = fma(s2 * z, p, s2);
+    return fma((double)k, 0.6931471805599453094, lm);
+}
+
 __device__ __forceinline__ double rvl_warp_sum(double v)
 {
 #pragma unroll

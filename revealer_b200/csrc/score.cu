@@ -37,7 +37,9 @@ struct __align__(16) RvlWarpScratch {
     uint16_t live[RVL_MAXG * RVL_MAXG];
 };
 
-__device__ __forceinline__ double rvl_xlogx(double q) { return q * log(q); }
+// FAST: rvl_log_pos (normal positive arguments only); otherwise the library log.
+template <bool FAST> __device__ __forceinline__ double rvl_logq(double q) { return FAST ? rvl_log_pos(q) : log(q); }
+template <bool FAST> __device__ __forceinline__ double rvl_xlogx(double q) { return q * rvl_logq<FAST>(q); }
 
 // Accumulate the class-masked Gaussian sums for grid point `lane` over samples [s_begin, s_end)
 // with stride s_step.  yrow / zrow are bit rows (zrow may be NULL: single z class).
@@ -56,6 +58,7 @@ __device__ __forceinline__ void rvl_accumulate_dense(const double *__restrict__ 
 }
 
 // 3-D epilogue: CMI from A (in scratch), axis kernels gy/gz, eps' = eps/kappa.  Whole warp.
+template <bool FAST>
 __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int lane, int *nlive_out)
 {
     const unsigned FULL = 0xffffffffu;
@@ -103,15 +106,15 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int la
             double q0 = fma(S.A[i][0], w00, fma(S.A[i][1], w01, fma(S.A[i][2], w10, fma(S.A[i][3], w11, epsq))));
             double q1 = fma(S.A[i + 1][0], w00,
                             fma(S.A[i + 1][1], w01, fma(S.A[i + 1][2], w10, fma(S.A[i + 1][3], w11, epsq))));
-            acc0 = fma(q0, log(q0), acc0);
-            acc1 = fma(q1, log(q1), acc1);
+            acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
+            acc1 = fma(q1, rvl_logq<FAST>(q1), acc1);
         }
         if (i < G) {
             double q0 = fma(S.A[i][0], w00, fma(S.A[i][1], w01, fma(S.A[i][2], w10, fma(S.A[i][3], w11, epsq))));
-            acc0 = fma(q0, log(q0), acc0);
+            acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
         }
     }
-    double L3 = rvl_warp_sum(acc0 + acc1) + (double)(GG - nlive) * (double)G * rvl_xlogx(epsq);
+    double L3 = rvl_warp_sum(acc0 + acc1) + (double)(GG - nlive) * (double)G * rvl_xlogx<FAST>(epsq);
 
     // marginals: Q_ik (XZ), Q_jk (YZ), Q_k (Z)
     double accxz = 0.0, accyz = 0.0;
@@ -122,13 +125,13 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int la
         double qyz = fma(sa[0] * S.gy[0][a], S.gz[0][k],
                          fma(sa[1] * S.gy[0][a], S.gz[1][k],
                              fma(sa[2] * S.gy[1][a], S.gz[0][k], fma(sa[3] * S.gy[1][a], S.gz[1][k], gE))));
-        accxz += rvl_xlogx(qxz);
-        accyz += rvl_xlogx(qyz);
+        accxz += rvl_xlogx<FAST>(qxz);
+        accyz += rvl_xlogx<FAST>(qyz);
     }
     double accz = 0.0;
     if (lane < G) {
         double qz = fma((sa[0] + sa[2]) * Gy, S.gz[0][lane], fma((sa[1] + sa[3]) * Gy, S.gz[1][lane], (double)GG * epsq));
-        accz = rvl_xlogx(qz);
+        accz = rvl_xlogx<FAST>(qz);
     }
     double Lxz = rvl_warp_sum(accxz), Lyz = rvl_warp_sum(accyz), Lz = rvl_warp_sum(accz);
     double Stot = (sa[0] + sa[1] + sa[2] + sa[3]) * Gy * Gz + (double)GG * (double)G * epsq;
@@ -136,6 +139,7 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int la
 }
 
 // 2-D epilogue (mutual.inf.v2, LIB:2536-2550): MI from B_a[i] = A[i][a*2] and gy.  Whole warp.
+template <bool FAST>
 __device__ double rvl_mi_epilogue(RvlWarpScratch &S, int G, double epsq, int lane)
 {
     double b0 = (lane < G) ? S.A[lane][0] : 0.0, b1 = (lane < G) ? S.A[lane][2] : 0.0;
@@ -148,14 +152,14 @@ __device__ double rvl_mi_epilogue(RvlWarpScratch &S, int G, double epsq, int lan
     for (int p = lane; p < GG; p += 32) {
         int i = p / G, j = p - i * G;
         double q = fma(S.A[i][0], S.gy[0][j], fma(S.A[i][2], S.gy[1][j], epsq));
-        acc += rvl_xlogx(q);
+        acc += rvl_xlogx<FAST>(q);
     }
     double accx = 0.0, accy = 0.0;
     if (lane < G) {
         double qx = fma(b0 + b1, Gy, gE);
         double qy = fma(sb0, S.gy[0][lane], fma(sb1, S.gy[1][lane], gE));
-        accx = rvl_xlogx(qx);
-        accy = rvl_xlogx(qy);
+        accx = rvl_xlogx<FAST>(qx);
+        accy = rvl_xlogx<FAST>(qy);
     }
     double L2 = rvl_warp_sum(acc), Lx = rvl_warp_sum(accx), Ly = rvl_warp_sum(accy);
     double Stot = (sb0 + sb1) * Gy + (double)GG * epsq;
@@ -197,7 +201,7 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
         rvl_fill_axis(S.gy, G, hy, lane);
         __syncwarp();
         double epsq = RVL_DBL_EPS * (RVL_TWO_PI * dn * hx * hy);
-        double mi = rvl_mi_epilogue(S, G, epsq, lane);
+        double mi = (epsq >= 1e-290) ? rvl_mi_epilogue<true>(S, G, epsq, lane) : rvl_mi_epilogue<false>(S, G, epsq, lane);
         return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * mi));
     }
     double hy = P.bw_mult * bcv_y * c, hz = P.bw_mult * bcv_z * c;
@@ -205,7 +209,9 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
     rvl_fill_axis(S.gz, G, hz, lane);
     __syncwarp();
     double epsq = RVL_DBL_EPS * (dn * RVL_TWO_PI * sqrt(RVL_TWO_PI) * hx * hy * hz);
-    double cmi = rvl_cmi_epilogue(S, G, epsq, lane, nlive_out);
+    // every Q lies in [eps', 4 n G^3]: normal doubles unless eps' itself is tiny (degenerate bandwidths)
+    double cmi = (epsq >= 1e-290) ? rvl_cmi_epilogue<true>(S, G, epsq, lane, nlive_out)
+                                  : rvl_cmi_epilogue<false>(S, G, epsq, lane, nlive_out);
     return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * cmi));
 }
 

@@ -1,0 +1,41 @@
+"""CPU emulation of rvl_log_pos (revealer_b200/csrc/rvl_common.cuh): the branch-free log the entropy
+epilogue uses for positive normal doubles.  Same bit manipulations, same operation order (numpy float64
+has no FMA, which only makes this emulation slightly *less* accurate than the device code); the MUFU
+reciprocal seed is modelled by a float32 reciprocal (2^-24; the PTX rcp.approx.ftz.f64 guarantees 2^-23,
+and two Newton steps square that twice).  Must stay within 4 ulp of numpy's log over the range of Q."""
+import numpy as np
+
+
+def rvl_log_pos(q):
+    bits = q.view(np.uint64)
+    hi = (bits >> np.uint64(32)).astype(np.int64)
+    lo = bits & np.uint64(0xFFFFFFFF)
+    hi = hi + (0x3FF00000 - 0x3FE6A09E)
+    k = (hi >> 20) - 0x3FF
+    hi = (hi & 0x000FFFFF) + 0x3FE6A09E
+    m = ((hi.astype(np.uint64) << np.uint64(32)) | lo).view(np.float64)
+    f, t = m - 1.0, m + 1.0
+    r = (np.float32(1.0) / t.astype(np.float32)).astype(np.float64)
+    e = 1.0 - t * r
+    r = r + r * e
+    e = 1.0 - t * r
+    r = r + r * e
+    s = f * r
+    z = s * s
+    p = np.full_like(z, 1.0 / 19.0)
+    for d in (17.0, 15.0, 13.0, 11.0, 9.0, 7.0, 5.0, 3.0):
+        p = p * z + 1.0 / d
+    s2 = s + s
+    return k * 0.6931471805599453094 + (s2 * z * p + s2)
+
+
+def test_fast_log_within_a_few_ulp():
+    rng = np.random.default_rng(0)
+    q = np.concatenate([np.exp(rng.uniform(-200, 40, 1_000_000)), np.exp(rng.uniform(-1e-3, 1e-3, 200_000)),
+                        np.array([1.0, 2.0, 0.5, np.sqrt(0.5), np.sqrt(2.0), 2.220446049250313e-16, 1e-290])])
+    got, ref = rvl_log_pos(q), np.log(q)
+    ulp = np.spacing(np.maximum(np.abs(ref), 1e-300))
+    big = np.abs(ref) > 1e-3
+    assert np.max(np.abs(got - ref)[big] / ulp[big]) <= 4.0
+    assert np.max(np.abs(got - ref)[~big]) <= 1e-18
+    assert rvl_log_pos(np.array([1.0]))[0] == 0.0
