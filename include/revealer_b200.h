@@ -165,6 +165,12 @@ int rvl_score_kernel_time(rvl_ctx *ctx, double *out_ms, int64_t *out_launches, i
  * feature over all n samples (the literal form) instead of using the per-iteration
  * bandwidth-interpolation table + minority-class visit.  Same results to ~1e-12; ~5x slower. */
 int rvl_set_dense_x(rvl_ctx *ctx, int on);
+/* Density-column pruning of the 3-D entropy epilogue.  A (y,z)-grid column whose cells can hold at
+ * most theta / n_grid^3 of the total probability mass is replaced by the reference's
+ * .Machine$double.eps floor (LIB:2581); this changes CMI by at most theta * (|log eps'| + 1)
+ * (about 4e-13 for the default theta = 1e-14, against the 1e-6 relative tolerance on scores).
+ * theta = 0 keeps only the exact rule (columns that cannot change fl(density + eps)). */
+int rvl_set_prune_theta(rvl_ctx *ctx, double theta);
 /* Work counters of the score kernel since the last reset: out4[0] evaluations that ran the KDE path,
  * out4[1] live (j,k) density columns (n_grid log() each), out4[2] dense-pass exp() evaluations. */
 int rvl_get_counters(rvl_ctx *ctx, uint64_t *out4, int reset);

@@ -272,6 +272,10 @@ class RevealerContext:
         """Validation mode: literal per-feature x-axis sums over all samples (see rvl_set_dense_x)."""
         self._ck(self._lib.rvl_set_dense_x(self._h, int(bool(on))))
 
+    def set_prune_theta(self, theta):
+        """Density-column pruning threshold of the 3-D epilogue (see rvl_set_prune_theta); 0 = exact rule only."""
+        self._ck(self._lib.rvl_set_prune_theta(self._h, float(theta)))
+
     def counters(self, reset=False):
         out = (C.c_uint64 * 4)()
         self._ck(self._lib.rvl_get_counters(self._h, out, int(reset)))

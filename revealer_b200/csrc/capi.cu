@@ -26,7 +26,7 @@ size_t rvl_score_smem_bytes(int n, int words);
 cudaError_t rvl_score_configure(size_t smem);
 void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits, const double *u_all,
                       const double *xc_all, const RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
-                      const double *tt, double *scores, unsigned long long *ctr, cudaStream_t st);
+                      const double *tt, double *scores, RvlCandHead *part, unsigned long long *ctr, cudaStream_t st);
 void rvl_launch_ttable(const RvlParams *P, const RvlTarget *tg, const double *u_all, const uint64_t *seeds,
                        double *tt, cudaStream_t st);
 void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaStream_t st);
@@ -34,12 +34,11 @@ void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const uint64_t *see
                           cudaStream_t st);
 void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of, const double *u_all,
                       const double *xc_all, const uint64_t *y_all, const double *bcvtab, double *out,
-                      cudaStream_t st);
-void rvl_launch_argmax(const RvlParams *P, const double *scores, const uint64_t *bits, unsigned char *send,
-                       size_t rec_bytes, cudaStream_t st);
+                      size_t y_stride, size_t out_stride, cudaStream_t st);
+void rvl_launch_argmax(const RvlParams *P, const RvlCandHead *part, int nparts, const uint64_t *bits,
+                       unsigned char *send, size_t rec_bytes, cudaStream_t st);
 void rvl_launch_merge(const RvlParams *P, int iter, int iters, int first_null, const unsigned char *recv,
-                      size_t rec_bytes, RvlTarget *tg, uint64_t *seeds, const double *u_all, const double *xc_all,
-                      const double *bcvtab, int64_t *top, double *top_score, uint64_t *seed_iter, double *cmi_seed,
+                      size_t rec_bytes, uint64_t *seeds, int64_t *top, double *top_score, uint64_t *seed_iter,
                       cudaStream_t st);
 void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols, int words,
                                   uint64_t *bits, int *flag, cudaStream_t st);
@@ -80,6 +79,7 @@ struct rvl_ctx {
     double *d_tt = nullptr;
     size_t tt_cap = 0;
     int dense_x = 0;
+    double prune_theta = 1e-14;
 
     // seeds
     uint64_t *d_seed0 = nullptr; // initial seeds [T][words]
@@ -97,6 +97,14 @@ struct rvl_ctx {
     unsigned char *d_send = nullptr, *d_recv = nullptr; // exchange buffers
     unsigned char *d_own_xchg = nullptr;                // owned fallback (world == 1)
     size_t own_xchg_bytes = 0;
+
+    // per-CTA bests of the last k_score launch [T][score_grid_x]; side stream for the seed IC
+    RvlCandHead *d_part = nullptr;
+    size_t part_cap = 0;
+    int score_grid_x = 0;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_pending = false;
 
     // instrumentation
     unsigned long long *d_ctr = nullptr; // [0] KDE evaluations, [1] live (j,k) columns, [2] dense-pass exps
@@ -157,6 +165,7 @@ static RvlParams make_params(const rvl_ctx *c)
     P.tt_nodes = (int)ceil(tau_max / P.tt_dt) + 2 * RVL_TT_PAD + 1;
     if (P.tt_nodes < RVL_TT_STENCIL) P.tt_nodes = RVL_TT_STENCIL;
     P.dense_x = c->dense_x;
+    P.prune_theta = c->prune_theta;
     return P;
 }
 
@@ -184,6 +193,9 @@ extern "C" int rvl_create(rvl_ctx **out, int device)
         cudaMalloc((void **)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_ctr, 4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_ctr, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
         return RVL_ERR_CUDA;
@@ -224,6 +236,10 @@ extern "C" void rvl_destroy(rvl_ctx *ctx)
     dfree(ctx->d_flag);
     dfree(ctx->d_ctr);
     for (auto &p : ctx->score_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    dfree(ctx->d_part);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -540,6 +556,13 @@ static int launch_score(rvl_ctx *ctx, double *base)
     int64_t per_block = 8 * 4; // RVL_SCORE_WARPS warps x 4 rows each: the hardware block scheduler balances the tail
     int64_t gx = (ctx->F + per_block - 1) / per_block;
     if (gx > 65535 * 16) gx = 65535 * 16;
+    size_t pneed = (size_t)ctx->T * (size_t)gx;
+    if (pneed > ctx->part_cap) {
+        dfree(ctx->d_part);
+        CK(dalloc(&ctx->d_part, pneed));
+        ctx->part_cap = pneed;
+    }
+    ctx->score_grid_x = (int)gx;
     if (ctx->score_events_used == ctx->score_events.size()) {
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));
@@ -549,10 +572,20 @@ static int launch_score(rvl_ctx *ctx, double *base)
     auto &ev = ctx->score_events[ctx->score_events_used++];
     CK(cudaEventRecord(ev.first, ctx->stream));
     rvl_launch_score(&P, (int)gx, smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab,
-                     ctx->d_tt, base, ctx->d_ctr, ctx->stream);
+                     ctx->d_tt, base, ctx->d_part, ctx->d_ctr, ctx->stream);
     CK(cudaEventRecord(ev.second, ctx->stream));
     ctx->launches++;
     CK(cudaGetLastError());
+    return RVL_OK;
+}
+
+// Make the main stream wait for the side-stream seed ICs (before results are read or reused).
+static int join_side(rvl_ctx *ctx)
+{
+    if (!ctx->side_pending) return RVL_OK;
+    CK(cudaEventRecord(ctx->ev_join, ctx->side));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    ctx->side_pending = false;
     return RVL_OK;
 }
 
@@ -573,6 +606,8 @@ extern "C" int rvl_search_begin(rvl_ctx *ctx, int iters)
     int rc = ready(ctx);
     if (rc) return rc;
     if (iters < 1) return fail(ctx, RVL_ERR_ARG, "iters < 1");
+    rc = join_side(ctx); // a previous search's seed ICs must land before buffers are reused
+    if (rc) return rc;
     rc = ensure_results(ctx, iters);
     if (rc) return rc;
     ctx->iters = iters;
@@ -591,7 +626,8 @@ extern "C" int rvl_search_begin(rvl_ctx *ctx, int iters)
     rc = prep_iteration(ctx);
     if (rc) return rc;
     // cmi.seed.iter0 <- assoc(target, seed)  LIB:1833
-    rvl_launch_assoc(&P, ctx->T, ctx->d_tg, nullptr, ctx->d_u, ctx->d_xc, ctx->d_seed, ctx->d_bcvtab, ctx->d_ic0, ctx->stream);
+    rvl_launch_assoc(&P, ctx->T, ctx->d_tg, nullptr, ctx->d_u, ctx->d_xc, ctx->d_seed, ctx->d_bcvtab, ctx->d_ic0,
+                     (size_t)ctx->words, 1, ctx->stream);
     ctx->launches += 1;
     CK(cudaGetLastError());
     return RVL_OK;
@@ -604,7 +640,7 @@ extern "C" int rvl_iter_score(rvl_ctx *ctx, int iter)
     int rc = launch_score(ctx, ctx->d_scores + (size_t)iter * ctx->T * ctx->F);
     if (rc) return rc;
     RvlParams P2 = make_params(ctx);
-    rvl_launch_argmax(&P2, ctx->d_scores + (size_t)iter * ctx->T * ctx->F, ctx->d_bits, ctx->d_send,
+    rvl_launch_argmax(&P2, ctx->d_part, ctx->F > 0 ? ctx->score_grid_x : 0, ctx->d_bits, ctx->d_send,
                       sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -617,10 +653,20 @@ extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
     if (iter < 0 || iter >= ctx->iters) return fail(ctx, RVL_ERR_ARG, "iter out of range");
     RvlParams P = make_params(ctx);
     rvl_launch_merge(&P, iter, ctx->iters, ctx->first_null, ctx->d_recv,
-                     sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, ctx->d_tg, ctx->d_seed, ctx->d_u,
-                     ctx->d_xc, ctx->d_bcvtab, ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, ctx->d_cmi_seed,
-                     ctx->stream);
+                     sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, ctx->d_seed, ctx->d_top,
+                     ctx->d_top_score, ctx->d_seed_iter, ctx->stream);
     ctx->launches += 1;
+    CK(cudaGetLastError());
+    // cmi.seed[iter] <- assoc(target, seed) (LIB:2170) is off the critical path: side stream, reading
+    // the seed_iter row k_merge just wrote (never modified again)
+    int nreal = ctx->first_null > 0 ? ctx->first_null : ctx->T;
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    rvl_launch_assoc(&P, nreal, ctx->d_tg, nullptr, ctx->d_u, ctx->d_xc, ctx->d_seed_iter + (size_t)iter * ctx->words,
+                     ctx->d_bcvtab, ctx->d_cmi_seed + iter, (size_t)ctx->iters * ctx->words, (size_t)ctx->iters,
+                     ctx->side);
+    ctx->launches += 1;
+    ctx->side_pending = true;
     CK(cudaGetLastError());
     return prep_iteration(ctx);
 }
@@ -628,6 +674,8 @@ extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
 extern "C" int rvl_synchronize(rvl_ctx *ctx)
 {
     GUARD();
+    int jrc = join_side(ctx);
+    if (jrc) return jrc;
     CK(cudaStreamSynchronize(ctx->stream));
     drain_score_events(ctx);
     return RVL_OK;
@@ -639,6 +687,8 @@ extern "C" int rvl_search_fetch(rvl_ctx *ctx, rvl_result *out)
     if (!out) return fail(ctx, RVL_ERR_ARG, "result is NULL");
     int T = ctx->T, iters = ctx->iters, words = ctx->words, n = ctx->n;
     if (iters < 1) return fail(ctx, RVL_ERR_STATE, "no search has run");
+    int jrc = join_side(ctx);
+    if (jrc) return jrc;
     CK(cudaStreamSynchronize(ctx->stream));
     drain_score_events(ctx);
     if (out->cmi && ctx->F > 0) {
@@ -721,7 +771,7 @@ extern "C" int rvl_assoc(rvl_ctx *ctx, int64_t target_index, const uint8_t *y, i
     RvlParams P = make_params(ctx);
     cudaMemcpyAsync(d_y, packed.data(), sizeof(uint64_t) * ctx->words, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_t, &ti, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-    rvl_launch_assoc(&P, 1, ctx->d_tg, d_t, ctx->d_u, ctx->d_xc, d_y, ctx->d_bcvtab, d_o, ctx->stream);
+    rvl_launch_assoc(&P, 1, ctx->d_tg, d_t, ctx->d_u, ctx->d_xc, d_y, ctx->d_bcvtab, d_o, (size_t)ctx->words, 1, ctx->stream);
     ctx->launches++;
     cudaMemcpyAsync(out_ic, d_o, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -860,5 +910,13 @@ extern "C" int rvl_set_dense_x(rvl_ctx *ctx, int on)
 {
     GUARD();
     ctx->dense_x = on ? 1 : 0;
+    return RVL_OK;
+}
+
+extern "C" int rvl_set_prune_theta(rvl_ctx *ctx, double theta)
+{
+    GUARD();
+    if (!(theta >= 0.0) || theta > 1e-9) return fail(ctx, RVL_ERR_ARG, "prune theta must be in [0, 1e-9]");
+    ctx->prune_theta = theta;
     return RVL_OK;
 }

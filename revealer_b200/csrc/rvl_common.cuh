@@ -53,6 +53,7 @@ struct RvlParams {
     int32_t tt_nodes, tt_pad;
     double tt_dt;
     int32_t dense_x;  // 1: recompute the x-axis sums per feature over all samples (validation mode)
+    double prune_theta; // density columns holding < theta/G^3 of the mass are replaced by the eps floor
 };
 
 #define RVL_TT_STENCIL 8   // Lagrange points
@@ -61,13 +62,46 @@ struct RvlParams {
 
 #define RVL_DBL_EPS 2.220446049250313e-16
 
+// Coefficients of rvl_log_pos in constant memory so that DFMA takes them as c[bank][offset] operands
+// (no per-use UMOV pair): R(z) = Lg1 z + ... + Lg7 z^7 ~ (log(1+s) - log(1-s) - 2s)/s on
+// z = s^2 <= 0.0295 (the minimax fit published with fdlibm's e_log.c, |error| < 2^-58.45), then ln 2.
+static __constant__ double RVL_LG[8] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                                 2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                                 1.479819860511658591e-01, 0.6931471805599453094};
+
 // log(q) for a positive, finite, NORMAL double (callers guarantee the range once per evaluation).
 // Branch-free: mantissa folded to [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1) by a MUFU reciprocal seed
-// + two Newton steps, log m = 2 atanh(s) as a 9-term odd series (|s| <= 0.1716), k*ln2 added last.
-// <= 2 ulp against a correctly rounded log over [1e-18, 1e5] (emulated in tests/test_fastlog.py);
-// 21 FP64-pipe instructions, no special-case branches, coefficients stay in registers across a loop.
+// + two Newton steps, log m = 2s + s R(s^2), k*ln2 added last.
+// <= 4 ulp against numpy's log over [1e-87, 1e17] (emulated in tests/test_fastlog.py);
+// 18 FP64-pipe instructions, no special-case branches.
 __device__ __forceinline__ double rvl_log_pos(double q)
 {
+#if 1
+    int hi = __double2hiint(q);
+    const int lo = __double2loint(q);
+    hi += 0x3ff00000 - 0x3fe6a09e;
+    const int k = (hi >> 20) - 0x3ff;
+    hi = (hi & 0x000fffff) + 0x3fe6a09e;
+    const double m = __hiloint2double(hi, lo);
+    const double f = m - 1.0, t = m + 1.0;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(t));
+    double e = fma(-t, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-t, r, 1.0);
+    r = fma(r, e, r);
+    const double s = f * r;
+    const double z = s * s;
+    double p = RVL_LG[6];
+    p = fma(p, z, RVL_LG[5]);
+    p = fma(p, z, RVL_LG[4]);
+    p = fma(p, z, RVL_LG[3]);
+    p = fma(p, z, RVL_LG[2]);
+    p = fma(p, z, RVL_LG[1]);
+    p = fma(p, z, RVL_LG[0]);
+    const double lm = fma(s * z, p, s + s);
+    return fma((double)k, RVL_LG[7], lm);
+#else
     int hi = __double2hiint(q);
     const int lo = __double2loint(q);
     hi += 0x3ff00000 - 0x3fe6a09e;
@@ -95,6 +129,7 @@ __device__ __forceinline__ double rvl_log_pos(double q)
     const double s2 = s + s;
     const double lm = fma(s2 * z, p, s2);
     return fma((double)k, 0.6931471805599453094, lm);
+#endif
 }
 
 __device__ __forceinline__ double rvl_warp_sum(double v)

@@ -59,7 +59,7 @@ __device__ __forceinline__ void rvl_accumulate_dense(const double *__restrict__ 
 
 // 3-D epilogue: CMI from A (in scratch), axis kernels gy/gz, eps' = eps/kappa.  Whole warp.
 template <bool FAST>
-__device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int lane, int *nlive_out)
+__device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, double theta, int lane, int *nlive_out)
 {
     const unsigned FULL = 0xffffffffu;
     // per-class totals and maxima over the x grid
@@ -75,8 +75,12 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int la
     double Gy = rvl_warp_sum(gyv); // = sum_j gy_1[j] as well (mirror image)
     double Gz = rvl_warp_sum(gzv);
 
-    // live (j,k) columns
-    const double dead_thr = epsq * 0x1p-55;
+    // live (j,k) columns.  A column is skipped when its largest possible density is below
+    //   max(eps' * 2^-55, theta * S / G^3):
+    // the first bound is exact (fl(D + eps') == eps'); the second replaces cells of mass < theta/G^3
+    // by the eps' floor, which moves CMI by at most theta * (|log eps'| + 1) in total.
+    const double Stot = (sa[0] + sa[1] + sa[2] + sa[3]) * Gy * Gz + (double)(G * G) * (double)G * epsq;
+    const double dead_thr = fmax(epsq * 0x1p-55, theta * Stot / ((double)(G * G) * (double)G));
     int GG = G * G, nlive = 0;
     for (int p0 = 0; p0 < GG; p0 += 32) {
         int p = p0 + lane;
@@ -94,13 +98,17 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int la
     __syncwarp();
     *nlive_out = nlive;
 
-    // L3 = sum over all cells of Q log Q
-    double acc0 = 0.0, acc1 = 0.0;
+    // L3 = sum over all cells of Q log Q;  Lyz = sum over (j,k) of Q_jk log Q_jk with
+    // Q_jk = sum_i Q_ijk in closed form (skipped columns: Q_jk = G eps' to rounding)
+    double acc0 = 0.0, acc1 = 0.0, accyz = 0.0;
+    const double gE = (double)G * epsq;
     for (int idx = lane; idx < nlive; idx += 32) {
         int p = S.live[idx];
         int j = p / G, k = p - j * G;
         double w00 = S.gy[0][j] * S.gz[0][k], w01 = S.gy[0][j] * S.gz[1][k];
         double w10 = S.gy[1][j] * S.gz[0][k], w11 = S.gy[1][j] * S.gz[1][k];
+        double qyz = fma(sa[0], w00, fma(sa[1], w01, fma(sa[2], w10, fma(sa[3], w11, gE))));
+        accyz = fma(qyz, rvl_logq<FAST>(qyz), accyz);
         int i = 0;
         for (; i + 1 < G; i += 2) {
             double q0 = fma(S.A[i][0], w00, fma(S.A[i][1], w01, fma(S.A[i][2], w10, fma(S.A[i][3], w11, epsq))));
@@ -114,27 +122,23 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, int la
             acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
         }
     }
-    double L3 = rvl_warp_sum(acc0 + acc1) + (double)(GG - nlive) * (double)G * rvl_xlogx<FAST>(epsq);
+    const double ndead = (double)(GG - nlive);
+    double L3 = rvl_warp_sum(acc0 + acc1) + ndead * (double)G * rvl_xlogx<FAST>(epsq);
+    double Lyz = rvl_warp_sum(accyz) + ndead * rvl_xlogx<FAST>(gE);
 
-    // marginals: Q_ik (XZ), Q_jk (YZ), Q_k (Z)
-    double accxz = 0.0, accyz = 0.0;
-    double gE = (double)G * epsq;
+    // marginals: Q_ik (XZ), Q_k (Z)
+    double accxz = 0.0;
     for (int p = lane; p < GG; p += 32) {
-        int a = p / G, k = p - a * G; // a is i for XZ, j for YZ
-        double qxz = fma((S.A[a][0] + S.A[a][2]) * Gy, S.gz[0][k], fma((S.A[a][1] + S.A[a][3]) * Gy, S.gz[1][k], gE));
-        double qyz = fma(sa[0] * S.gy[0][a], S.gz[0][k],
-                         fma(sa[1] * S.gy[0][a], S.gz[1][k],
-                             fma(sa[2] * S.gy[1][a], S.gz[0][k], fma(sa[3] * S.gy[1][a], S.gz[1][k], gE))));
+        int i = p / G, k = p - i * G;
+        double qxz = fma((S.A[i][0] + S.A[i][2]) * Gy, S.gz[0][k], fma((S.A[i][1] + S.A[i][3]) * Gy, S.gz[1][k], gE));
         accxz += rvl_xlogx<FAST>(qxz);
-        accyz += rvl_xlogx<FAST>(qyz);
     }
     double accz = 0.0;
     if (lane < G) {
         double qz = fma((sa[0] + sa[2]) * Gy, S.gz[0][lane], fma((sa[1] + sa[3]) * Gy, S.gz[1][lane], (double)GG * epsq));
         accz = rvl_xlogx<FAST>(qz);
     }
-    double Lxz = rvl_warp_sum(accxz), Lyz = rvl_warp_sum(accyz), Lz = rvl_warp_sum(accz);
-    double Stot = (sa[0] + sa[1] + sa[2] + sa[3]) * Gy * Gz + (double)GG * (double)G * epsq;
+    double Lxz = rvl_warp_sum(accxz), Lz = rvl_warp_sum(accz);
     return (L3 - Lxz - Lyz + Lz) / Stot;
 }
 
@@ -210,8 +214,8 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
     __syncwarp();
     double epsq = RVL_DBL_EPS * (dn * RVL_TWO_PI * sqrt(RVL_TWO_PI) * hx * hy * hz);
     // every Q lies in [eps', 4 n G^3]: normal doubles unless eps' itself is tiny (degenerate bandwidths)
-    double cmi = (epsq >= 1e-290) ? rvl_cmi_epilogue<true>(S, G, epsq, lane, nlive_out)
-                                  : rvl_cmi_epilogue<false>(S, G, epsq, lane, nlive_out);
+    double cmi = (epsq >= 1e-290) ? rvl_cmi_epilogue<true>(S, G, epsq, P.prune_theta, lane, nlive_out)
+                                  : rvl_cmi_epilogue<false>(S, G, epsq, P.prune_theta, lane, nlive_out);
     return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * cmi));
 }
 
@@ -247,13 +251,25 @@ k_ttable(RvlParams P, const RvlTarget *__restrict__ tg_all, const double *__rest
     const double beta = (m == P.tt_pad) ? beta0 : beta0 * exp(tau);
     const double *u = u_all + (size_t)t * P.n;
     const uint64_t *z = (tg.mode == RVL_MODE_CIC) ? seeds + (size_t)tg.seed_of * P.words : nullptr;
+    // samples staged through shared memory in chunks of 1024 (coalesced loads, then broadcast reads)
+    __shared__ double su[1024];
+    __shared__ uint64_t sz[16];
     double a0 = 0.0, a1 = 0.0;
     const double gi = (double)lane;
-    for (int s = warp; s < P.n; s += nwarps) {
-        double d = gi - u[s];
-        double e = exp(-beta * d * d);
-        bool zb = z ? ((z[s >> 6] >> (s & 63)) & 1ull) : false;
-        if (zb) a1 += e; else a0 += e;
+    for (int base = 0; base < P.n; base += 1024) {
+        const int cnt = min(1024, P.n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) su[i] = u[base + i];
+        if (threadIdx.x < 16) {
+            int w = (base >> 6) + threadIdx.x;
+            sz[threadIdx.x] = (z && w < P.words) ? z[w] : 0ull;
+        }
+        __syncthreads();
+        for (int s = warp; s < cnt; s += nwarps) {
+            double d = gi - su[s];
+            double e = exp(-beta * d * d);
+            if ((sz[s >> 6] >> (s & 63)) & 1ull) a1 += e; else a0 += e;
+        }
     }
     part[warp][0][lane] = a0;
     part[warp][1][lane] = a1;
@@ -306,16 +322,37 @@ __device__ __forceinline__ void rvl_tt_lookup(const RvlParams &P, const double *
     }
 }
 
+// "a is ahead of b" in R's stable order(decreasing = !negative): NaN last, ties by lower row.
+// (value, row) pairs under this relation form a total order, so reductions may be nested freely:
+// warp -> CTA (k_score) -> shard (k_argmax) -> world (k_merge) all give order()[1].
+__device__ __forceinline__ bool rvl_ahead(double va, int64_t ia, double vb, int64_t ib, int negative)
+{
+    if (ib < 0) return ia >= 0;
+    if (ia < 0) return false;
+    bool na = isnan(va), nb = isnan(vb);
+    if (na || nb) {
+        if (na && nb) return ia < ib;
+        return nb;
+    }
+    if (va != vb) return negative ? (va < vb) : (va > vb);
+    return ia < ib;
+}
+
 // ---- k_score --------------------------------------------------------------------------------
 // grid = (feature blocks, targets); block = RVL_SCORE_WARPS warps; each warp walks features
 // blockIdx.x*W + warp, += gridDim.x*W.  Dynamic smem: u[n] doubles, seed bit row, per-warp
-// scratch + bit row.
+// scratch + bit row.  Besides the score of every row, each CTA emits its best (score, local row)
+// into part[target][blockIdx.x] so that the rank step never re-reads the F scores.
 __global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
 k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict__ u_all,
         const double *__restrict__ xc_all, const RvlTarget *__restrict__ tg_all,
         const uint64_t *__restrict__ seeds, const double *__restrict__ bcvtab, const double *__restrict__ tt,
-        double *__restrict__ scores, unsigned long long *__restrict__ ctr)
+        double *__restrict__ scores, RvlCandHead *__restrict__ part, unsigned long long *__restrict__ ctr)
 {
+    __shared__ double part_v[RVL_SCORE_WARPS];
+    __shared__ long long part_i[RVL_SCORE_WARPS];
+    double best_v = 0.0;
+    int64_t best_i = -1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n, words = P.words, G = P.G;
     const int t = blockIdx.y;
@@ -358,6 +395,7 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
         __syncwarp();
         if (mode == RVL_MODE_ZERO || n1 == 0 || n1 == n) { // LIB:2507: constant x or y -> 0
             if (lane == 0) out[f] = 0.0;
+            if (rvl_ahead(0.0, f, best_v, best_i, P.negative)) { best_v = 0.0; best_i = f; }
             continue;
         }
         double rho = rvl_rho(s1c, n1, n, tg.sxx);
@@ -422,7 +460,19 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
                 atomicAdd(&ctr[2], (unsigned long long)nexp * G);  // x-axis exp() evaluations
             }
         }
+        if (rvl_ahead(score, f, best_v, best_i, P.negative)) { best_v = score; best_i = f; }
         __syncwarp();
+    }
+    // CTA-level best (every lane of a warp holds the same best_v / best_i)
+    if (lane == 0) { part_v[warp] = best_v; part_i[warp] = best_i; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < RVL_SCORE_WARPS; w++)
+            if (rvl_ahead(part_v[w], part_i[w], best_v, best_i, P.negative)) { best_v = part_v[w]; best_i = part_i[w]; }
+        RvlCandHead h;
+        h.score = best_v;
+        h.row = best_i;
+        part[(size_t)t * gridDim.x + blockIdx.x] = h;
     }
 }
 
@@ -519,46 +569,32 @@ __device__ double rvl_assoc_block(const RvlParams &P, const RvlTarget &tg, const
 __global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
 k_assoc(RvlParams P, const RvlTarget *__restrict__ tg_all, const int *__restrict__ target_of,
         const double *__restrict__ u_all, const double *__restrict__ xc_all, const uint64_t *__restrict__ y_all,
-        const double *__restrict__ bcvtab, double *__restrict__ out)
+        const double *__restrict__ bcvtab, double *__restrict__ out, size_t y_stride, size_t out_stride)
 {
     __shared__ RvlAssocShared sh;
     int q = blockIdx.x;
     int t = target_of ? target_of[q] : q;
     double v = rvl_assoc_block(P, tg_all[t], u_all + (size_t)t * P.n, xc_all + (size_t)t * P.n,
-                               y_all + (size_t)q * P.words, bcvtab, sh);
-    if (threadIdx.x == 0) out[q] = v;
+                               y_all + (size_t)q * y_stride, bcvtab, sh);
+    if (threadIdx.x == 0) out[(size_t)q * out_stride] = v;
 }
 
 // ---- rank: local best per target ---------------------------------------------------------------
 
-// "a is ahead of b" in R's stable order(decreasing = !negative): NaN last, ties by lower row.
-__device__ __forceinline__ bool rvl_ahead(double va, int64_t ia, double vb, int64_t ib, int negative)
-{
-    if (ib < 0) return ia >= 0;
-    if (ia < 0) return false;
-    bool na = isnan(va), nb = isnan(vb);
-    if (na || nb) {
-        if (na && nb) return ia < ib;
-        return nb;
-    }
-    if (va != vb) return negative ? (va < vb) : (va > vb);
-    return ia < ib;
-}
-
-// One block per target: scan the local scores, write the candidate record
-// [score][global row][bit row] into the send buffer.
-__global__ void k_argmax(RvlParams P, const double *__restrict__ scores, const uint64_t *__restrict__ bits,
-                         unsigned char *__restrict__ send, size_t rec_bytes)
+// One block per target: reduce the per-CTA bests k_score left in part[target][nparts] and write the
+// candidate record [score][global row][bit row] into the send buffer.
+__global__ void k_argmax(RvlParams P, const RvlCandHead *__restrict__ part, int nparts,
+                         const uint64_t *__restrict__ bits, unsigned char *__restrict__ send, size_t rec_bytes)
 {
     __shared__ double shv[32];
     __shared__ long long shi[32];
     int t = blockIdx.x;
-    const double *v = scores + (size_t)t * P.F;
+    const RvlCandHead *v = part + (size_t)t * nparts;
     double bv = 0.0;
     int64_t bi = -1;
-    for (int64_t k = threadIdx.x; k < P.F; k += blockDim.x) {
-        double x = v[k];
-        if (rvl_ahead(x, k, bv, bi, P.negative)) { bv = x; bi = k; }
+    for (int k = threadIdx.x; k < nparts; k += blockDim.x) {
+        RvlCandHead h = v[k];
+        if (rvl_ahead(h.score, h.row, bv, bi, P.negative)) { bv = h.score; bi = h.row; }
     }
     for (int o = 16; o > 0; o >>= 1) {
         double ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -591,13 +627,13 @@ __global__ void k_argmax(RvlParams P, const double *__restrict__ scores, const u
 // ---- merge: global winner, seed OR-merge, seed IC, next-iteration seed state ---------------------
 // recv holds `world` blocks of T records.  One block per target.  Every rank runs the same
 // deterministic resolution, so the seeds stay replicated without a second exchange.
-__global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
+// assoc(target, seed) of the merged seed (LIB:2170) is not needed by the next iteration: the host
+// side launches it as k_assoc on a side stream, reading the immutable seed_iter row written here.
+__global__ void __launch_bounds__(128)
 k_merge(RvlParams P, int iter, int iters, int first_null, const unsigned char *__restrict__ recv, size_t rec_bytes,
-        RvlTarget *tg_all, uint64_t *seeds, const double *__restrict__ u_all, const double *__restrict__ xc_all,
-        const double *__restrict__ bcvtab, int64_t *__restrict__ top, double *__restrict__ top_score,
-        uint64_t *__restrict__ seed_iter, double *__restrict__ cmi_seed)
+        uint64_t *seeds, int64_t *__restrict__ top, double *__restrict__ top_score,
+        uint64_t *__restrict__ seed_iter)
 {
-    __shared__ RvlAssocShared sh;
     __shared__ int win_rank;
     int t = blockIdx.x;
     bool is_null = (first_null > 0 && t >= first_null);
@@ -625,10 +661,6 @@ k_merge(RvlParams P, int iter, int iters, int first_null, const unsigned char *_
             z[i] = v;
             zi[i] = v;
         }
-        __syncthreads();
-        double ic = rvl_assoc_block(P, tg_all[t], u_all + (size_t)t * P.n, xc_all + (size_t)t * P.n, z, bcvtab, sh);
-        if (threadIdx.x == 0) cmi_seed[(size_t)t * iters + iter] = ic; // LIB:2170
-        __syncthreads();
     }
 }
 
@@ -728,10 +760,11 @@ extern "C" cudaError_t rvl_score_configure(size_t smem)
 extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits,
                                  const double *u_all, const double *xc_all, const RvlTarget *tg,
                                  const uint64_t *seeds, const double *bcvtab, const double *tt, double *scores,
-                                 unsigned long long *ctr, cudaStream_t st)
+                                 RvlCandHead *part, unsigned long long *ctr, cudaStream_t st)
 {
     dim3 grid(grid_x, P->T);
-    k_score<<<grid, RVL_SCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, ctr);
+    k_score<<<grid, RVL_SCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, part,
+                                                      ctr);
 }
 
 extern "C" void rvl_launch_ttable(const RvlParams *P, const RvlTarget *tg, const double *u_all,
@@ -768,24 +801,24 @@ extern "C" void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const ui
 
 extern "C" void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of,
                                  const double *u_all, const double *xc_all, const uint64_t *y_all,
-                                 const double *bcvtab, double *out, cudaStream_t st)
+                                 const double *bcvtab, double *out, size_t y_stride, size_t out_stride,
+                                 cudaStream_t st)
 {
-    k_assoc<<<npairs, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, target_of, u_all, xc_all, y_all, bcvtab, out);
+    k_assoc<<<npairs, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, target_of, u_all, xc_all, y_all, bcvtab, out, y_stride,
+                                                     out_stride);
 }
 
-extern "C" void rvl_launch_argmax(const RvlParams *P, const double *scores, const uint64_t *bits,
+extern "C" void rvl_launch_argmax(const RvlParams *P, const RvlCandHead *part, int nparts, const uint64_t *bits,
                                   unsigned char *send, size_t rec_bytes, cudaStream_t st)
 {
-    k_argmax<<<P->T, 1024, 0, st>>>(*P, scores, bits, send, rec_bytes);
+    k_argmax<<<P->T, 1024, 0, st>>>(*P, part, nparts, bits, send, rec_bytes);
 }
 
 extern "C" void rvl_launch_merge(const RvlParams *P, int iter, int iters, int first_null,
-                                 const unsigned char *recv, size_t rec_bytes, RvlTarget *tg, uint64_t *seeds,
-                                 const double *u_all, const double *xc_all, const double *bcvtab, int64_t *top,
-                                 double *top_score, uint64_t *seed_iter, double *cmi_seed, cudaStream_t st)
+                                 const unsigned char *recv, size_t rec_bytes, uint64_t *seeds, int64_t *top,
+                                 double *top_score, uint64_t *seed_iter, cudaStream_t st)
 {
-    k_merge<<<P->T, RVL_SCORE_WARPS * 32, 0, st>>>(*P, iter, iters, first_null, recv, rec_bytes, tg, seeds, u_all,
-                                                   xc_all, bcvtab, top, top_score, seed_iter, cmi_seed);
+    k_merge<<<P->T, 128, 0, st>>>(*P, iter, iters, first_null, recv, rec_bytes, seeds, top, top_score, seed_iter);
 }
 
 extern "C" void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols,

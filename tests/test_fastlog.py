@@ -22,11 +22,12 @@ def rvl_log_pos(q):
     r = r + r * e
     s = f * r
     z = s * s
-    p = np.full_like(z, 1.0 / 19.0)
-    for d in (17.0, 15.0, 13.0, 11.0, 9.0, 7.0, 5.0, 3.0):
-        p = p * z + 1.0 / d
-    s2 = s + s
-    return k * 0.6931471805599453094 + (s2 * z * p + s2)
+    lg = (6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+          1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01)
+    p = np.full_like(z, lg[6])
+    for c in lg[5::-1]:
+        p = p * z + c
+    return k * 0.6931471805599453094 + ((s * z) * p + (s + s))
 
 
 def test_fast_log_within_a_few_ulp():

@@ -336,6 +336,32 @@ def test_table_mode_equals_dense_mode(n, F, dense_rows):
             assert np.max(np.abs(a[big] - b[big]) / np.abs(b[big])) < 1e-10
 
 
+def test_column_pruning_stays_within_its_bound(oracle):
+    """Default pruning (theta = 1e-14) against the exact rule (theta = 0): CMI may move by at most
+    theta*(|log eps'|+1) ~ 4e-13, i.e. IC = sqrt(1-exp(-2 CMI)) by <= 4e-13/IC."""
+    w = _workload(400, 1500)
+    with _ctx() as ctx:
+        ctx.load_matrix(w["m2"])
+        ctx.set_targets(w["target"])
+        ctx.set_seed(w["seed"])
+        a = ctx.score_once()[0]
+        ca = ctx.counters(reset=True)
+        ctx.set_prune_theta(0.0)
+        b = ctx.score_once()[0]
+        cb = ctx.counters(reset=True)
+        with pytest.raises(Exception):
+            ctx.set_prune_theta(1e-3)
+    assert ca["live_columns"] < cb["live_columns"]
+    cmi_a = -0.5 * np.log1p(-a * a)
+    cmi_b = -0.5 * np.log1p(-b * b)
+    assert np.max(np.abs(cmi_a - cmi_b)) <= 1e-12
+    assert np.array_equal(np.sign(a), np.sign(b))
+    rows = np.arange(0, 1500, 10)
+    o = oracle.score_rows(w["target"], w["m2"][rows].astype(float), w["seed"].astype(float))
+    ok, err = score_close(a[rows], o)
+    assert ok, err
+
+
 # ------------------------------------------------------------------ target batches and the permutation null
 
 def test_target_batch_equals_individual_runs():
