@@ -23,15 +23,17 @@ void rvl_launch_bcv_binary_table(int n, double *table, cudaStream_t st);
 void rvl_launch_target_setup(const double *x_all, int n, int T, int G, RvlTarget *tg, double *u_all, double *xc_all,
                              int *bin_all, int *cnt_all, int *nonfinite, cudaStream_t st);
 size_t rvl_score_smem_bytes(int n, int words);
-cudaError_t rvl_score_configure(size_t smem);
+cudaError_t rvl_score_configure(size_t smem, int device, int *grid_out);
+int rvl_score_warps(void);
 void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits, const double *u_all,
                       const double *xc_all, const RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
-                      const double *tt, double *scores, RvlCandHead *part, unsigned long long *ctr, cudaStream_t st);
+                      const double *tt, double *scores, RvlCandHead *part, unsigned long long *work,
+                      unsigned long long *ctr, cudaStream_t st);
 void rvl_launch_ttable(const RvlParams *P, const RvlTarget *tg, const double *u_all, const uint64_t *seeds,
                        double *tt, cudaStream_t st);
 void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaStream_t st);
 void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
-                          cudaStream_t st);
+                          RvlCandHead *part, int nslots, unsigned long long *work, cudaStream_t st);
 void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of, const double *u_all,
                       const double *xc_all, const uint64_t *y_all, const double *bcvtab, double *out,
                       size_t y_stride, size_t out_stride, cudaStream_t st);
@@ -101,7 +103,10 @@ struct rvl_ctx {
     // per-CTA bests of the last k_score launch [T][score_grid_x]; side stream for the seed IC
     RvlCandHead *d_part = nullptr;
     size_t part_cap = 0;
-    int score_grid_x = 0;
+    int score_grid_x = 0; // persistent grid of k_score (SMs x resident CTAs)
+    size_t score_smem = 0;
+    unsigned long long *d_work = nullptr; // k_score's item counter
+    bool work_dirty = true;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool side_pending = false;
@@ -240,6 +245,7 @@ extern "C" void rvl_destroy(rvl_ctx *ctx)
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     dfree(ctx->d_part);
+    dfree(ctx->d_work);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -481,6 +487,28 @@ extern "C" int rvl_set_seed(rvl_ctx *ctx, const uint8_t *seed, int64_t n, int pe
 
 // ---- search ------------------------------------------------------------------------------------
 
+// Persistent-grid configuration of k_score for the current (n, T): shared memory, grid = SMs x
+// resident CTAs, the per-warp best slots and the work counter.
+static int configure_score(rvl_ctx *ctx)
+{
+    size_t smem = rvl_score_smem_bytes(ctx->n, ctx->words);
+    if (smem > 227 * 1024) return fail(ctx, RVL_ERR_ARG, "n=%d needs %zu B of shared memory per block (> 227 KB)", ctx->n, smem);
+    if (smem != ctx->score_smem || ctx->score_grid_x <= 0) {
+        int grid = 0;
+        CK(rvl_score_configure(smem, ctx->device, &grid));
+        ctx->score_smem = smem;
+        ctx->score_grid_x = grid;
+    }
+    size_t pneed = (size_t)ctx->T * (size_t)ctx->score_grid_x * rvl_score_warps();
+    if (pneed > ctx->part_cap) {
+        dfree(ctx->d_part);
+        CK(dalloc(&ctx->d_part, pneed));
+        ctx->part_cap = pneed;
+    }
+    if (!ctx->d_work) CK(dalloc(&ctx->d_work, 1));
+    return RVL_OK;
+}
+
 // Per-iteration seed state + the x-axis table that depends on it.
 static int prep_iteration(rvl_ctx *ctx)
 {
@@ -491,7 +519,11 @@ static int prep_iteration(rvl_ctx *ctx)
         CK(dalloc(&ctx->d_tt, need));
         ctx->tt_cap = need;
     }
-    rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->stream);
+    int rc = configure_score(ctx);
+    if (rc) return rc;
+    rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->d_part, ctx->score_grid_x * rvl_score_warps(),
+                         ctx->d_work, ctx->stream);
+    ctx->work_dirty = false;
     ctx->launches++;
     if (!ctx->dense_x) {
         rvl_launch_ttable(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_tt, ctx->stream);
@@ -549,20 +581,7 @@ static int ensure_results(rvl_ctx *ctx, int iters)
 static int launch_score(rvl_ctx *ctx, double *base)
 {
     RvlParams P = make_params(ctx);
-    size_t smem = rvl_score_smem_bytes(ctx->n, ctx->words);
-    if (smem > 227 * 1024) return fail(ctx, RVL_ERR_ARG, "n=%d needs %zu B of shared memory per block (> 227 KB)", ctx->n, smem);
-    CK(rvl_score_configure(smem));
-    if (ctx->F == 0) return RVL_OK;
-    int64_t per_block = 8 * 4; // RVL_SCORE_WARPS warps x 4 rows each: the hardware block scheduler balances the tail
-    int64_t gx = (ctx->F + per_block - 1) / per_block;
-    if (gx > 65535 * 16) gx = 65535 * 16;
-    size_t pneed = (size_t)ctx->T * (size_t)gx;
-    if (pneed > ctx->part_cap) {
-        dfree(ctx->d_part);
-        CK(dalloc(&ctx->d_part, pneed));
-        ctx->part_cap = pneed;
-    }
-    ctx->score_grid_x = (int)gx;
+    if (ctx->F == 0) return RVL_OK; // k_seed_prep already left every best slot at "none"
     if (ctx->score_events_used == ctx->score_events.size()) {
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));
@@ -570,9 +589,11 @@ static int launch_score(rvl_ctx *ctx, double *base)
         ctx->score_events.push_back({a, b});
     }
     auto &ev = ctx->score_events[ctx->score_events_used++];
+    if (ctx->work_dirty) CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned long long), ctx->stream));
+    ctx->work_dirty = true; // k_seed_prep re-arms the counter; a repeated launch without it must do so here
     CK(cudaEventRecord(ev.first, ctx->stream));
-    rvl_launch_score(&P, (int)gx, smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab,
-                     ctx->d_tt, base, ctx->d_part, ctx->d_ctr, ctx->stream);
+    rvl_launch_score(&P, ctx->score_grid_x, ctx->score_smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed,
+                     ctx->d_bcvtab, ctx->d_tt, base, ctx->d_part, ctx->d_work, ctx->d_ctr, ctx->stream);
     CK(cudaEventRecord(ev.second, ctx->stream));
     ctx->launches++;
     CK(cudaGetLastError());
@@ -640,7 +661,7 @@ extern "C" int rvl_iter_score(rvl_ctx *ctx, int iter)
     int rc = launch_score(ctx, ctx->d_scores + (size_t)iter * ctx->T * ctx->F);
     if (rc) return rc;
     RvlParams P2 = make_params(ctx);
-    rvl_launch_argmax(&P2, ctx->d_part, ctx->F > 0 ? ctx->score_grid_x : 0, ctx->d_bits, ctx->d_send,
+    rvl_launch_argmax(&P2, ctx->d_part, ctx->score_grid_x * rvl_score_warps(), ctx->d_bits, ctx->d_send,
                       sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());

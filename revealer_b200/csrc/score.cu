@@ -100,7 +100,7 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, double
 
     // L3 = sum over all cells of Q log Q;  Lyz = sum over (j,k) of Q_jk log Q_jk with
     // Q_jk = sum_i Q_ijk in closed form (skipped columns: Q_jk = G eps' to rounding)
-    double acc0 = 0.0, acc1 = 0.0, accyz = 0.0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0, accyz = 0.0;
     const double gE = (double)G * epsq;
     for (int idx = lane; idx < nlive; idx += 32) {
         int p = S.live[idx];
@@ -109,21 +109,27 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, double
         double w10 = S.gy[1][j] * S.gz[0][k], w11 = S.gy[1][j] * S.gz[1][k];
         double qyz = fma(sa[0], w00, fma(sa[1], w01, fma(sa[2], w10, fma(sa[3], w11, gE))));
         accyz = fma(qyz, rvl_logq<FAST>(qyz), accyz);
+        // four independent logs in flight per lane (the FP64 chains are ~16 dependent ops long)
+#define RVL_CELL(ii) fma(S.A[ii][0], w00, fma(S.A[ii][1], w01, fma(S.A[ii][2], w10, fma(S.A[ii][3], w11, epsq))))
         int i = 0;
-        for (; i + 1 < G; i += 2) {
-            double q0 = fma(S.A[i][0], w00, fma(S.A[i][1], w01, fma(S.A[i][2], w10, fma(S.A[i][3], w11, epsq))));
-            double q1 = fma(S.A[i + 1][0], w00,
-                            fma(S.A[i + 1][1], w01, fma(S.A[i + 1][2], w10, fma(S.A[i + 1][3], w11, epsq))));
-            acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
-            acc1 = fma(q1, rvl_logq<FAST>(q1), acc1);
+#pragma unroll 1
+        for (; i + 3 < G; i += 4) {
+            double q0 = RVL_CELL(i), q1 = RVL_CELL(i + 1), q2 = RVL_CELL(i + 2), q3 = RVL_CELL(i + 3);
+            double l0 = rvl_logq<FAST>(q0), l1 = rvl_logq<FAST>(q1), l2 = rvl_logq<FAST>(q2), l3 = rvl_logq<FAST>(q3);
+            acc0 = fma(q0, l0, acc0);
+            acc1 = fma(q1, l1, acc1);
+            acc2 = fma(q2, l2, acc2);
+            acc3 = fma(q3, l3, acc3);
         }
-        if (i < G) {
-            double q0 = fma(S.A[i][0], w00, fma(S.A[i][1], w01, fma(S.A[i][2], w10, fma(S.A[i][3], w11, epsq))));
+#pragma unroll 1
+        for (; i < G; i++) {
+            double q0 = RVL_CELL(i);
             acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
         }
+#undef RVL_CELL
     }
     const double ndead = (double)(GG - nlive);
-    double L3 = rvl_warp_sum(acc0 + acc1) + ndead * (double)G * rvl_xlogx<FAST>(epsq);
+    double L3 = rvl_warp_sum((acc0 + acc1) + (acc2 + acc3)) + ndead * (double)G * rvl_xlogx<FAST>(epsq);
     double Lyz = rvl_warp_sum(accyz) + ndead * rvl_xlogx<FAST>(gE);
 
     // marginals: Q_ik (XZ), Q_k (Z)
@@ -339,43 +345,59 @@ __device__ __forceinline__ bool rvl_ahead(double va, int64_t ia, double vb, int6
 }
 
 // ---- k_score --------------------------------------------------------------------------------
-// grid = (feature blocks, targets); block = RVL_SCORE_WARPS warps; each warp walks features
-// blockIdx.x*W + warp, += gridDim.x*W.  Dynamic smem: u[n] doubles, seed bit row, per-warp
-// scratch + bit row.  Besides the score of every row, each CTA emits its best (score, local row)
-// into part[target][blockIdx.x] so that the rank step never re-reads the F scores.
+// Persistent kernel: grid = SMs x resident CTAs, block = RVL_SCORE_WARPS warps.  Every warp is an
+// independent worker: it draws the next (target, row) item from a global counter (target-major, so
+// neighbouring items share the target's small arrays in L1), scores it, and keeps its running best per
+// target.  No block barrier anywhere: evaluation cost varies with the number of live density columns,
+// and a barrier or a static row split would leave FP64 pipes idle at every CTA tail.
+// Dynamic smem: per-warp scratch + the row's bits.  Besides the score of every row, each warp leaves
+// its best (score, local row) per target in part[target][global warp id] (pre-set to "none" by
+// k_seed_prep) so that the rank step never re-reads the F scores.
 __global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
 k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict__ u_all,
         const double *__restrict__ xc_all, const RvlTarget *__restrict__ tg_all,
         const uint64_t *__restrict__ seeds, const double *__restrict__ bcvtab, const double *__restrict__ tt,
-        double *__restrict__ scores, RvlCandHead *__restrict__ part, unsigned long long *__restrict__ ctr)
+        double *__restrict__ scores, RvlCandHead *__restrict__ part, unsigned long long *__restrict__ work,
+        unsigned long long *__restrict__ ctr)
 {
-    __shared__ double part_v[RVL_SCORE_WARPS];
-    __shared__ long long part_i[RVL_SCORE_WARPS];
-    double best_v = 0.0;
-    int64_t best_i = -1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n, words = P.words, G = P.G;
-    const int t = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * RVL_SCORE_WARPS + warp, nslots = gridDim.x * RVL_SCORE_WARPS;
 
-    // 16-byte aligned scratch first; the 8-byte arrays follow
     RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
     uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_SCORE_WARPS);
-    uint64_t *zrow = yrows + (size_t)RVL_SCORE_WARPS * words;
-    double *u = reinterpret_cast<double *>(zrow + words);
     RvlWarpScratch &S = scr[warp];
     uint64_t *yrow = yrows + (size_t)warp * words;
 
-    const RvlTarget tg = tg_all[t];
-    const double *xc = xc_all + (size_t)t * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) u[i] = u_all[(size_t)t * n + i];
-    for (int i = threadIdx.x; i < words; i += blockDim.x) zrow[i] = seeds[(size_t)tg.seed_of * words + i];
-    __syncthreads();
+    const unsigned long long total = (unsigned long long)P.F * (unsigned long long)P.T;
+    int t = -1, mode = RVL_MODE_ZERO;
+    RvlTarget tg;
+    const double *xc = nullptr, *u = nullptr;
+    const uint64_t *zrow = nullptr;
+    double *out = nullptr;
+    double best_v = 0.0;
+    int64_t best_i = -1;
 
-    const int mode = tg.mode;
-    double *out = scores + (size_t)t * P.F;
-
-    for (int64_t f = (int64_t)blockIdx.x * RVL_SCORE_WARPS + warp; f < P.F; f += (int64_t)gridDim.x * RVL_SCORE_WARPS) {
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(work, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        const int it = (int)(item / (unsigned long long)P.F);
+        const int64_t f = (int64_t)(item - (unsigned long long)it * (unsigned long long)P.F);
+        if (it != t) { // new target: flush the running best, switch the per-target pointers
+            if (t >= 0 && lane == 0) { RvlCandHead h; h.score = best_v; h.row = best_i; part[(size_t)t * nslots + slot] = h; }
+            t = it;
+            tg = tg_all[t];
+            mode = tg.mode;
+            xc = xc_all + (size_t)t * n;
+            u = u_all + (size_t)t * n;
+            zrow = seeds + (size_t)tg.seed_of * words;
+            out = scores + (size_t)t * P.F;
+            best_v = 0.0;
+            best_i = -1;
+        }
         // bit row -> smem, popcount, masked target sum
         const uint64_t *row = bits + (size_t)f * words;
         int n1 = 0;
@@ -463,17 +485,8 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
         if (rvl_ahead(score, f, best_v, best_i, P.negative)) { best_v = score; best_i = f; }
         __syncwarp();
     }
-    // CTA-level best (every lane of a warp holds the same best_v / best_i)
-    if (lane == 0) { part_v[warp] = best_v; part_i[warp] = best_i; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < RVL_SCORE_WARPS; w++)
-            if (rvl_ahead(part_v[w], part_i[w], best_v, best_i, P.negative)) { best_v = part_v[w]; best_i = part_i[w]; }
-        RvlCandHead h;
-        h.score = best_v;
-        h.row = best_i;
-        part[(size_t)t * gridDim.x + blockIdx.x] = h;
-    }
+    // every lane of a warp holds the same best_v / best_i
+    if (t >= 0 && lane == 0) { RvlCandHead h; h.score = best_v; h.row = best_i; part[(size_t)t * nslots + slot] = h; }
 }
 
 // ---- seed state ------------------------------------------------------------------------------
@@ -500,10 +513,19 @@ __device__ void rvl_seed_prep_block(const RvlParams &P, RvlTarget *tg_all, const
     __syncthreads();
 }
 
-__global__ void k_seed_prep(RvlParams P, RvlTarget *tg_all, const uint64_t *seeds, const double *bcvtab)
+// Also re-arms the next k_score launch: work counter to zero, every per-warp best slot to "none".
+__global__ void k_seed_prep(RvlParams P, RvlTarget *tg_all, const uint64_t *seeds, const double *bcvtab,
+                            RvlCandHead *part, int nslots, unsigned long long *work)
 {
     __shared__ int sh_i[32];
     rvl_seed_prep_block(P, tg_all, seeds, bcvtab, blockIdx.x, sh_i);
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
+        RvlCandHead h;
+        h.score = 0.0;
+        h.row = -1;
+        part[(size_t)blockIdx.x * nslots + i] = h;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *work = 0ull;
 }
 
 // assoc(x_t, y, "IC") by one block (8 warps): warps split the samples, lanes own grid points.
@@ -748,23 +770,35 @@ __global__ void k_pvalues(const double *__restrict__ cmi, int64_t F, const doubl
 
 extern "C" size_t rvl_score_smem_bytes(int n, int words)
 {
-    return sizeof(double) * (size_t)n + sizeof(uint64_t) * (size_t)words +
-           sizeof(RvlWarpScratch) * RVL_SCORE_WARPS + sizeof(uint64_t) * (size_t)words * RVL_SCORE_WARPS;
+    (void)n;
+    return sizeof(RvlWarpScratch) * RVL_SCORE_WARPS + sizeof(uint64_t) * (size_t)words * RVL_SCORE_WARPS;
 }
 
-extern "C" cudaError_t rvl_score_configure(size_t smem)
+// Sets the dynamic shared memory limit and returns the persistent grid: SMs x resident CTAs per SM.
+extern "C" cudaError_t rvl_score_configure(size_t smem, int device, int *grid_out)
 {
-    return cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score, RVL_SCORE_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    *grid_out = sms * per_sm;
+    return cudaSuccess;
 }
+
+extern "C" int rvl_score_warps(void) { return RVL_SCORE_WARPS; }
 
 extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits,
                                  const double *u_all, const double *xc_all, const RvlTarget *tg,
                                  const uint64_t *seeds, const double *bcvtab, const double *tt, double *scores,
-                                 RvlCandHead *part, unsigned long long *ctr, cudaStream_t st)
+                                 RvlCandHead *part, unsigned long long *work, unsigned long long *ctr,
+                                 cudaStream_t st)
 {
-    dim3 grid(grid_x, P->T);
-    k_score<<<grid, RVL_SCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, part,
-                                                      ctr);
+    k_score<<<grid_x, RVL_SCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, part,
+                                                        work, ctr);
 }
 
 extern "C" void rvl_launch_ttable(const RvlParams *P, const RvlTarget *tg, const double *u_all,
@@ -794,9 +828,10 @@ extern "C" void rvl_launch_fp64_peak(int blocks, int threads, int iters, double 
 }
 
 extern "C" void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const uint64_t *seeds,
-                                     const double *bcvtab, cudaStream_t st)
+                                     const double *bcvtab, RvlCandHead *part, int nslots, unsigned long long *work,
+                                     cudaStream_t st)
 {
-    k_seed_prep<<<P->T, 128, 0, st>>>(*P, tg, seeds, bcvtab);
+    k_seed_prep<<<P->T, 128, 0, st>>>(*P, tg, seeds, bcvtab, part, nslots, work);
 }
 
 extern "C" void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of,
