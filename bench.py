@@ -33,8 +33,8 @@ UNIT = "evaluations/s"
 
 # FP64 work convention for the roofline numerator (DESIGN.md "Roofline"): FP64-pipe instructions
 # the kernel issues per transcendental, counted in the SASS of this build (profiles/), 2 flop each.
-FLOP_PER_EXP = 2 * 18
-FLOP_PER_LOG = 2 * 24
+FLOP_PER_EXP = 2 * 18   # CUDA exp(): 14 DFMA + 2 DMUL + 2 DADD in the SASS of score.o
+FLOP_PER_LOG = 2 * 18   # rvl_log_pos: 12 DFMA + 3 DMUL + 3 DADD (rvl_common.cuh)
 
 
 def parse():
@@ -282,9 +282,13 @@ def main():
         dur = k_ms / k_n * 1e-3                                   # average launch duration (s)
         evals = ctr["kde_evaluations"] / k_n
         G = 25
-        logs = (ctr["live_columns"] * G) / k_n + evals * (2 * G * G + G)
-        exps = ctr["dense_exps"] / k_n + evals * 2 * G
-        plain = (ctr["live_columns"] * G * 10 + ctr["dense_exps"] * 6) / k_n + evals * (2 * G * G * 12)
+        direct = ctr["live_columns"] / k_n            # (j,k) columns evaluated cell by cell
+        fact = ctr["factorised_columns"] / k_n        # (j,k) columns in the O(1) factorised form
+        # per evaluation (score.cu, rvl_cmi_epilogue_f): pass A 2 G^2 logs, pass B one log per non-dead
+        # column, pass C G logs per direct column, G for the z marginal, 1 in the table lookup
+        logs = evals * (2 * G * G + G + 1) + direct * (G + 1) + fact
+        exps = ctr["dense_exps"] / k_n + evals * (2 * G + 1)
+        plain = evals * (G * G * 18 + G * G * 24 + 80) + direct * G * 10 + ctr["dense_exps"] / k_n * 6
         flops = exps * FLOP_PER_EXP + logs * FLOP_PER_LOG + plain
         words = ((n + 63) // 64 + 1) & ~1
         bytes_alg = cnt * T * (words * 8 + 8)

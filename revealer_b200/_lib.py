@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "librevealer_b200.so")
+SO_PATH = os.environ.get("RVL_LIB") or os.path.join(HERE, "librevealer_b200.so")  # RVL_LIB: tuning builds only
 
 RVL_OK = 0
 RVL_ERR_CUDA = -1

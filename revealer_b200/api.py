@@ -279,7 +279,8 @@ class RevealerContext:
     def counters(self, reset=False):
         out = (C.c_uint64 * 4)()
         self._ck(self._lib.rvl_get_counters(self._h, out, int(reset)))
-        return dict(kde_evaluations=int(out[0]), live_columns=int(out[1]), dense_exps=int(out[2]))
+        return dict(kde_evaluations=int(out[0]), live_columns=int(out[1]), dense_exps=int(out[2]),
+                    factorised_columns=int(out[3]))
 
     def measure_fp64_peak(self):
         out = C.c_double()

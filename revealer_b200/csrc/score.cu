@@ -148,6 +148,127 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, double
     return (L3 - Lxz - Lyz + Lz) / Stot;
 }
 
+// 3-D epilogue, production form.  Same quantity as rvl_cmi_epilogue, organised around the majority
+// y-class `am` (the class holding most samples; a = 0 for the usual sparse alteration row):
+//   Q_ijk = g_M[j] * V_k[i] + g_m[j] * W_k[i] + eps',   V_k[i] = A_{am,0}[i] gz_0[k] + A_{am,1}[i] gz_1[k]
+// (W likewise for the minority class).  Pass A (lanes = k) builds V, W once per (i,k) and takes the
+// x-z marginal log there.  Pass B (lanes = k, loop over j) sorts every (j,k) column into
+//   dead        largest possible density below the pruning threshold  -> constant G eps' log eps'
+//   factorised  minority term cannot change fl(Q) (g_m maxW <= 2^-54 (g_M minV + eps')) and
+//               eps' <= g_M minV / 16: then sum_i Q log Q = g (log g * SV + LV) + eps' (G log g + LLV + G)
+//               with SV = sum V, LV = sum V log V, LLV = sum log V from pass A and log g known in closed
+//               form.  This is (a + e) log(a + e) expanded to first order in e = eps'; the neglected
+//               part is < eps'/32 per cell, i.e. < G^3 eps' / (32 S) ~ 1e-16 on CMI -- O(1) per column
+//   direct      everything else: G cells, one log each (pass C, lanes = columns, 4 logs in flight)
+// For a sparse row every column on the majority side of the y axis is factorised, which removes
+// roughly half of the logs.
+template <bool FAST>
+__device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, double theta, double hy, int am, int lane,
+                                     int *ndirect_out, int *nfact_out)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int M0 = am * 2, M1 = am * 2 + 1, m0 = (1 - am) * 2, m1 = (1 - am) * 2 + 1;
+    double sa[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) sa[c] = rvl_warp_sum((lane < G) ? S.A[lane][c] : 0.0);
+    const double Gy = rvl_warp_sum((lane < G) ? S.gy[0][lane] : 0.0);
+    const double Gz = rvl_warp_sum((lane < G) ? S.gz[0][lane] : 0.0);
+    const int GG = G * G;
+    const double gE = (double)G * epsq;
+    const double Stot = (sa[0] + sa[1] + sa[2] + sa[3]) * Gy * Gz + (double)GG * (double)G * epsq;
+    const double dead_thr = fmax(epsq * 0x1p-55, theta * Stot / ((double)GG * (double)G));
+    const bool active = lane < G;
+    const int kk = active ? lane : 0;
+    const double gz0 = S.gz[0][kk], gz1 = S.gz[1][kk];
+
+    // ---- pass A: per-k tables over i, and the x-z marginal
+    double SV = 0.0, LV = 0.0, LLV = 0.0, minV = INFINITY, maxV = 0.0, maxW = 0.0, accxz = 0.0;
+#pragma unroll 2
+    for (int i = 0; i < G; i++) {
+        const double V = fma(S.A[i][M0], gz0, S.A[i][M1] * gz1);
+        const double W = fma(S.A[i][m0], gz0, S.A[i][m1] * gz1);
+        minV = fmin(minV, V);
+        maxV = fmax(maxV, V);
+        maxW = fmax(maxW, W);
+        const double Vs = fmax(V, 1e-290); // keeps the fast log in range; such a column is never factorised
+        const double lv = rvl_logq<FAST>(Vs);
+        SV += V;
+        LV = fma(V, lv, LV);
+        LLV += lv;
+        const double qxz = fma(Gy, V + W, gE);
+        accxz = fma(qxz, rvl_logq<FAST>(qxz), accxz);
+    }
+    if (!active) accxz = 0.0;
+    const double sM = fma(sa[M0], gz0, sa[M1] * gz1), sm = fma(sa[m0], gz0, sa[m1] * gz1);
+
+    // ---- pass B: classify the G columns of this k, one j per round
+    double accF = 0.0, accyz = 0.0;
+    int ndirect = 0, nfact = 0, ndead = 0;
+    const double inv = 1.0 / ((double)(G - 1) * hy);
+#pragma unroll 1
+    for (int j = 0; j < G; j++) {
+        const double g0 = S.gy[0][j], g1 = S.gy[1][j];
+        const double gM = am ? g1 : g0, gm = am ? g0 : g1;
+        const double dmax = fma(gM, maxV, gm * maxW);
+        const bool dead = dmax < dead_thr;
+        const bool fact = !dead && (gm * maxW <= 0x1p-54 * fma(gM, minV, epsq)) && (gM * minV >= 16.0 * epsq);
+        if (active && !dead) {
+            const double qyz = fma(gM, sM, fma(gm, sm, gE));
+            accyz = fma(qyz, rvl_logq<FAST>(qyz), accyz);
+        }
+        if (active && fact) {
+            const double t = (double)(am ? (G - 1 - j) : j) * inv;
+            const double lg = -0.5 * t * t; // log g_M[j]
+            accF += fma(gM, fma(lg, SV, LV), epsq * (fma((double)G, lg, LLV) + (double)G));
+        }
+        const bool direct = active && !dead && !fact;
+        const unsigned md = __ballot_sync(FULL, direct);
+        if (direct) S.live[ndirect + __popc(md & ((1u << lane) - 1u))] = (uint16_t)(j * G + lane);
+        ndirect += __popc(md);
+        nfact += __popc(__ballot_sync(FULL, active && fact));
+        ndead += __popc(__ballot_sync(FULL, active && dead));
+    }
+    __syncwarp();
+    *ndirect_out = ndirect;
+    *nfact_out = nfact;
+
+    // ---- pass C: direct columns, lanes = columns
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    for (int idx = lane; idx < ndirect; idx += 32) {
+        const int p = S.live[idx];
+        const int j = p / G, k = p - j * G;
+        const double w00 = S.gy[0][j] * S.gz[0][k], w01 = S.gy[0][j] * S.gz[1][k];
+        const double w10 = S.gy[1][j] * S.gz[0][k], w11 = S.gy[1][j] * S.gz[1][k];
+#define RVL_CELL(ii) fma(S.A[ii][0], w00, fma(S.A[ii][1], w01, fma(S.A[ii][2], w10, fma(S.A[ii][3], w11, epsq))))
+        int i = 0;
+#pragma unroll 1
+        for (; i + 3 < G; i += 4) {
+            double q0 = RVL_CELL(i), q1 = RVL_CELL(i + 1), q2 = RVL_CELL(i + 2), q3 = RVL_CELL(i + 3);
+            double l0 = rvl_logq<FAST>(q0), l1 = rvl_logq<FAST>(q1), l2 = rvl_logq<FAST>(q2), l3 = rvl_logq<FAST>(q3);
+            acc0 = fma(q0, l0, acc0);
+            acc1 = fma(q1, l1, acc1);
+            acc2 = fma(q2, l2, acc2);
+            acc3 = fma(q3, l3, acc3);
+        }
+#pragma unroll 1
+        for (; i < G; i++) {
+            double q0 = RVL_CELL(i);
+            acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
+        }
+#undef RVL_CELL
+    }
+    const double L3 = rvl_warp_sum((acc0 + acc1) + (acc2 + acc3) + accF) + (double)ndead * (double)G * rvl_xlogx<FAST>(epsq);
+    const double Lyz = rvl_warp_sum(accyz) + (double)ndead * rvl_xlogx<FAST>(gE);
+    const double Lxz = rvl_warp_sum(accxz);
+    double accz = 0.0;
+    if (active) {
+        double qz = fma((sa[0] + sa[2]) * Gy, gz0, fma((sa[1] + sa[3]) * Gy, gz1, (double)GG * epsq));
+        accz = rvl_xlogx<FAST>(qz);
+    }
+    const double Lz = rvl_warp_sum(accz);
+    return (L3 - Lxz - Lyz + Lz) / Stot;
+}
+
 // 2-D epilogue (mutual.inf.v2, LIB:2536-2550): MI from B_a[i] = A[i][a*2] and gy.  Whole warp.
 template <bool FAST>
 __device__ double rvl_mi_epilogue(RvlWarpScratch &S, int G, double epsq, int lane)
@@ -200,10 +321,13 @@ __device__ __forceinline__ double rvl_rho(double s1c, int n1, int n, double sxx)
 // Finish one evaluation once A (dense sums) is in scratch.  Returns IC or CIC.
 // mode: RVL_MODE_IC (2-D) or RVL_MODE_CIC (3-D).  c is the bandwidth shrink factor already applied
 // to hx (beta); here it is applied to hy / hz.
+// am: majority y-class (0 unless the row has more ones than zeros).  nlive_out: columns evaluated
+// cell by cell; nfact_out: columns handled by the O(1) factorised form.
 __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, double rho, double c, double hx,
-                             double bcv_y, double bcv_z, int lane, int *nlive_out)
+                             double bcv_y, double bcv_z, int am, int lane, int *nlive_out, int *nfact_out)
 {
     *nlive_out = 0;
+    *nfact_out = 0;
     int G = P.G;
     double dn = (double)P.n;
     if (mode == RVL_MODE_IC) {
@@ -220,8 +344,10 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
     __syncwarp();
     double epsq = RVL_DBL_EPS * (dn * RVL_TWO_PI * sqrt(RVL_TWO_PI) * hx * hy * hz);
     // every Q lies in [eps', 4 n G^3]: normal doubles unless eps' itself is tiny (degenerate bandwidths)
-    double cmi = (epsq >= 1e-290) ? rvl_cmi_epilogue<true>(S, G, epsq, P.prune_theta, lane, nlive_out)
-                                  : rvl_cmi_epilogue<false>(S, G, epsq, P.prune_theta, lane, nlive_out);
+    double cmi;
+    if (epsq < 1e-290) cmi = rvl_cmi_epilogue<false>(S, G, epsq, P.prune_theta, lane, nlive_out);
+    else if (P.dense_x) cmi = rvl_cmi_epilogue<true>(S, G, epsq, P.prune_theta, lane, nlive_out); // literal mode
+    else cmi = rvl_cmi_epilogue_f<true>(S, G, epsq, P.prune_theta, hy, am, lane, nlive_out, nfact_out);
     return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * cmi));
 }
 
@@ -353,7 +479,10 @@ __device__ __forceinline__ bool rvl_ahead(double va, int64_t ia, double vb, int6
 // Dynamic smem: per-warp scratch + the row's bits.  Besides the score of every row, each warp leaves
 // its best (score, local row) per target in part[target][global warp id] (pre-set to "none" by
 // k_seed_prep) so that the rank step never re-reads the F scores.
-__global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
+#ifndef RVL_SCORE_MIN_CTAS
+#define RVL_SCORE_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(RVL_SCORE_WARPS * 32, RVL_SCORE_MIN_CTAS)
 k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict__ u_all,
         const double *__restrict__ xc_all, const RvlTarget *__restrict__ tg_all,
         const uint64_t *__restrict__ seeds, const double *__restrict__ bcvtab, const double *__restrict__ tt,
@@ -472,14 +601,15 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
             S.A[lane][0] = acc[0]; S.A[lane][1] = acc[1]; S.A[lane][2] = acc[2]; S.A[lane][3] = acc[3];
         }
         __syncwarp();
-        int nlive;
-        double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, lane, &nlive);
+        int nlive, nfact;
+        double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, n1 > n - n1 ? 1 : 0, lane, &nlive, &nfact);
         if (lane == 0) {
             out[f] = score;
             if (ctr) { // instrumentation: work actually executed (bench.py's roofline numerator)
                 atomicAdd(&ctr[0], 1ull);                          // evaluations that ran the KDE path
-                atomicAdd(&ctr[1], (unsigned long long)nlive);     // live (j,k) columns -> G logs each
+                atomicAdd(&ctr[1], (unsigned long long)nlive);     // (j,k) columns evaluated cell by cell
                 atomicAdd(&ctr[2], (unsigned long long)nexp * G);  // x-axis exp() evaluations
+                atomicAdd(&ctr[3], (unsigned long long)nfact);     // (j,k) columns in factorised form
             }
         }
         if (rvl_ahead(score, f, best_v, best_i, P.negative)) { best_v = score; best_i = f; }
@@ -581,8 +711,8 @@ __device__ double rvl_assoc_block(const RvlParams &P, const RvlTarget &tg, const
             sh.S.A[lane][0] = b0; sh.S.A[lane][1] = 0.0; sh.S.A[lane][2] = b1; sh.S.A[lane][3] = 0.0;
         }
         __syncwarp();
-        int nlive;
-        score = rvl_finish(sh.S, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, lane, &nlive);
+        int nlive, nfact;
+        score = rvl_finish(sh.S, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, 0, lane, &nlive, &nfact);
     }
     return score; // valid in warp 0
 }
