@@ -171,6 +171,13 @@ int rvl_set_dense_x(rvl_ctx *ctx, int on);
  * (about 4e-13 for the default theta = 1e-14, against the 1e-6 relative tolerance on scores).
  * theta = 0 keeps only the exact rule (columns that cannot change fl(density + eps)). */
 int rvl_set_prune_theta(rvl_ctx *ctx, double theta);
+/* Exact-duplicate rows (LIB:1727-1748 consolidates them by name pasting).  Identical
+ * rows have identical scores and R's stable order() ranks the first of them first, so by default
+ * only the first row of each group is scored and the others receive a copy of its score (grouping is
+ * done on the device at load time: hash, stable sort, exact compare).  on = 0 scores every row. */
+int rvl_set_dedup(rvl_ctx *ctx, int on);
+/* Number of distinct rows in the loaded shard. */
+int64_t rvl_unique_rows(const rvl_ctx *ctx);
 /* Work counters of the score kernel since the last reset: out4[0] evaluations that ran the KDE path,
  * out4[1] live (j,k) density columns (n_grid log() each), out4[2] dense-pass exp() evaluations. */
 int rvl_get_counters(rvl_ctx *ctx, uint64_t *out4, int reset);

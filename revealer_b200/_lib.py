@@ -66,6 +66,8 @@ SIGNATURES = {
     "rvl_score_kernel_time": (_i, [_vp, _dp, _i64p, _i]),
     "rvl_set_dense_x": (_i, [_vp, _i]),
     "rvl_set_prune_theta": (_i, [_vp, C.c_double]),
+    "rvl_set_dedup": (_i, [_vp, _i]),
+    "rvl_unique_rows": (_i64, [_vp]),
     "rvl_get_counters": (_i, [_vp, _u64p, _i]),
     "rvl_measure_fp64_peak": (_i, [_vp, _dp]),
 }

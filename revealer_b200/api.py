@@ -272,6 +272,13 @@ class RevealerContext:
         """Validation mode: literal per-feature x-axis sums over all samples (see rvl_set_dense_x)."""
         self._ck(self._lib.rvl_set_dense_x(self._h, int(bool(on))))
 
+    def set_dedup(self, on):
+        """Score only the first row of every group of identical rows (default on; see rvl_set_dedup)."""
+        self._ck(self._lib.rvl_set_dedup(self._h, int(bool(on))))
+
+    def unique_rows(self):
+        return int(self._lib.rvl_unique_rows(self._h))
+
     def set_prune_theta(self, theta):
         """Density-column pruning threshold of the 3-D epilogue (see rvl_set_prune_theta); 0 = exact rule only."""
         self._ck(self._lib.rvl_set_prune_theta(self._h, float(theta)))

@@ -16,6 +16,10 @@
 #include <thrust/execution_policy.h>
 #include <thrust/partition.h>
 #include <thrust/sort.h>
+#include <thrust/scan.h>
+#include <thrust/copy.h>
+#include <thrust/functional.h>
+#include <thrust/iterator/counting_iterator.h>
 
 // launchers (score.cu, bandwidth.cu)
 extern "C" {
@@ -28,7 +32,7 @@ int rvl_score_warps(void);
 void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits, const double *u_all,
                       const double *xc_all, const RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
                       const double *tt, double *scores, RvlCandHead *part, unsigned long long *work,
-                      unsigned long long *ctr, cudaStream_t st);
+                      unsigned long long *ctr, const int64_t *uniq, int64_t U, cudaStream_t st);
 void rvl_launch_ttable(const RvlParams *P, const RvlTarget *tg, const double *u_all, const uint64_t *seeds,
                        double *tt, cudaStream_t st);
 void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaStream_t st);
@@ -48,6 +52,11 @@ void rvl_launch_pack_u8_rowmajor(const uint8_t *m, int64_t F0, int64_t Fc, int n
                                  int *flag, cudaStream_t st);
 void rvl_launch_check_padding(const uint64_t *bits, int64_t F, int n, int words, int *flag, cudaStream_t st);
 void rvl_launch_row_counts(const uint64_t *bits, int64_t F, int words, int32_t *out, cudaStream_t st);
+void rvl_launch_row_hash(const uint64_t *bits, int64_t F, int words, uint64_t *hash, int64_t *idx, cudaStream_t st);
+void rvl_launch_dedup_heads(const uint64_t *hash, int64_t F, int64_t *headpos, cudaStream_t st);
+void rvl_launch_dedup_verify(const uint64_t *bits, int64_t F, int words, const int64_t *idx, const int64_t *headpos,
+                             int64_t *rep, cudaStream_t st);
+void rvl_launch_fill_duplicates(double *scores, int64_t F, int64_t rows, const int64_t *rep, cudaStream_t st);
 void rvl_launch_pvalues(const double *cmi, int64_t F, const double *rand_sorted, int64_t n_valid, int64_t n_rand,
                         double *pval, cudaStream_t st);
 }
@@ -68,6 +77,11 @@ struct rvl_ctx {
     int n = 0, words = 0;
     uint64_t *d_bits = nullptr;
     bool own_bits = true;
+    // exact-duplicate rows: rep[f] = first identical row; uniq = rows with rep[f] == f
+    int64_t *d_rep = nullptr, *d_uniq = nullptr;
+    int64_t U = 0;
+    int dedup = 1;
+    bool fill_pending = false; // duplicate rows of the score buffer not filled in yet
 
     // targets
     int T = 0;
@@ -214,6 +228,8 @@ static void free_matrix(rvl_ctx *c)
 {
     if (c->own_bits) dfree(c->d_bits);
     c->d_bits = nullptr;
+    dfree(c->d_rep); dfree(c->d_uniq);
+    c->U = 0;
     c->own_bits = true;
     c->F = -1;
 }
@@ -288,6 +304,49 @@ extern "C" int rvl_set_shard(rvl_ctx *ctx, int rank, int world, int64_t row_offs
 
 // ---- matrix ---------------------------------------------------------------------------------
 
+struct rvl_is_rep {
+    const int64_t *rep;
+    __host__ __device__ bool operator()(int64_t f) const { return rep[f] == f; }
+};
+
+// Group identical rows (hash -> stable sort -> exact compare); see score.cu "exact-duplicate rows".
+static int build_dedup(rvl_ctx *ctx)
+{
+    int64_t F = ctx->F;
+    dfree(ctx->d_rep); dfree(ctx->d_uniq);
+    ctx->U = F;
+    if (F <= 0) return RVL_OK;
+    uint64_t *d_hash = nullptr;
+    int64_t *d_idx = nullptr, *d_head = nullptr;
+    CK(dalloc(&ctx->d_rep, (size_t)F));
+    CK(dalloc(&ctx->d_uniq, (size_t)F));
+    CK(dalloc(&d_hash, (size_t)F));
+    CK(dalloc(&d_idx, (size_t)F));
+    CK(dalloc(&d_head, (size_t)F));
+    int rc = RVL_OK;
+    try {
+        auto pol = thrust::cuda::par.on(ctx->stream);
+        rvl_launch_row_hash(ctx->d_bits, F, ctx->words, d_hash, d_idx, ctx->stream);
+        thrust::stable_sort_by_key(pol, thrust::device_ptr<uint64_t>(d_hash), thrust::device_ptr<uint64_t>(d_hash) + F,
+                                   thrust::device_ptr<int64_t>(d_idx));
+        rvl_launch_dedup_heads(d_hash, F, d_head, ctx->stream);
+        thrust::inclusive_scan(pol, thrust::device_ptr<int64_t>(d_head), thrust::device_ptr<int64_t>(d_head) + F,
+                               thrust::device_ptr<int64_t>(d_head), thrust::maximum<int64_t>());
+        rvl_launch_dedup_verify(ctx->d_bits, F, ctx->words, d_idx, d_head, ctx->d_rep, ctx->stream);
+        rvl_is_rep pred{ctx->d_rep};
+        auto end = thrust::copy_if(pol, thrust::counting_iterator<int64_t>(0), thrust::counting_iterator<int64_t>(F),
+                                   thrust::device_ptr<int64_t>(ctx->d_uniq), pred);
+        ctx->U = end - thrust::device_ptr<int64_t>(ctx->d_uniq);
+        ctx->launches += 6;
+    } catch (...) {
+        rc = fail(ctx, RVL_ERR_CUDA, "duplicate-row grouping failed on the device");
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_hash); cudaFree(d_idx); cudaFree(d_head);
+    if (rc) free_matrix(ctx);
+    return rc;
+}
+
 static int begin_matrix(rvl_ctx *ctx, int64_t F, int64_t n)
 {
     if (F < 0 || n < 2 || n > (1 << 24)) return fail(ctx, RVL_ERR_ARG, "need F >= 0 and 2 <= n <= 2^24 (F=%lld n=%lld)", (long long)F, (long long)n);
@@ -338,8 +397,8 @@ extern "C" int rvl_load_matrix_f64_colmajor(rvl_ctx *ctx, const double *m2, int6
     cudaFree(stage);
     if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "pack: %s", cudaGetErrorString(e));
     rc = check_flag(ctx, "feature matrix has an entry that is not 0 or 1 (binary features only; no fallback)");
-    if (rc) free_matrix(ctx);
-    return rc;
+    if (rc) { free_matrix(ctx); return rc; }
+    return build_dedup(ctx);
 }
 
 extern "C" int rvl_load_matrix_u8_rowmajor(rvl_ctx *ctx, const uint8_t *m2, int64_t F, int64_t n)
@@ -368,8 +427,8 @@ extern "C" int rvl_load_matrix_u8_rowmajor(rvl_ctx *ctx, const uint8_t *m2, int6
     cudaFree(stage);
     if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "pack: %s", cudaGetErrorString(e));
     rc = check_flag(ctx, "feature matrix has an entry that is not 0 or 1 (binary features only; no fallback)");
-    if (rc) free_matrix(ctx);
-    return rc;
+    if (rc) { free_matrix(ctx); return rc; }
+    return build_dedup(ctx);
 }
 
 static int load_bits_common(rvl_ctx *ctx, const void *src, bool src_device, int64_t F, int64_t n, int64_t words)
@@ -390,8 +449,8 @@ static int load_bits_common(rvl_ctx *ctx, const void *src, bool src_device, int6
     rvl_launch_check_padding(ctx->d_bits, F, (int)n, ctx->words, ctx->d_flag, ctx->stream);
     ctx->launches++;
     rc = check_flag(ctx, "bit-packed matrix has non-zero padding bits beyond sample n");
-    if (rc) free_matrix(ctx);
-    return rc;
+    if (rc) { free_matrix(ctx); return rc; }
+    return build_dedup(ctx);
 }
 
 extern "C" int rvl_load_matrix_bits(rvl_ctx *ctx, const uint64_t *bits, int64_t F, int64_t n, int64_t words)
@@ -593,7 +652,9 @@ static int launch_score(rvl_ctx *ctx, double *base)
     ctx->work_dirty = true; // k_seed_prep re-arms the counter; a repeated launch without it must do so here
     CK(cudaEventRecord(ev.first, ctx->stream));
     rvl_launch_score(&P, ctx->score_grid_x, ctx->score_smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed,
-                     ctx->d_bcvtab, ctx->d_tt, base, ctx->d_part, ctx->d_work, ctx->d_ctr, ctx->stream);
+                     ctx->d_bcvtab, ctx->d_tt, base, ctx->d_part, ctx->d_work, ctx->d_ctr,
+                     (ctx->dedup && ctx->U < ctx->F) ? ctx->d_uniq : nullptr, ctx->U, ctx->stream);
+    ctx->fill_pending = ctx->dedup && ctx->U < ctx->F;
     CK(cudaEventRecord(ev.second, ctx->stream));
     ctx->launches++;
     CK(cudaGetLastError());
@@ -712,6 +773,11 @@ extern "C" int rvl_search_fetch(rvl_ctx *ctx, rvl_result *out)
     if (jrc) return jrc;
     CK(cudaStreamSynchronize(ctx->stream));
     drain_score_events(ctx);
+    if (ctx->fill_pending && ctx->F > 0) { // duplicate rows get their group's score, once, for all iterations
+        rvl_launch_fill_duplicates(ctx->d_scores, ctx->F, (int64_t)iters * T, ctx->d_rep, ctx->stream);
+        ctx->launches++;
+        ctx->fill_pending = false;
+    }
     if (out->cmi && ctx->F > 0) {
         // device layout [iters][T][F] -> caller layout [T][iters][F]
         for (int t = 0; t < T; t++)
@@ -765,6 +831,11 @@ extern "C" int rvl_score_once(rvl_ctx *ctx, double *out_scores)
     if (rc) return rc;
     rc = launch_score(ctx, ctx->d_scores);
     if (rc) return rc;
+    if (ctx->fill_pending && ctx->F > 0) {
+        rvl_launch_fill_duplicates(ctx->d_scores, ctx->F, (int64_t)ctx->T, ctx->d_rep, ctx->stream);
+        ctx->launches++;
+        ctx->fill_pending = false;
+    }
     if (out_scores && ctx->F > 0)
         CK(cudaMemcpyAsync(out_scores, ctx->d_scores, sizeof(double) * (size_t)ctx->T * ctx->F, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -941,3 +1012,12 @@ extern "C" int rvl_set_prune_theta(rvl_ctx *ctx, double theta)
     ctx->prune_theta = theta;
     return RVL_OK;
 }
+
+extern "C" int rvl_set_dedup(rvl_ctx *ctx, int on)
+{
+    GUARD();
+    ctx->dedup = on ? 1 : 0;
+    return RVL_OK;
+}
+
+extern "C" int64_t rvl_unique_rows(const rvl_ctx *ctx) { return ctx ? ctx->U : 0; }

@@ -487,8 +487,9 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
         const double *__restrict__ xc_all, const RvlTarget *__restrict__ tg_all,
         const uint64_t *__restrict__ seeds, const double *__restrict__ bcvtab, const double *__restrict__ tt,
         double *__restrict__ scores, RvlCandHead *__restrict__ part, unsigned long long *__restrict__ work,
-        unsigned long long *__restrict__ ctr)
+        unsigned long long *__restrict__ ctr, const int64_t *__restrict__ uniq, int64_t U)
 {
+    // uniq[0..U): the rows to score (first row of every group of identical rows); NULL = all F rows
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n, words = P.words, G = P.G;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -499,7 +500,8 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
     RvlWarpScratch &S = scr[warp];
     uint64_t *yrow = yrows + (size_t)warp * words;
 
-    const unsigned long long total = (unsigned long long)P.F * (unsigned long long)P.T;
+    const unsigned long long nrows = (unsigned long long)(uniq ? U : P.F);
+    const unsigned long long total = nrows * (unsigned long long)P.T;
     int t = -1, mode = RVL_MODE_ZERO;
     RvlTarget tg;
     const double *xc = nullptr, *u = nullptr;
@@ -513,8 +515,9 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
         if (lane == 0) item = atomicAdd(work, 1ull);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= total) break;
-        const int it = (int)(item / (unsigned long long)P.F);
-        const int64_t f = (int64_t)(item - (unsigned long long)it * (unsigned long long)P.F);
+        const int it = (int)(item / nrows);
+        const int64_t q = (int64_t)(item - (unsigned long long)it * nrows);
+        const int64_t f = uniq ? uniq[q] : q;
         if (it != t) { // new target: flush the running best, switch the per-target pointers
             if (t >= 0 && lane == 0) { RvlCandHead h; h.score = best_v; h.row = best_i; part[(size_t)t * nslots + slot] = h; }
             t = it;
@@ -879,6 +882,56 @@ __global__ void k_row_counts(const uint64_t *__restrict__ bits, int64_t F, int w
     out[k] = c;
 }
 
+// ---- exact-duplicate rows (amplicon blocks of identical rows are normal) --
+// Identical rows have identical scores, and R's stable order() ranks the lowest index first, so only the
+// first row of every group of identical rows is scored; the others receive a copy of its score.
+
+__global__ void k_row_hash(const uint64_t *__restrict__ bits, int64_t F, int words, uint64_t *__restrict__ hash,
+                           int64_t *__restrict__ idx)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F) return;
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (int w = 0; w < words; w++) {
+        h ^= bits[(size_t)k * words + w];
+        h *= 0xBF58476D1CE4E5B9ull;
+        h ^= h >> 29;
+    }
+    hash[k] = h;
+    idx[k] = k;
+}
+
+// After a stable sort by hash: position p is a group head when its hash differs from p-1's.
+__global__ void k_dedup_heads(const uint64_t *__restrict__ hash, int64_t F, int64_t *__restrict__ headpos)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= F) return;
+    headpos[p] = (p == 0 || hash[p] != hash[p - 1]) ? p : 0; // max-scanned into "position of my group's head"
+}
+
+// rep[row] = first row of the hash group if the bit rows really are equal, else the row itself.
+__global__ void k_dedup_verify(const uint64_t *__restrict__ bits, int64_t F, int words, const int64_t *__restrict__ idx,
+                               const int64_t *__restrict__ headpos, int64_t *__restrict__ rep)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= F) return;
+    int64_t row = idx[p], head = idx[headpos[p]];
+    bool same = true;
+    if (head != row)
+        for (int w = 0; w < words; w++) same = same && (bits[(size_t)row * words + w] == bits[(size_t)head * words + w]);
+    rep[row] = same ? head : row;
+}
+
+// scores[r][f] = scores[r][rep[f]] for every duplicate row f, over `rows` score vectors of length F.
+__global__ void k_fill_duplicates(double *__restrict__ scores, int64_t F, int64_t rows, const int64_t *__restrict__ rep)
+{
+    int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    int64_t r = rep[f];
+    if (r == f) return;
+    for (int64_t v = blockIdx.y; v < rows; v += gridDim.y) scores[(size_t)v * F + f] = scores[(size_t)v * F + r];
+}
+
 // Permutation p-values (LIB:1869): pval[i] = #(rand > cmi[i]) / n_rand with `rand` sorted ascending
 // and NaNs removed: count = n_valid - upper_bound(rand, cmi[i]).
 __global__ void k_pvalues(const double *__restrict__ cmi, int64_t F, const double *__restrict__ rand_sorted,
@@ -925,10 +978,10 @@ extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, co
                                  const double *u_all, const double *xc_all, const RvlTarget *tg,
                                  const uint64_t *seeds, const double *bcvtab, const double *tt, double *scores,
                                  RvlCandHead *part, unsigned long long *work, unsigned long long *ctr,
-                                 cudaStream_t st)
+                                 const int64_t *uniq, int64_t U, cudaStream_t st)
 {
     k_score<<<grid_x, RVL_SCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, part,
-                                                        work, ctr);
+                                                        work, ctr, uniq, U);
 }
 
 extern "C" void rvl_launch_ttable(const RvlParams *P, const RvlTarget *tg, const double *u_all,
@@ -1008,6 +1061,30 @@ extern "C" void rvl_launch_check_padding(const uint64_t *bits, int64_t F, int n,
 extern "C" void rvl_launch_row_counts(const uint64_t *bits, int64_t F, int words, int32_t *out, cudaStream_t st)
 {
     k_row_counts<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(bits, F, words, out);
+}
+
+extern "C" void rvl_launch_row_hash(const uint64_t *bits, int64_t F, int words, uint64_t *hash, int64_t *idx,
+                                    cudaStream_t st)
+{
+    k_row_hash<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(bits, F, words, hash, idx);
+}
+
+extern "C" void rvl_launch_dedup_heads(const uint64_t *hash, int64_t F, int64_t *headpos, cudaStream_t st)
+{
+    k_dedup_heads<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(hash, F, headpos);
+}
+
+extern "C" void rvl_launch_dedup_verify(const uint64_t *bits, int64_t F, int words, const int64_t *idx,
+                                        const int64_t *headpos, int64_t *rep, cudaStream_t st)
+{
+    k_dedup_verify<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(bits, F, words, idx, headpos, rep);
+}
+
+extern "C" void rvl_launch_fill_duplicates(double *scores, int64_t F, int64_t rows, const int64_t *rep,
+                                           cudaStream_t st)
+{
+    dim3 grid((unsigned)((F + 255) / 256), (unsigned)(rows < 1024 ? rows : 1024));
+    k_fill_duplicates<<<grid, 256, 0, st>>>(scores, F, rows, rep);
 }
 
 extern "C" void rvl_launch_pvalues(const double *cmi, int64_t F, const double *rand_sorted, int64_t n_valid,

@@ -336,6 +336,32 @@ def test_table_mode_equals_dense_mode(n, F, dense_rows):
             assert np.max(np.abs(a[big] - b[big]) / np.abs(b[big])) < 1e-10
 
 
+def test_duplicate_row_grouping_is_exact():
+    """Scoring only the first row of each group of identical rows (default) must give bit-identical
+    scores, winners and seeds to scoring every row; also with scattered (non-adjacent) duplicates and
+    with the all-zero / all-one guard rows."""
+    w = _workload(160, 900)
+    m2 = w["m2"].copy()
+    rng = np.random.default_rng(8)
+    src = rng.integers(0, 900, 60)
+    dst = rng.integers(0, 900, 60)
+    m2[dst] = m2[src]
+    uniq = len({r.tobytes() for r in m2})
+    outs = []
+    with _ctx() as ctx:
+        ctx.set_targets(np.stack([w["target"], rng.standard_normal(160)]))
+        ctx.set_seed(w["seed"])
+        for on in (True, False):
+            ctx.set_dedup(on)
+            ctx.load_matrix(m2)
+            assert ctx.unique_rows() == uniq
+            outs.append((ctx.score_once(), ctx.search(3)))
+    (sa, ra), (sb, rb_) = outs
+    assert np.array_equal(sa, sb)
+    for k in ("cmi", "top", "top_score", "seed_iter", "cmi_seed"):
+        assert np.array_equal(ra[k], rb_[k]), k
+
+
 def test_column_pruning_stays_within_its_bound(oracle):
     """Default pruning (theta = 1e-14) against the exact rule (theta = 0): CMI may move by at most
     theta*(|log eps'|+1) ~ 4e-13, i.e. IC = sqrt(1-exp(-2 CMI)) by <= 4e-13/IC."""
