@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -33,8 +34,9 @@ void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_
                       const double *xc_all, const RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
                       const double *tt, double *scores, RvlCandHead *part, unsigned long long *work,
                       unsigned long long *ctr, const int64_t *uniq, int64_t U, cudaStream_t st);
-void rvl_launch_ttable(const RvlParams *P, const RvlTarget *tg, const double *u_all, const uint64_t *seeds,
-                       double *tt, cudaStream_t st);
+void rvl_launch_ttable(const RvlParams *P, RvlTarget *tg, const double *u_all, const uint64_t *seeds,
+                       const double *bcvtab, double *tt, RvlCandHead *slots, int nslots, unsigned long long *work,
+                       cudaStream_t st);
 void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaStream_t st);
 void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
                           RvlCandHead *part, int nslots, unsigned long long *work, cudaStream_t st);
@@ -52,6 +54,8 @@ void rvl_launch_pack_u8_rowmajor(const uint8_t *m, int64_t F0, int64_t Fc, int n
                                  int *flag, cudaStream_t st);
 void rvl_launch_check_padding(const uint64_t *bits, int64_t F, int n, int words, int *flag, cudaStream_t st);
 void rvl_launch_row_counts(const uint64_t *bits, int64_t F, int words, int32_t *out, cudaStream_t st);
+void rvl_launch_rho_max(const RvlParams *P, const uint64_t *bits, const double *xc_all, RvlTarget *tg,
+                        const int64_t *uniq, int64_t U, cudaStream_t st);
 void rvl_launch_row_hash(const uint64_t *bits, int64_t F, int words, uint64_t *hash, int64_t *idx, cudaStream_t st);
 void rvl_launch_dedup_heads(const uint64_t *hash, int64_t F, int64_t *headpos, cudaStream_t st);
 void rvl_launch_dedup_verify(const uint64_t *bits, int64_t F, int words, const int64_t *idx, const int64_t *headpos,
@@ -82,6 +86,7 @@ struct rvl_ctx {
     int64_t U = 0;
     int dedup = 1;
     bool fill_pending = false; // duplicate rows of the score buffer not filled in yet
+    bool rho_dirty = true;     // RvlTarget.rho_*_max_bits must be recomputed (matrix or targets changed)
 
     // targets
     int T = 0;
@@ -230,6 +235,7 @@ static void free_matrix(rvl_ctx *c)
     c->d_bits = nullptr;
     dfree(c->d_rep); dfree(c->d_uniq);
     c->U = 0;
+    c->rho_dirty = true;
     c->own_bits = true;
     c->F = -1;
 }
@@ -239,6 +245,7 @@ static void free_targets(rvl_ctx *c)
     dfree(c->d_tg); dfree(c->d_seed0); dfree(c->d_seed); dfree(c->d_tt);
     c->tt_cap = 0;
     c->T = 0; c->have_seed = false;
+    c->rho_dirty = true;
 }
 static void free_results(rvl_ctx *c)
 {
@@ -580,14 +587,25 @@ static int prep_iteration(rvl_ctx *ctx)
     }
     int rc = configure_score(ctx);
     if (rc) return rc;
-    rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->d_part, ctx->score_grid_x * rvl_score_warps(),
-                         ctx->d_work, ctx->stream);
+    if (ctx->rho_dirty && !ctx->dense_x) { // range of the bandwidth shrink over the loaded rows (once per matrix/targets)
+        CK(cudaMemset2DAsync((char *)ctx->d_tg + offsetof(RvlTarget, rho_pos_max_bits), sizeof(RvlTarget), 0,
+                             2 * sizeof(unsigned long long), (size_t)ctx->T, ctx->stream));
+        if (ctx->F > 0) {
+            rvl_launch_rho_max(&P, ctx->d_bits, ctx->d_xc, ctx->d_tg, ctx->U < ctx->F ? ctx->d_uniq : nullptr, ctx->U,
+                               ctx->stream);
+            ctx->launches++;
+        }
+        ctx->rho_dirty = false;
+    }
+    const int nslots = ctx->score_grid_x * rvl_score_warps();
+    if (ctx->dense_x) { // literal mode has no table: the seed state gets its own small launch
+        rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->d_part, nslots, ctx->d_work, ctx->stream);
+    } else {
+        rvl_launch_ttable(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_bcvtab, ctx->d_tt, ctx->d_part, nslots,
+                          ctx->d_work, ctx->stream);
+    }
     ctx->work_dirty = false;
     ctx->launches++;
-    if (!ctx->dense_x) {
-        rvl_launch_ttable(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_tt, ctx->stream);
-        ctx->launches++;
-    }
     CK(cudaGetLastError());
     return RVL_OK;
 }

@@ -21,6 +21,9 @@ struct RvlTarget {
     int32_t is_const; // length(unique(x)) == 1              LIB:2495 / 2507
     int32_t seed_of;  // index of the target whose seed this target is scored against
                       // (itself, or 0 for permutation-null targets LIB:1853-1855)
+    // largest rho^+ and |rho| = cor(x, row) over the loaded rows (k_rho_max): bounds the range of the
+    // bandwidth shrink factor c, hence how many nodes of the x-axis table are ever read
+    unsigned long long rho_pos_max_bits, rho_abs_max_bits;
     // --- per iteration (written by k_seed_prep)
     int32_t nz;       // popcount(seed)
     int32_t mode;     // RVL_MODE_*

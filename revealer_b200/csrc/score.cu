@@ -318,6 +318,55 @@ __device__ __forceinline__ double rvl_rho(double s1c, int n1, int n, double sxx)
     return fmin(1.0, fmax(-1.0, r));
 }
 
+// One warp: popcount of a bit row and sum of the centred target over its set bits (fixed order: lane
+// owns words lane, lane+32, ...; then the shuffle tree).  Optionally copies the row to shared memory.
+__device__ __forceinline__ void rvl_row_stats(const uint64_t *__restrict__ row, int words, const double *__restrict__ xc,
+                                              int lane, uint64_t *yrow, int &n1, double &s1c)
+{
+    n1 = 0;
+    s1c = 0.0;
+    for (int w = lane; w < words; w += 32) {
+        uint64_t v = row[w];
+        if (yrow) yrow[w] = v;
+        n1 += __popcll(v);
+        while (v) {
+            int b = __ffsll((long long)v) - 1;
+            v &= v - 1;
+            s1c += xc[w * 64 + b];
+        }
+    }
+    n1 = rvl_warp_sum_i(n1);
+    s1c = rvl_warp_sum(s1c);
+}
+
+// Largest rho^+ and |rho| over the loaded rows, per target (non-negative doubles order like their bit
+// patterns, so atomicMax on the bits is exact).  grid = (row blocks, targets), one warp per row.
+__global__ void k_rho_max(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict__ xc_all,
+                          RvlTarget *tg_all, const int64_t *__restrict__ uniq, int64_t U)
+{
+    const int t = blockIdx.y, lane = threadIdx.x & 31;
+    const int64_t nrows = uniq ? U : P.F;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const double sxx = tg_all[t].sxx;
+    if (tg_all[t].is_const) return;
+    double pos = 0.0, ab = 0.0;
+    for (int64_t q = wid; q < nrows; q += nw) {
+        const int64_t f = uniq ? uniq[q] : q;
+        int n1;
+        double s1c;
+        rvl_row_stats(bits + (size_t)f * P.words, P.words, xc_all + (size_t)t * P.n, lane, nullptr, n1, s1c);
+        if (n1 == 0 || n1 == P.n) continue;
+        double r = rvl_rho(s1c, n1, P.n, sxx);
+        pos = fmax(pos, r);
+        ab = fmax(ab, fabs(r));
+    }
+    if (lane == 0) {
+        atomicMax(&tg_all[t].rho_pos_max_bits, (unsigned long long)__double_as_longlong(pos));
+        atomicMax(&tg_all[t].rho_abs_max_bits, (unsigned long long)__double_as_longlong(ab));
+    }
+}
+
 // Finish one evaluation once A (dense sums) is in scratch.  Returns IC or CIC.
 // mode: RVL_MODE_IC (2-D) or RVL_MODE_CIC (3-D).  c is the bandwidth shrink factor already applied
 // to hx (beta); here it is applied to hy / hz.
@@ -363,26 +412,60 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
 // Node tt_pad is tau = 0 exactly (c = 1: every feature with rho <= 0), so those use it unweighted.
 // Layout: tt[target][node][b][RVL_MAXG].
 
+// k_ttable also carries the per-iteration seed state (previously a separate launch): every block
+// recomputes popcount(seed) -> cond.assoc's dispatch (LIB:2507-2517); the block of node 0 publishes
+// it in RvlTarget, resets the target's per-warp best slots and (target 0) the k_score work counter.
 __global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
-k_ttable(RvlParams P, const RvlTarget *__restrict__ tg_all, const double *__restrict__ u_all,
-         const uint64_t *__restrict__ seeds, double *__restrict__ tt)
+k_ttable(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, const uint64_t *__restrict__ seeds,
+         const double *__restrict__ bcvtab, double *__restrict__ tt, RvlCandHead *__restrict__ slots, int nslots,
+         unsigned long long *__restrict__ work)
 {
     __shared__ double part[RVL_SCORE_WARPS][2][RVL_MAXG];
+    __shared__ int s_nz;
     const int t = blockIdx.y, m = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const RvlTarget tg = tg_all[t];
+    const uint64_t *zall = seeds + (size_t)tg.seed_of * P.words;
+    if (warp == 0) {
+        int c = 0;
+        for (int w = lane; w < P.words; w += 32) c += __popcll(zall[w]);
+        c = rvl_warp_sum_i(c);
+        if (lane == 0) s_nz = c;
+    }
+    __syncthreads();
+    const int nz = s_nz;
+    const int mode = tg.is_const ? RVL_MODE_ZERO : ((nz == 0 || nz == P.n) ? RVL_MODE_IC : RVL_MODE_CIC);
+    if (m == 0) {
+        if (threadIdx.x == 0) {
+            tg_all[t].nz = nz;
+            tg_all[t].bcv_z = bcvtab[nz];
+            tg_all[t].mode = mode;
+            if (t == 0) *work = 0ull;
+        }
+        for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
+            RvlCandHead h;
+            h.score = 0.0;
+            h.row = -1;
+            slots[(size_t)t * nslots + i] = h;
+        }
+    }
     double *out = tt + (((size_t)t * P.tt_nodes + m) * 2) * RVL_MAXG;
-    if (tg.mode == RVL_MODE_ZERO) {
+    if (mode == RVL_MODE_ZERO) {
         if (threadIdx.x < 2 * RVL_MAXG) out[threadIdx.x] = 0.0;
         return;
     }
-    const double hx0 = (tg.mode == RVL_MODE_IC) ? tg.bcv / 4 : P.bw_mult * tg.bcv;
+    // nodes beyond the largest shrink any loaded row can produce are never read (k_rho_max)
+    const double rmax = __longlong_as_double((long long)(mode == RVL_MODE_IC ? tg.rho_abs_max_bits : tg.rho_pos_max_bits));
+    const double cmin = 1.0 + P.bw_shrink * fmin(rmax * (1.0 + 1e-9) + 1e-12, 1.0);
+    const int needed = (int)ceil(-2.0 * log(cmin) / P.tt_dt) + 2 * P.tt_pad + 1;
+    if (m >= needed) return;
+    const double hx0 = (mode == RVL_MODE_IC) ? tg.bcv / 4 : P.bw_mult * tg.bcv;
     const double dx = (tg.xmax - tg.xmin) / (double)(P.G - 1);
     const double beta0 = 0.5 * (dx / hx0) * (dx / hx0);
     const double tau = (double)(m - P.tt_pad) * P.tt_dt;
     const double beta = (m == P.tt_pad) ? beta0 : beta0 * exp(tau);
     const double *u = u_all + (size_t)t * P.n;
-    const uint64_t *z = (tg.mode == RVL_MODE_CIC) ? seeds + (size_t)tg.seed_of * P.words : nullptr;
+    const uint64_t *z = (mode == RVL_MODE_CIC) ? zall : nullptr;
     // samples staged through shared memory in chunks of 1024 (coalesced loads, then broadcast reads)
     __shared__ double su[1024];
     __shared__ uint64_t sz[16];
@@ -397,9 +480,21 @@ k_ttable(RvlParams P, const RvlTarget *__restrict__ tg_all, const double *__rest
             sz[threadIdx.x] = (z && w < P.words) ? z[w] : 0ull;
         }
         __syncthreads();
-        for (int s = warp; s < cnt; s += nwarps) {
-            double d = gi - su[s];
-            double e = exp(-beta * d * d);
+        // four independent exp chains in flight per lane; fixed summation order (s ascending per warp)
+        int s = warp;
+        for (; s + 3 * nwarps < cnt; s += 4 * nwarps) {
+            const int s1 = s + nwarps, s2 = s + 2 * nwarps, s3 = s + 3 * nwarps;
+            const double d0 = gi - su[s], d1 = gi - su[s1], d2 = gi - su[s2], d3 = gi - su[s3];
+            const double e0 = exp(-beta * d0 * d0), e1 = exp(-beta * d1 * d1), e2 = exp(-beta * d2 * d2),
+                         e3 = exp(-beta * d3 * d3);
+            if ((sz[s >> 6] >> (s & 63)) & 1ull) a1 += e0; else a0 += e0;
+            if ((sz[s1 >> 6] >> (s1 & 63)) & 1ull) a1 += e1; else a0 += e1;
+            if ((sz[s2 >> 6] >> (s2 & 63)) & 1ull) a1 += e2; else a0 += e2;
+            if ((sz[s3 >> 6] >> (s3 & 63)) & 1ull) a1 += e3; else a0 += e3;
+        }
+        for (; s < cnt; s += nwarps) {
+            const double d = gi - su[s];
+            const double e = exp(-beta * d * d);
             if ((sz[s >> 6] >> (s & 63)) & 1ull) a1 += e; else a0 += e;
         }
     }
@@ -408,9 +503,9 @@ k_ttable(RvlParams P, const RvlTarget *__restrict__ tg_all, const double *__rest
     __syncthreads();
     if (threadIdx.x < 2 * RVL_MAXG) {
         int b = threadIdx.x >> 5;
-        double s = 0.0;
-        for (int w = 0; w < nwarps; w++) s += part[w][b][lane];
-        out[b * RVL_MAXG + lane] = s;
+        double sum = 0.0;
+        for (int w = 0; w < nwarps; w++) sum += part[w][b][lane];
+        out[b * RVL_MAXG + lane] = sum;
     }
 }
 
@@ -531,21 +626,9 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
             best_i = -1;
         }
         // bit row -> smem, popcount, masked target sum
-        const uint64_t *row = bits + (size_t)f * words;
-        int n1 = 0;
-        double s1c = 0.0;
-        for (int w = lane; w < words; w += 32) {
-            uint64_t v = row[w];
-            yrow[w] = v;
-            n1 += __popcll(v);
-            while (v) {
-                int b = __ffsll((long long)v) - 1;
-                v &= v - 1;
-                s1c += xc[w * 64 + b];
-            }
-        }
-        n1 = rvl_warp_sum_i(n1);
-        s1c = rvl_warp_sum(s1c);
+        int n1;
+        double s1c;
+        rvl_row_stats(bits + (size_t)f * words, words, xc, lane, yrow, n1, s1c);
         __syncwarp();
         if (mode == RVL_MODE_ZERO || n1 == 0 || n1 == n) { // LIB:2507: constant x or y -> 0
             if (lane == 0) out[f] = 0.0;
@@ -984,11 +1067,12 @@ extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, co
                                                         work, ctr, uniq, U);
 }
 
-extern "C" void rvl_launch_ttable(const RvlParams *P, const RvlTarget *tg, const double *u_all,
-                                  const uint64_t *seeds, double *tt, cudaStream_t st)
+extern "C" void rvl_launch_ttable(const RvlParams *P, RvlTarget *tg, const double *u_all, const uint64_t *seeds,
+                                  const double *bcvtab, double *tt, RvlCandHead *slots, int nslots,
+                                  unsigned long long *work, cudaStream_t st)
 {
     dim3 grid(P->tt_nodes, P->T);
-    k_ttable<<<grid, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, u_all, seeds, tt);
+    k_ttable<<<grid, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, u_all, seeds, bcvtab, tt, slots, nslots, work);
 }
 
 // FP64 FMA peak micro-benchmark (MEASURED_PEAKS.json has no FP64 figure): 8 independent DFMA chains
@@ -1061,6 +1145,17 @@ extern "C" void rvl_launch_check_padding(const uint64_t *bits, int64_t F, int n,
 extern "C" void rvl_launch_row_counts(const uint64_t *bits, int64_t F, int words, int32_t *out, cudaStream_t st)
 {
     k_row_counts<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(bits, F, words, out);
+}
+
+extern "C" void rvl_launch_rho_max(const RvlParams *P, const uint64_t *bits, const double *xc_all, RvlTarget *tg,
+                                   const int64_t *uniq, int64_t U, cudaStream_t st)
+{
+    int64_t nrows = uniq ? U : P->F;
+    if (nrows <= 0) return;
+    int64_t blocks = (nrows + 63) / 64; // 8 warps per block, ~8 rows per warp
+    if (blocks > 2048) blocks = 2048;
+    dim3 grid((unsigned)blocks, P->T);
+    k_rho_max<<<grid, 256, 0, st>>>(*P, bits, xc_all, tg, uniq, U);
 }
 
 extern "C" void rvl_launch_row_hash(const uint64_t *bits, int64_t F, int words, uint64_t *hash, int64_t *idx,
