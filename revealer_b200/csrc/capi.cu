@@ -18,6 +18,7 @@
 #include <thrust/partition.h>
 #include <thrust/sort.h>
 #include <thrust/scan.h>
+#include <thrust/transform.h>
 #include <thrust/copy.h>
 #include <thrust/functional.h>
 #include <thrust/iterator/counting_iterator.h>
@@ -311,6 +312,17 @@ extern "C" int rvl_set_shard(rvl_ctx *ctx, int rank, int world, int64_t row_offs
 
 // ---- matrix ---------------------------------------------------------------------------------
 
+// sort key of a row for the k_score work list: minus its minority-class count (densest first)
+struct rvl_cost_key {
+    const int32_t *cnt;
+    int n;
+    __host__ __device__ int32_t operator()(int64_t f) const
+    {
+        int32_t c = cnt[f];
+        return -(c < n - c ? c : n - c);
+    }
+};
+
 struct rvl_is_rep {
     const int64_t *rep;
     __host__ __device__ bool operator()(int64_t f) const { return rep[f] == f; }
@@ -344,7 +356,17 @@ static int build_dedup(rvl_ctx *ctx)
         auto end = thrust::copy_if(pol, thrust::counting_iterator<int64_t>(0), thrust::counting_iterator<int64_t>(F),
                                    thrust::device_ptr<int64_t>(ctx->d_uniq), pred);
         ctx->U = end - thrust::device_ptr<int64_t>(ctx->d_uniq);
-        ctx->launches += 6;
+        // schedule the densest rows first (their evaluations are the longest: more live density columns),
+        // so that the persistent k_score grid drains on short items -- order affects timing only
+        int32_t *d_cnt = reinterpret_cast<int32_t *>(d_head); // reuse: F int64 >= F int32
+        int32_t *d_key = reinterpret_cast<int32_t *>(d_idx);
+        rvl_launch_row_counts(ctx->d_bits, F, ctx->words, d_cnt, ctx->stream);
+        rvl_cost_key key{d_cnt, ctx->n};
+        thrust::transform(pol, thrust::device_ptr<int64_t>(ctx->d_uniq), thrust::device_ptr<int64_t>(ctx->d_uniq) + ctx->U,
+                          thrust::device_ptr<int32_t>(d_key), key);
+        thrust::stable_sort_by_key(pol, thrust::device_ptr<int32_t>(d_key), thrust::device_ptr<int32_t>(d_key) + ctx->U,
+                                   thrust::device_ptr<int64_t>(ctx->d_uniq));
+        ctx->launches += 9;
     } catch (...) {
         rc = fail(ctx, RVL_ERR_CUDA, "duplicate-row grouping failed on the device");
     }
@@ -671,7 +693,7 @@ static int launch_score(rvl_ctx *ctx, double *base)
     CK(cudaEventRecord(ev.first, ctx->stream));
     rvl_launch_score(&P, ctx->score_grid_x, ctx->score_smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed,
                      ctx->d_bcvtab, ctx->d_tt, base, ctx->d_part, ctx->d_work, ctx->d_ctr,
-                     (ctx->dedup && ctx->U < ctx->F) ? ctx->d_uniq : nullptr, ctx->U, ctx->stream);
+                     ctx->dedup ? ctx->d_uniq : nullptr, ctx->U, ctx->stream);
     ctx->fill_pending = ctx->dedup && ctx->U < ctx->F;
     CK(cudaEventRecord(ev.second, ctx->stream));
     ctx->launches++;
