@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--workload", default="C3_1kx100k")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--iters", type=int, default=0, help="override the workload's iteration count")
+    ap.add_argument("--features", type=int, default=0, help="override the workload's row count (not the headline config)")
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -174,8 +175,10 @@ def main():
     n, F, iters, n_seed, T = synth.CONFIGS[args.workload]
     if args.iters:
         iters = args.iters
+    if args.features:
+        F = args.features
     lo, cnt = rb.shard_rows(F, world, rank)
-    w = synth.make_workload(args.workload, row_lo=lo, row_hi=lo + cnt)
+    w = synth.make_workload(args.workload, F=F, row_lo=lo, row_hi=lo + cnt)
     targets = np.atleast_2d(w["target"])
     m2_u8 = w["m2"]
 

@@ -77,7 +77,8 @@ def make_workload(name=None, n=None, F=None, n_seed_rows=1, n_targets=1, seed_of
     """Returns dict(target(s), m2 (uint8 rows [row_lo,row_hi)), seed (uint8[n]), iters)."""
     iters = 5
     if name is not None:
-        n, F, iters, n_seed_rows, n_targets = CONFIGS[name]
+        n, F0, iters, n_seed_rows, n_targets = CONFIGS[name]
+        F = F or F0                                   # F given: a row-count override of the named shape
         seed_offset = CONFIG_INDEX[name]
     rng = np.random.Generator(np.random.PCG64(BASE_SEED + seed_offset))
     target = make_target(n, rng)
