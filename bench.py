@@ -295,9 +295,16 @@ def main():
         flops = exps * FLOP_PER_EXP + logs * FLOP_PER_LOG + plain
         words = ((n + 63) // 64 + 1) & ~1
         bytes_alg = cnt * T * (words * 8 + 8)
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu capture of this workload (1 GPU)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_score_traffic.json")))
+            if tj["workload"] == args.workload and world == 1 and not args.features:
+                traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+        except Exception:
+            pass
         roofline = {
             "kernel": "k_score", "bound": "fp64", "achieved": flops / dur / 1e12, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": flops / dur / 1e12 / fp64_peak if fp64_peak else None, "traffic": None,
+            "unit": "TFLOP/s", "frac": flops / dur / 1e12 / fp64_peak if fp64_peak else None, "traffic": traffic,
             "peak_source": "measured live: rvl_measure_fp64_peak (DFMA chain); MEASURED_PEAKS.json has no FP64 figure",
             "launch_ms": dur * 1e3, "launches": int(k_n), "share_of_step": k_ms / (ms * args.steps),
             "convention": "executed work from kernel counters: exp=%d flop, log=%d flop (FP64-pipe SASS "
