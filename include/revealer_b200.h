@@ -104,6 +104,12 @@ int rvl_load_matrix_bits_device(rvl_ctx *ctx, const void *dev_bits, int64_t F, i
  * bcv() for binary vectors.  n_targets > 1 = a batch of independent searches (config C5), or,
  * with rvl_set_null_targets, the reference's permuted targets (LIB:1843-1844). */
 int rvl_set_targets(rvl_ctx *ctx, const double *targets, int64_t n, int64_t n_targets);
+/* As rvl_set_targets, for the reference's permutation nulls (target.rand, LIB:1843-1844; the 10 000
+ * sample(target) draws of REVEALER_assess_features.v1, LIB:2885): targets 1..n_targets-1 are declared to
+ * be permutations of target 0.  bcv() is permutation-invariant, so its O(n^2) pair histogram and
+ * Brent search run once instead of n_targets times.  The claim is verified with an order-independent
+ * fingerprint of the values; RVL_ERR_ARG if it does not hold. */
+int rvl_set_targets_permuted(rvl_ctx *ctx, const double *targets, int64_t n, int64_t n_targets);
 /* Targets [first_null, n_targets) are permutation-null targets: scored against target 0's
  * seed, excluded from the winner selection.  first_null <= 0 disables. */
 int rvl_set_null_targets(rvl_ctx *ctx, int64_t first_null);

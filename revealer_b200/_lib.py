@@ -46,6 +46,7 @@ SIGNATURES = {
     "rvl_load_matrix_bits": (_i, [_vp, _u64p, _i64, _i64, _i64]),
     "rvl_load_matrix_bits_device": (_i, [_vp, _vp, _i64, _i64, _i64]),
     "rvl_set_targets": (_i, [_vp, _dp, _i64, _i64]),
+    "rvl_set_targets_permuted": (_i, [_vp, _dp, _i64, _i64]),
     "rvl_set_null_targets": (_i, [_vp, _i64]),
     "rvl_set_seed": (_i, [_vp, _u8p, _i64, _i]),
     "rvl_score_once": (_i, [_vp, _dp]),

@@ -157,10 +157,13 @@ class RevealerContext:
         self._ck(self._lib.rvl_load_matrix_bits_device(self._h, C.c_void_p(int(dev_ptr)), F, n, words))
         self.F, self.n = F, n
 
-    def set_targets(self, targets, first_null=0):
+    def set_targets(self, targets, first_null=0, permuted=False):
+        """targets: [n] or [T][n].  permuted=True declares rows 1.. to be permutations of row 0 (verified
+        on the device): they then share row 0's bcv bandwidth instead of recomputing it T times."""
         t = np.ascontiguousarray(np.atleast_2d(np.asarray(targets, dtype=np.float64)))
         T, n = t.shape
-        self._ck(self._lib.rvl_set_targets(self._h, _dp(t), n, T))
+        fn = self._lib.rvl_set_targets_permuted if permuted else self._lib.rvl_set_targets
+        self._ck(fn(self._h, _dp(t), n, T))
         self.T, self.n = T, n
         if first_null and first_null > 0:
             self._ck(self._lib.rvl_set_null_targets(self._h, first_null))
@@ -361,7 +364,7 @@ def revealer_search(target, m2, seed=None, max_n_iter=5, target_match="positive"
         if target_rand is not None:
             targets = np.vstack([targets, np.asarray(target_rand, dtype=np.float64)])
             first_null = 1
-        ctx.set_targets(targets, first_null=first_null)
+        ctx.set_targets(targets, first_null=first_null, permuted=target_rand is not None)
         ctx.set_seed(np.zeros(n, dtype=np.uint8) if seed is None else seed)
         res = ctx.search(max_n_iter)
         cmi = res["cmi"][0].T.copy()  # F x iters like R
@@ -378,6 +381,37 @@ def revealer_search(target, m2, seed=None, max_n_iter=5, target_match="positive"
     finally:
         if own:
             ctx.close()
+
+
+def assess_features(target, features, n_perm=10000, r_seed=5209761, n_grid=25, device=0, target_rand=None):
+    """The numerical core of REVEALER_assess_features.v1 (LIB:2672-2933): for every feature row,
+    IC = mutual.inf.v2(target, feature)$IC (LIB:2875) and its permutation p-value against n.perm
+    shuffled targets (LIB:2885-2890: sum(null >= IC)/n.perm for IC >= 0, sum(null <= IC)/n.perm
+    otherwise).  features: F x n 0/1 matrix.  target_rand: optional n.perm x n permuted targets
+    (R's sample() stream is not reproduced; default: numpy PCG64(r_seed)).
+    Returns dict(IC [F], p_val [F], null_IC [n_perm][F]).  Plots, ROC and squared error stay in R."""
+    target = np.asarray(target, dtype=np.float64)
+    n = target.shape[0]
+    if target_rand is None:
+        rng = np.random.Generator(np.random.PCG64(r_seed))
+        target_rand = np.stack([rng.permutation(target) for _ in range(n_perm)]) if n_perm > 0 else np.empty((0, n))
+    target_rand = np.asarray(target_rand, dtype=np.float64)
+    ic = None
+    null = []
+    chunk = 60000                                   # targets per upload (the ABI takes <= 65535)
+    with RevealerContext(device, n_grid=n_grid) as ctx:
+        ctx.load_matrix(features)
+        for lo in range(0, max(1, len(target_rand)), chunk):
+            part = target_rand[lo:lo + chunk]
+            ctx.set_targets(np.vstack([target[None, :], part]), permuted=True)
+            ctx.set_seed(np.zeros(n, dtype=np.uint8))  # constant z: cond.assoc -> mutual.inf.v2 (LIB:2509)
+            sc = ctx.score_once()
+            ic = sc[0]
+            null.append(sc[1:])
+    null = np.concatenate(null, axis=0) if null else np.empty((0, len(ic)))
+    n_perm = max(1, null.shape[0])
+    p = np.where(ic >= 0, (null >= ic[None, :]).sum(axis=0), (null <= ic[None, :]).sum(axis=0)) / n_perm
+    return dict(IC=ic, p_val=p, null_IC=null)
 
 
 def read_gct(path):

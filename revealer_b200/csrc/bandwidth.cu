@@ -142,11 +142,16 @@ __global__ void k_target_stats(const double *__restrict__ x_all, int n, int G, R
     const double *x = x_all + (size_t)t * n;
     double lo = INFINITY, hi = -INFINITY, s = 0.0;
     int bad = 0;
+    unsigned long long fp = 0ull;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double v = x[i];
         if (!isfinite(v)) bad = 1;
         lo = fmin(lo, v); hi = fmax(hi, v); s += v;
+        unsigned long long h = (unsigned long long)__double_as_longlong(v == 0.0 ? 0.0 : v); // -0 == +0
+        h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+        fp += h; // a sum of hashes does not depend on the order of the samples
     }
+    atomicAdd(&tg[t].fingerprint, fp);
     if (bad) atomicOr(nonfinite, 1);
     double tot = rvl_block_sum(s, sh);
     double mean = tot / n;
@@ -251,15 +256,28 @@ extern "C" void rvl_launch_bcv_binary_table(int n, double *table, cudaStream_t s
     k_bcv_binary_table<<<blocks, threads, 0, st>>>(n, table);
 }
 
+// Targets 1..T-1 declared to be permutations of target 0 (LIB:1843-1844, 2885): bcv() is invariant
+// under permutation, so they inherit target 0's bandwidth.  The claim is checked with the
+// order-independent fingerprint; *flag |= 2 when it does not hold.
+__global__ void k_bcv_copy_permuted(int T, RvlTarget *__restrict__ tg, int *__restrict__ flag)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 1 || t >= T) return;
+    if (tg[t].fingerprint != tg[0].fingerprint) atomicOr(flag, 2);
+    tg[t].bcv = tg[0].bcv;
+}
+
 extern "C" void rvl_launch_target_setup(const double *x_all, int n, int T, int G, RvlTarget *tg, double *u_all,
                                         double *xc_all, int *bin_all, int *cnt_all, int *nonfinite,
-                                        cudaStream_t st)
+                                        int permuted, cudaStream_t st)
 {
     k_target_stats<<<T, 256, 0, st>>>(x_all, n, G, tg, u_all, xc_all, bin_all, nonfinite);
-    cudaMemsetAsync(cnt_all, 0, sizeof(int) * (size_t)T * RVL_NB, st);
+    const int Th = permuted ? 1 : T; // targets that need their own pair histogram + Brent search
+    cudaMemsetAsync(cnt_all, 0, sizeof(int) * (size_t)Th * RVL_NB, st);
     int chunks = n < 512 ? n : 512;
     if (chunks < 1) chunks = 1;
-    dim3 grid(chunks, T);
+    dim3 grid(chunks, Th);
     k_pair_histogram<<<grid, 256, 0, st>>>(bin_all, n, cnt_all);
-    k_bcv_target<<<(T + 31) / 32, 32, 0, st>>>(n, T, cnt_all, tg);
+    k_bcv_target<<<(Th + 31) / 32, 32, 0, st>>>(n, Th, cnt_all, tg);
+    if (permuted && T > 1) k_bcv_copy_permuted<<<(T + 127) / 128, 128, 0, st>>>(T, tg, nonfinite);
 }

@@ -27,7 +27,7 @@
 extern "C" {
 void rvl_launch_bcv_binary_table(int n, double *table, cudaStream_t st);
 void rvl_launch_target_setup(const double *x_all, int n, int T, int G, RvlTarget *tg, double *u_all, double *xc_all,
-                             int *bin_all, int *cnt_all, int *nonfinite, cudaStream_t st);
+                             int *bin_all, int *cnt_all, int *nonfinite, int permuted, cudaStream_t st);
 size_t rvl_score_smem_bytes(int n, int words);
 cudaError_t rvl_score_configure(size_t smem, int device, int *grid_out);
 int rvl_score_warps(void);
@@ -177,6 +177,15 @@ template <class T> static void dfree(T *&p)
     p = nullptr;
 }
 
+// The x-axis table costs about as much as 70-360 literal passes per target and iteration; with only
+// a handful of rows to score (REVEALER_assess_features: a few rows x 10 000 permuted targets) the
+// literal per-row pass is cheaper.
+static bool use_dense_x(const rvl_ctx *c)
+{
+    int64_t rows = c->dedup ? c->U : c->F;
+    return c->dense_x || (rows >= 0 && rows <= 64);
+}
+
 static RvlParams make_params(const rvl_ctx *c)
 {
     RvlParams P;
@@ -189,7 +198,8 @@ static RvlParams make_params(const rvl_ctx *c)
     P.tt_pad = RVL_TT_PAD;
     P.tt_nodes = (int)ceil(tau_max / P.tt_dt) + 2 * RVL_TT_PAD + 1;
     if (P.tt_nodes < RVL_TT_STENCIL) P.tt_nodes = RVL_TT_STENCIL;
-    P.dense_x = c->dense_x;
+    P.dense_x = use_dense_x(c) ? 1 : 0;
+    P.literal = c->dense_x;
     P.prune_theta = c->prune_theta;
     return P;
 }
@@ -496,9 +506,22 @@ extern "C" int rvl_load_matrix_bits_device(rvl_ctx *ctx, const void *dev_bits, i
 
 // ---- targets and seeds -----------------------------------------------------------------------
 
+static int set_targets_impl(rvl_ctx *ctx, const double *targets, int64_t n, int64_t n_targets, int permuted);
+
 extern "C" int rvl_set_targets(rvl_ctx *ctx, const double *targets, int64_t n, int64_t n_targets)
 {
     GUARD();
+    return set_targets_impl(ctx, targets, n, n_targets, 0);
+}
+
+extern "C" int rvl_set_targets_permuted(rvl_ctx *ctx, const double *targets, int64_t n, int64_t n_targets)
+{
+    GUARD();
+    return set_targets_impl(ctx, targets, n, n_targets, 1);
+}
+
+static int set_targets_impl(rvl_ctx *ctx, const double *targets, int64_t n, int64_t n_targets, int permuted)
+{
     if (!targets || n < 2 || n_targets < 1 || n_targets > 65535) return fail(ctx, RVL_ERR_ARG, "bad targets (n=%lld, n_targets=%lld; need n >= 2, 1 <= n_targets <= 65535)", (long long)n, (long long)n_targets);
     if (ctx->F >= 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "targets have n=%lld but matrix has n=%d", (long long)n, ctx->n);
     free_targets(ctx);
@@ -518,8 +541,8 @@ extern "C" int rvl_set_targets(rvl_ctx *ctx, const double *targets, int64_t n, i
     CK(cudaMemcpyAsync(ctx->d_x, targets, sizeof(double) * (size_t)T * n, cudaMemcpyHostToDevice, ctx->stream));
     rvl_launch_bcv_binary_table((int)n, ctx->d_bcvtab, ctx->stream);
     rvl_launch_target_setup(ctx->d_x, (int)n, T, ctx->opts.n_grid, ctx->d_tg, ctx->d_u, ctx->d_xc, ctx->d_bin,
-                            ctx->d_cnt, ctx->d_flag, ctx->stream);
-    ctx->launches += 4;
+                            ctx->d_cnt, ctx->d_flag, permuted, ctx->stream);
+    ctx->launches += 4 + (permuted ? 1 : 0);
     CK(cudaGetLastError());
     ctx->T = T;
     ctx->G_targets = ctx->opts.n_grid;
@@ -528,7 +551,8 @@ extern "C" int rvl_set_targets(rvl_ctx *ctx, const double *targets, int64_t n, i
     int h = 0;
     CK(cudaMemcpyAsync(&h, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (h) { free_targets(ctx); return fail(ctx, RVL_ERR_NONFINITE, "target has NA/NaN/Inf values"); }
+    if (h & 1) { free_targets(ctx); return fail(ctx, RVL_ERR_NONFINITE, "target has NA/NaN/Inf values"); }
+    if (h & 2) { free_targets(ctx); return fail(ctx, RVL_ERR_ARG, "rvl_set_targets_permuted: a target is not a permutation of target 0"); }
     // seed_of defaults to self
     std::vector<RvlTarget> tg(T);
     CK(cudaMemcpy(tg.data(), ctx->d_tg, sizeof(RvlTarget) * T, cudaMemcpyDeviceToHost));
@@ -609,7 +633,7 @@ static int prep_iteration(rvl_ctx *ctx)
     }
     int rc = configure_score(ctx);
     if (rc) return rc;
-    if (ctx->rho_dirty && !ctx->dense_x) { // range of the bandwidth shrink over the loaded rows (once per matrix/targets)
+    if (ctx->rho_dirty && !use_dense_x(ctx)) { // range of the bandwidth shrink over the loaded rows (once per matrix/targets)
         CK(cudaMemset2DAsync((char *)ctx->d_tg + offsetof(RvlTarget, rho_pos_max_bits), sizeof(RvlTarget), 0,
                              2 * sizeof(unsigned long long), (size_t)ctx->T, ctx->stream));
         if (ctx->F > 0) {
@@ -620,7 +644,7 @@ static int prep_iteration(rvl_ctx *ctx)
         ctx->rho_dirty = false;
     }
     const int nslots = ctx->score_grid_x * rvl_score_warps();
-    if (ctx->dense_x) { // literal mode has no table: the seed state gets its own small launch
+    if (use_dense_x(ctx)) { // no table in this mode: the seed state gets its own small launch
         rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->d_part, nslots, ctx->d_work, ctx->stream);
     } else {
         rvl_launch_ttable(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_bcvtab, ctx->d_tt, ctx->d_part, nslots,

@@ -24,6 +24,7 @@ struct RvlTarget {
     // largest rho^+ and |rho| = cor(x, row) over the loaded rows (k_rho_max): bounds the range of the
     // bandwidth shrink factor c, hence how many nodes of the x-axis table are ever read
     unsigned long long rho_pos_max_bits, rho_abs_max_bits;
+    unsigned long long fingerprint; // order-independent hash of the multiset of target values
     // --- per iteration (written by k_seed_prep)
     int32_t nz;       // popcount(seed)
     int32_t mode;     // RVL_MODE_*
@@ -55,7 +56,9 @@ struct RvlParams {
     // bandwidth-interpolation table (see score.cu, "x-axis sums"): nodes tau_m = (m - tt_pad) * tt_dt
     int32_t tt_nodes, tt_pad;
     double tt_dt;
-    int32_t dense_x;  // 1: recompute the x-axis sums per feature over all samples (validation mode)
+    int32_t dense_x;  // 1: x-axis sums recomputed per feature over all samples (validation mode, or
+                      //    chosen automatically when so few rows are scored that a table does not pay)
+    int32_t literal;  // 1: literal entropy epilogue, no factorised columns (validation mode)
     double prune_theta; // density columns holding < theta/G^3 of the mass are replaced by the eps floor
 };
 
@@ -79,7 +82,6 @@ static __constant__ double RVL_LG[8] = {6.666666666666735130e-01, 3.999999999940
 // 18 FP64-pipe instructions, no special-case branches.
 __device__ __forceinline__ double rvl_log_pos(double q)
 {
-#if 1
     int hi = __double2hiint(q);
     const int lo = __double2loint(q);
     hi += 0x3ff00000 - 0x3fe6a09e;
@@ -104,35 +106,6 @@ __device__ __forceinline__ double rvl_log_pos(double q)
     p = fma(p, z, RVL_LG[0]);
     const double lm = fma(s * z, p, s + s);
     return fma((double)k, RVL_LG[7], lm);
-#else
-    int hi = __double2hiint(q);
-    const int lo = __double2loint(q);
-    hi += 0x3ff00000 - 0x3fe6a09e;
-    const int k = (hi >> 20) - 0x3ff;
-    hi = (hi & 0x000fffff) + 0x3fe6a09e;
-    const double m = __hiloint2double(hi, lo);
-    const double f = m - 1.0, t = m + 1.0;
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(t));
-    double e = fma(-t, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-t, r, 1.0);
-    r = fma(r, e, r);
-    const double s = f * r;
-    const double z = s * s;
-    double p = 1.0 / 19.0;
-    p = fma(p, z, 1.0 / 17.0);
-    p = fma(p, z, 1.0 / 15.0);
-    p = fma(p, z, 1.0 / 13.0);
-    p = fma(p, z, 1.0 / 11.0);
-    p = fma(p, z, 1.0 / 9.0);
-    p = fma(p, z, 1.0 / 7.0);
-    p = fma(p, z, 1.0 / 5.0);
-    p = fma(p, z, 1.0 / 3.0);
-    const double s2 = s + s;
-    const double lm = fma(s2 * z, p, s2);
-    return fma((double)k, 0.6931471805599453094, lm);
-#endif
 }
 
 __device__ __forceinline__ double rvl_warp_sum(double v)

@@ -395,7 +395,7 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
     // every Q lies in [eps', 4 n G^3]: normal doubles unless eps' itself is tiny (degenerate bandwidths)
     double cmi;
     if (epsq < 1e-290) cmi = rvl_cmi_epilogue<false>(S, G, epsq, P.prune_theta, lane, nlive_out);
-    else if (P.dense_x) cmi = rvl_cmi_epilogue<true>(S, G, epsq, P.prune_theta, lane, nlive_out); // literal mode
+    else if (P.literal) cmi = rvl_cmi_epilogue<true>(S, G, epsq, P.prune_theta, lane, nlive_out); // literal mode
     else cmi = rvl_cmi_epilogue_f<true>(S, G, epsq, P.prune_theta, hy, am, lane, nlive_out, nfact_out);
     return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * cmi));
 }

@@ -429,6 +429,49 @@ def test_permutation_null_and_pvalues(oracle):
         assert np.array_equal(out["p_val"][it], want)
 
 
+def test_assess_features_matches_oracle(oracle):
+    """REVEALER_assess_features.v1's numbers (LIB:2875-2890): per-feature IC and its permutation p-value.
+    Few rows x many permuted targets: the core takes the literal x-axis pass here (no table)."""
+    import revealer_b200 as rb
+    rng = np.random.default_rng(21)
+    n, F, n_perm = 120, 5, 40
+    x = rng.standard_normal(n)
+    feats = (rng.random((F, n)) < 0.15).astype(np.uint8)
+    feats[1, :30] = (x[:30] > 0)                               # one feature that tracks the target
+    perms = np.stack([rng.permutation(x) for _ in range(n_perm)])
+    out = rb.assess_features(x, feats, target_rand=perms)
+    ic = np.array([oracle.mutual_inf_v2(x, feats[i].astype(float))["IC"] for i in range(F)])
+    ok, err = score_close(out["IC"], ic)
+    assert ok, err
+    null = np.array([[oracle.mutual_inf_v2(perms[h], feats[i].astype(float))["IC"] for i in range(F)]
+                     for h in range(n_perm)])
+    ok, err = score_close(out["null_IC"], null)
+    assert ok, err
+    want_p = np.where(ic >= 0, (null >= ic).sum(0), (null <= ic).sum(0)) / n_perm
+    assert np.allclose(out["p_val"], want_p)
+
+
+def test_permuted_targets_share_bandwidth_and_are_verified():
+    import revealer_b200 as rb
+    from revealer_b200 import _lib
+    rng = np.random.default_rng(22)
+    x = rng.standard_normal(200)
+    perms = np.stack([x] + [rng.permutation(x) for _ in range(5)])
+    with _ctx() as ctx:
+        ctx.set_targets(perms)
+        a = [ctx.target_bandwidth(t) for t in range(6)]
+        ctx.set_targets(perms, permuted=True)
+        b = [ctx.target_bandwidth(t) for t in range(6)]
+        # bcv is permutation-invariant; computed independently the variance's last bit may differ
+        assert len(set(b)) == 1 and b[0] == a[0]
+        assert max(abs(v - a[0]) for v in a) <= 1e-13 * a[0]
+        bad = perms.copy()
+        bad[3, 7] += 1e-9
+        with pytest.raises(rb.RevealerError) as e:
+            ctx.set_targets(bad, permuted=True)
+        assert e.value.code == _lib.RVL_ERR_ARG
+
+
 # ------------------------------------------------------------------ sharded form on one GPU
 
 def test_two_shards_equal_single_shard():
