@@ -108,6 +108,37 @@ __device__ __forceinline__ double rvl_log_pos(double q)
     return fma((double)k, RVL_LG[7], lm);
 }
 
+// exp(a) for a <= 0 (Gaussian kernel weights).  Branch-free: k = round(a log2 e) by the 1.5*2^52 trick,
+// r = a - k ln2 (hi/lo split, FMA), degree-12 Taylor polynomial on |r| <= 0.347, 2^k by an integer add
+// to the exponent field.  Results below ~2e-307 are flushed to 0 (they are > 280 orders of magnitude
+// under anything that can matter next to the eps floor).  <= 3 ulp (emulated in tests/test_fastlog.py);
+// 17 FP64-pipe instructions with the coefficients taken from constant memory.
+static __constant__ double RVL_EXPC[11] = {1.0 / 2,         1.0 / 6,          1.0 / 24,          1.0 / 120,
+                                           1.0 / 720,       1.0 / 5040,       1.0 / 40320,       1.0 / 362880,
+                                           1.0 / 3628800,   1.0 / 39916800,   1.0 / 479001600};
+__device__ __forceinline__ double rvl_exp_neg(double a)
+{
+    const double t = fma(a, 1.4426950408889634074, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, a);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double q = RVL_EXPC[10];
+    q = fma(q, r, RVL_EXPC[9]);
+    q = fma(q, r, RVL_EXPC[8]);
+    q = fma(q, r, RVL_EXPC[7]);
+    q = fma(q, r, RVL_EXPC[6]);
+    q = fma(q, r, RVL_EXPC[5]);
+    q = fma(q, r, RVL_EXPC[4]);
+    q = fma(q, r, RVL_EXPC[3]);
+    q = fma(q, r, RVL_EXPC[2]);
+    q = fma(q, r, RVL_EXPC[1]);
+    q = fma(q, r, RVL_EXPC[0]);
+    const double p = fma(r * r, q, r) + 1.0;
+    const double s = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return a < -707.0 ? 0.0 : s;
+}
+
 __device__ __forceinline__ double rvl_warp_sum(double v)
 {
 #pragma unroll

@@ -49,7 +49,7 @@ __device__ __forceinline__ void rvl_accumulate_dense(const double *__restrict__ 
 {
     for (int s = s_begin; s < s_end; s += s_step) {
         double t = gi - u[s];
-        double e = exp(-beta * t * t);
+        double e = rvl_exp_neg(-beta * t * t);
         int yb = (int)((yrow[s >> 6] >> (s & 63)) & 1ull);
         int zb = zrow ? (int)((zrow[s >> 6] >> (s & 63)) & 1ull) : 0;
         if (yb) { if (zb) acc[3] += e; else acc[2] += e; }
@@ -211,6 +211,10 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
         const double gM = am ? g1 : g0, gm = am ? g0 : g1;
         const double dmax = fma(gM, maxV, gm * maxW);
         const bool dead = dmax < dead_thr;
+        if (!__any_sync(FULL, active && !dead)) { // the whole y-slice is below the threshold (typical mid-axis j)
+            ndead += G;
+            continue;
+        }
         const bool fact = !dead && (gm * maxW <= 0x1p-54 * fma(gM, minV, epsq)) && (gM * minV >= 16.0 * epsq);
         if (active && !dead) {
             const double qyz = fma(gM, sM, fma(gm, sm, gE));
@@ -305,7 +309,7 @@ __device__ __forceinline__ void rvl_fill_axis(double g[2][RVL_MAXG], int G, doub
 {
     if (lane < G) {
         double t = (double)lane / (double)(G - 1) / h;
-        double v = exp(-0.5 * t * t);
+        double v = rvl_exp_neg(-0.5 * t * t);
         g[0][lane] = v;
         g[1][G - 1 - lane] = v;
     }
@@ -485,8 +489,8 @@ k_ttable(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, const
         for (; s + 3 * nwarps < cnt; s += 4 * nwarps) {
             const int s1 = s + nwarps, s2 = s + 2 * nwarps, s3 = s + 3 * nwarps;
             const double d0 = gi - su[s], d1 = gi - su[s1], d2 = gi - su[s2], d3 = gi - su[s3];
-            const double e0 = exp(-beta * d0 * d0), e1 = exp(-beta * d1 * d1), e2 = exp(-beta * d2 * d2),
-                         e3 = exp(-beta * d3 * d3);
+            const double e0 = rvl_exp_neg(-beta * d0 * d0), e1 = rvl_exp_neg(-beta * d1 * d1), e2 = rvl_exp_neg(-beta * d2 * d2),
+                         e3 = rvl_exp_neg(-beta * d3 * d3);
             if ((sz[s >> 6] >> (s & 63)) & 1ull) a1 += e0; else a0 += e0;
             if ((sz[s1 >> 6] >> (s1 & 63)) & 1ull) a1 += e1; else a0 += e1;
             if ((sz[s2 >> 6] >> (s2 & 63)) & 1ull) a1 += e2; else a0 += e2;
@@ -494,7 +498,7 @@ k_ttable(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, const
         }
         for (; s < cnt; s += nwarps) {
             const double d = gi - su[s];
-            const double e = exp(-beta * d * d);
+            const double e = rvl_exp_neg(-beta * d * d);
             if ((sz[s >> 6] >> (s & 63)) & 1ull) a1 += e; else a0 += e;
         }
     }
@@ -674,7 +678,7 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
                     int b = __ffsll((long long)v) - 1;
                     v &= v - 1;
                     double d = gi - u[w * 64 + b];
-                    double e = exp(-beta * d * d);
+                    double e = rvl_exp_neg(-beta * d * d);
                     if ((zw >> b) & 1ull) m1 += e; else m0 += e;
                 }
             }

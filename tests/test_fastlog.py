@@ -30,6 +30,33 @@ def rvl_log_pos(q):
     return k * 0.6931471805599453094 + ((s * z) * p + (s + s))
 
 
+def rvl_exp_neg(a):
+    """Emulation of rvl_exp_neg (rvl_common.cuh): exp(a) for a <= 0."""
+    import math
+    magic = 6755399441055744.0
+    t = a * 1.4426950408889634074 + magic
+    k = (t.view(np.int64) & 0xFFFFFFFF).astype(np.int64)
+    k = np.where(k >= 2 ** 31, k - 2 ** 32, k)
+    kd = t - magic
+    r = a - kd * 6.93147180369123816490e-01
+    r = r - kd * 1.90821492927058770002e-10
+    c = [1.0 / math.factorial(i) for i in range(13)]
+    q = np.full_like(r, c[12])
+    for i in range(11, 1, -1):
+        q = q * r + c[i]
+    p = (r * r) * q + r + 1.0
+    return np.where(a < -707.0, 0.0, np.ldexp(p, k.astype(np.int32)))
+
+
+def test_fast_exp_within_a_few_ulp():
+    rng = np.random.default_rng(1)
+    a = -np.concatenate([rng.uniform(0, 707, 1_000_000), rng.uniform(0, 3, 300_000), 10 ** rng.uniform(-12, 0, 100_000),
+                         np.array([0.0, 706.999, 1e-300])])
+    got, ref = rvl_exp_neg(a), np.exp(a)
+    assert np.max(np.abs(got - ref) / ref) <= 4 * 2.2204e-16
+    assert rvl_exp_neg(np.array([-708.0, -1e4]))[0] == 0.0 and rvl_exp_neg(np.array([0.0]))[0] == 1.0
+
+
 def test_fast_log_within_a_few_ulp():
     rng = np.random.default_rng(0)
     q = np.concatenate([np.exp(rng.uniform(-200, 40, 1_000_000)), np.exp(rng.uniform(-1e-3, 1e-3, 200_000)),
