@@ -35,20 +35,17 @@ void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_
                       const double *xc_all, const RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
                       const double *tt, double *scores, RvlCandHead *part, unsigned long long *work,
                       unsigned long long *ctr, const int64_t *uniq, int64_t U, cudaStream_t st);
-void rvl_launch_ttable(const RvlParams *P, RvlTarget *tg, const double *u_all, const uint64_t *seeds,
-                       const double *bcvtab, double *tt, RvlCandHead *slots, int nslots, unsigned long long *work,
-                       cudaStream_t st);
+void rvl_launch_advance(const RvlParams *P, RvlTarget *tg, const double *u_all, const uint64_t *seeds_in,
+                        uint64_t *seeds_out, const double *bcvtab, double *tt, RvlCandHead *slots, int nslots,
+                        unsigned long long *work, const unsigned char *recv, size_t rec_bytes, int iter, int iters,
+                        int first_null, int64_t *top, double *top_score, uint64_t *seed_iter, int allow_incr,
+                        cudaStream_t st);
 void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaStream_t st);
-void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
-                          RvlCandHead *part, int nslots, unsigned long long *work, cudaStream_t st);
 void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of, const double *u_all,
                       const double *xc_all, const uint64_t *y_all, const double *bcvtab, double *out,
                       size_t y_stride, size_t out_stride, cudaStream_t st);
 void rvl_launch_argmax(const RvlParams *P, const RvlCandHead *part, int nparts, const uint64_t *bits,
                        unsigned char *send, size_t rec_bytes, cudaStream_t st);
-void rvl_launch_merge(const RvlParams *P, int iter, int iters, int first_null, const unsigned char *recv,
-                      size_t rec_bytes, uint64_t *seeds, int64_t *top, double *top_score, uint64_t *seed_iter,
-                      cudaStream_t st);
 void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols, int words,
                                   uint64_t *bits, int *flag, cudaStream_t st);
 void rvl_launch_pack_u8_rowmajor(const uint8_t *m, int64_t F0, int64_t Fc, int n, int words, uint64_t *bits,
@@ -105,7 +102,8 @@ struct rvl_ctx {
 
     // seeds
     uint64_t *d_seed0 = nullptr; // initial seeds [T][words]
-    uint64_t *d_seed = nullptr;  // working seeds  [T][words]
+    uint64_t *d_seed = nullptr;  // working seeds  [T][words] (current)
+    uint64_t *d_seed_alt = nullptr; // the other half of the double buffer (k_advance reads one, writes the other)
     bool have_seed = false;
 
     // search state
@@ -253,7 +251,7 @@ static void free_matrix(rvl_ctx *c)
 static void free_targets(rvl_ctx *c)
 {
     dfree(c->d_x); dfree(c->d_u); dfree(c->d_xc); dfree(c->d_bcvtab); dfree(c->d_bin); dfree(c->d_cnt);
-    dfree(c->d_tg); dfree(c->d_seed0); dfree(c->d_seed); dfree(c->d_tt);
+    dfree(c->d_tg); dfree(c->d_seed0); dfree(c->d_seed); dfree(c->d_seed_alt); dfree(c->d_tt);
     c->tt_cap = 0;
     c->T = 0; c->have_seed = false;
     c->rho_dirty = true;
@@ -536,6 +534,7 @@ static int set_targets_impl(rvl_ctx *ctx, const double *targets, int64_t n, int6
     CK(dalloc(&ctx->d_tg, (size_t)T));
     CK(dalloc(&ctx->d_seed0, (size_t)T * ctx->words));
     CK(dalloc(&ctx->d_seed, (size_t)T * ctx->words));
+    CK(dalloc(&ctx->d_seed_alt, (size_t)T * ctx->words));
     CK(cudaMemsetAsync(ctx->d_tg, 0, sizeof(RvlTarget) * T, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_x, targets, sizeof(double) * (size_t)T * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -644,12 +643,9 @@ static int prep_iteration(rvl_ctx *ctx)
         ctx->rho_dirty = false;
     }
     const int nslots = ctx->score_grid_x * rvl_score_warps();
-    if (use_dense_x(ctx)) { // no table in this mode: the seed state gets its own small launch
-        rvl_launch_seed_prep(&P, ctx->d_tg, ctx->d_seed, ctx->d_bcvtab, ctx->d_part, nslots, ctx->d_work, ctx->stream);
-    } else {
-        rvl_launch_ttable(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_bcvtab, ctx->d_tt, ctx->d_part, nslots,
-                          ctx->d_work, ctx->stream);
-    }
+    // no merge here (recv = NULL): seed state + full table build for the seeds as they are
+    rvl_launch_advance(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_seed_alt, ctx->d_bcvtab, ctx->d_tt, ctx->d_part, nslots,
+                       ctx->d_work, nullptr, 0, 0, 1, ctx->first_null, nullptr, nullptr, nullptr, 0, ctx->stream);
     ctx->work_dirty = false;
     ctx->launches++;
     CK(cudaGetLastError());
@@ -798,13 +794,17 @@ extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
     GUARD();
     if (iter < 0 || iter >= ctx->iters) return fail(ctx, RVL_ERR_ARG, "iter out of range");
     RvlParams P = make_params(ctx);
-    rvl_launch_merge(&P, iter, ctx->iters, ctx->first_null, ctx->d_recv,
-                     sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, ctx->d_seed, ctx->d_top,
-                     ctx->d_top_score, ctx->d_seed_iter, ctx->stream);
+    // merge + seed state + x-axis table in one launch; seeds ping-pong between the two buffers
+    rvl_launch_advance(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_seed_alt, ctx->d_bcvtab, ctx->d_tt, ctx->d_part,
+                       ctx->score_grid_x * rvl_score_warps(), ctx->d_work, ctx->d_recv,
+                       sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, iter, ctx->iters, ctx->first_null,
+                       ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, 1, ctx->stream);
+    { uint64_t *tmp = ctx->d_seed; ctx->d_seed = ctx->d_seed_alt; ctx->d_seed_alt = tmp; }
+    ctx->work_dirty = false;
     ctx->launches += 1;
     CK(cudaGetLastError());
     // cmi.seed[iter] <- assoc(target, seed) (LIB:2170) is off the critical path: side stream, reading
-    // the seed_iter row k_merge just wrote (never modified again)
+    // the seed_iter row k_advance just wrote (never modified again)
     int nreal = ctx->first_null > 0 ? ctx->first_null : ctx->T;
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
@@ -814,7 +814,7 @@ extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
     ctx->launches += 1;
     ctx->side_pending = true;
     CK(cudaGetLastError());
-    return prep_iteration(ctx);
+    return RVL_OK;
 }
 
 extern "C" int rvl_synchronize(rvl_ctx *ctx)

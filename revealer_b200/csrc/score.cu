@@ -3,9 +3,9 @@
 //   k_score      cmi[k] = cond.assoc(target, m.2[k,], seed, "IC") for every local row k and
 //                every target at once                                  (LIB:1849-1856)
 //   k_argmax     order(cmi, decreasing = !negative)[1] on the shard    (LIB:1858-1862)
-//   k_merge      global winner from `world` candidate records, seed <- max(seed, m.2[top,]),
-//                cmi.seed[iter] <- assoc(target, seed)                 (LIB:2167-2170)
-//   k_seed_prep  per-iteration seed state (popcount, dispatch of cond.assoc LIB:2507-2517)
+//   k_advance    global winner from `world` candidate records, seed <- max(seed, m.2[top,])
+//                (LIB:2167-2168), seed state (dispatch of cond.assoc LIB:2507-2517), x-axis table
+//   k_assoc      cmi.seed[iter] <- assoc(target, seed)                 (LIB:2170), side stream
 //
 // Algebra.  With y, z in {0,1}^n the 25^3 KDE cube of misc3d::kde3d is
 //   d[i,j,k] = kappa * sum_{a,b in {0,1}} A_ab[i] * gy_a[j] * gz_b[k],
@@ -40,6 +40,22 @@ struct __align__(16) RvlWarpScratch {
 // FAST: rvl_log_pos (normal positive arguments only); otherwise the library log.
 template <bool FAST> __device__ __forceinline__ double rvl_logq(double q) { return FAST ? rvl_log_pos(q) : log(q); }
 template <bool FAST> __device__ __forceinline__ double rvl_xlogx(double q) { return q * rvl_logq<FAST>(q); }
+
+// "a is ahead of b" in R's stable order(decreasing = !negative): NaN last, ties by lower row.
+// (value, row) pairs under this relation form a total order, so reductions may be nested freely:
+// warp (k_score) -> shard (k_argmax) -> world (k_advance) all give order()[1].
+__device__ __forceinline__ bool rvl_ahead(double va, int64_t ia, double vb, int64_t ib, int negative)
+{
+    if (ib < 0) return ia >= 0;
+    if (ia < 0) return false;
+    bool na = isnan(va), nb = isnan(vb);
+    if (na || nb) {
+        if (na && nb) return ia < ib;
+        return nb;
+    }
+    if (va != vb) return negative ? (va < vb) : (va > vb);
+    return ia < ib;
+}
 
 // Accumulate the class-masked Gaussian sums for grid point `lane` over samples [s_begin, s_end)
 // with stride s_step.  yrow / zrow are bit rows (zrow may be NULL: single z class).
@@ -416,28 +432,66 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
 // Node tt_pad is tau = 0 exactly (c = 1: every feature with rho <= 0), so those use it unweighted.
 // Layout: tt[target][node][b][RVL_MAXG].
 
-// k_ttable also carries the per-iteration seed state (previously a separate launch): every block
-// recomputes popcount(seed) -> cond.assoc's dispatch (LIB:2507-2517); the block of node 0 publishes
-// it in RvlTarget, resets the target's per-warp best slots and (target 0) the k_score work counter.
+// k_advance = everything between two scoring passes, in one launch (grid = table nodes x targets):
+//   * merge (when `recv` is given): every block resolves, for its target's seed owner, the same global
+//     winner among the `world` candidate records (max score, ties -> lowest GLOBAL row, NaN last;
+//     LIB:1858-1862) and forms the new seed = old seed | winner row (LIB:2168) on the fly; the block of
+//     node 0 publishes it (seeds_out, seed.iter[iter,], top, top.score).  Seeds are double-buffered so
+//     that no block reads what another writes.
+//   * seed state: popcount -> cond.assoc's dispatch (LIB:2507-2517); node-0 block writes it to RvlTarget,
+//     resets the target's per-warp best slots and (target 0) k_score's work counter.
+//   * x-axis table: rebuilt from all samples (first iteration, or when the dispatch mode changed), or
+//     updated in place from the samples the winner just moved from z-class 0 to z-class 1
+//     (T_1 += d, T_0 -= d with d summed over those few samples): O(n1) instead of O(n) per node.
 __global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
-k_ttable(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, const uint64_t *__restrict__ seeds,
-         const double *__restrict__ bcvtab, double *__restrict__ tt, RvlCandHead *__restrict__ slots, int nslots,
-         unsigned long long *__restrict__ work)
+k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, const uint64_t *__restrict__ seeds_in,
+          uint64_t *__restrict__ seeds_out, const double *__restrict__ bcvtab, double *__restrict__ tt,
+          RvlCandHead *__restrict__ slots, int nslots, unsigned long long *__restrict__ work,
+          const unsigned char *__restrict__ recv, size_t rec_bytes, int iter, int iters, int first_null,
+          int64_t *__restrict__ top, double *__restrict__ top_score, uint64_t *__restrict__ seed_iter, int allow_incr)
 {
     __shared__ double part[RVL_SCORE_WARPS][2][RVL_MAXG];
-    __shared__ int s_nz;
+    __shared__ int s_nz_old, s_nz_new, s_win;
     const int t = blockIdx.y, m = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const RvlTarget tg = tg_all[t];
-    const uint64_t *zall = seeds + (size_t)tg.seed_of * P.words;
+    const RvlTarget tg = tg_all[t]; // only the per-target constants are used below (never nz / mode / bcv_z)
+    const int owner = tg.seed_of;
+    const bool is_null = (first_null > 0 && t >= first_null);
+    const uint64_t *zold = seeds_in + (size_t)owner * P.words;
+    const uint64_t *wrow = nullptr; // the winner's bit row (merge only)
+    if (recv) {
+        if (threadIdx.x == 0) {
+            double bv = 0.0;
+            int64_t bi = -1;
+            int br = 0;
+            for (int r = 0; r < P.world; r++) {
+                const RvlCandHead *h =
+                    reinterpret_cast<const RvlCandHead *>(recv + ((size_t)r * P.T + owner) * rec_bytes);
+                if (rvl_ahead(h->score, h->row, bv, bi, P.negative)) { bv = h->score; bi = h->row; br = r; }
+            }
+            s_win = br;
+            if (m == 0 && !is_null) {
+                top[(size_t)t * iters + iter] = bi;
+                top_score[(size_t)t * iters + iter] = bv;
+            }
+        }
+        __syncthreads();
+        wrow = reinterpret_cast<const uint64_t *>(recv + ((size_t)s_win * P.T + owner) * rec_bytes + sizeof(RvlCandHead));
+    }
     if (warp == 0) {
-        int c = 0;
-        for (int w = lane; w < P.words; w += 32) c += __popcll(zall[w]);
-        c = rvl_warp_sum_i(c);
-        if (lane == 0) s_nz = c;
+        int c0 = 0, c1 = 0;
+        for (int w = lane; w < P.words; w += 32) {
+            const uint64_t zo = zold[w], zn = wrow ? (zo | wrow[w]) : zo;
+            c0 += __popcll(zo);
+            c1 += __popcll(zn);
+        }
+        c0 = rvl_warp_sum_i(c0);
+        c1 = rvl_warp_sum_i(c1);
+        if (lane == 0) { s_nz_old = c0; s_nz_new = c1; }
     }
     __syncthreads();
-    const int nz = s_nz;
+    const int nz_old = s_nz_old, nz = s_nz_new;
+    const int mode_old = tg.is_const ? RVL_MODE_ZERO : ((nz_old == 0 || nz_old == P.n) ? RVL_MODE_IC : RVL_MODE_CIC);
     const int mode = tg.is_const ? RVL_MODE_ZERO : ((nz == 0 || nz == P.n) ? RVL_MODE_IC : RVL_MODE_CIC);
     if (m == 0) {
         if (threadIdx.x == 0) {
@@ -452,7 +506,17 @@ k_ttable(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, const
             h.row = -1;
             slots[(size_t)t * nslots + i] = h;
         }
+        if (recv && !is_null) { // apply(rbind(seed, m.2[top,]), 2, "max")  LIB:2168
+            uint64_t *zo = seeds_out + (size_t)t * P.words;
+            uint64_t *zi = seed_iter + ((size_t)t * iters + iter) * P.words;
+            for (int w = threadIdx.x; w < P.words; w += blockDim.x) {
+                const uint64_t v = zold[w] | wrow[w];
+                zo[w] = v;
+                zi[w] = v;
+            }
+        }
     }
+    if (P.dense_x) return; // literal mode keeps no table
     double *out = tt + (((size_t)t * P.tt_nodes + m) * 2) * RVL_MAXG;
     if (mode == RVL_MODE_ZERO) {
         if (threadIdx.x < 2 * RVL_MAXG) out[threadIdx.x] = 0.0;
@@ -469,19 +533,44 @@ k_ttable(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, const
     const double tau = (double)(m - P.tt_pad) * P.tt_dt;
     const double beta = (m == P.tt_pad) ? beta0 : beta0 * exp(tau);
     const double *u = u_all + (size_t)t * P.n;
-    const uint64_t *z = (mode == RVL_MODE_CIC) ? zall : nullptr;
-    // samples staged through shared memory in chunks of 1024 (coalesced loads, then broadcast reads)
+    const double gi = (double)lane;
+
+    // in-place update: valid when the table on record was built for the same x bandwidth and the same
+    // assignment of the untouched samples -- CIC before and after, or the all-zero seed (every sample in
+    // class 0, IC dispatch) whose x bandwidth bcv/4 coincides with bw_mult*bcv when bw_mult = 0.25
+    const bool incr = allow_incr && recv && mode == RVL_MODE_CIC &&
+                      (mode_old == RVL_MODE_CIC || (mode_old == RVL_MODE_IC && nz_old == 0 && P.bw_mult == 0.25));
+    if (incr) {
+        if (warp != 0) return;
+        double d = 0.0;
+        for (int w = 0; w < P.words; w++) {
+            uint64_t v = wrow[w] & ~zold[w]; // samples entering z-class 1 (warp-uniform word)
+            while (v) {
+                const int b = __ffsll((long long)v) - 1;
+                v &= v - 1;
+                const double dd = gi - u[w * 64 + b];
+                d += rvl_exp_neg(-beta * dd * dd);
+            }
+        }
+        out[lane] -= d;
+        out[RVL_MAXG + lane] += d;
+        return;
+    }
+
+    // full build: samples staged through shared memory in chunks of 1024 (coalesced loads, broadcast reads)
+    const bool use_z = (mode == RVL_MODE_CIC);
     __shared__ double su[1024];
     __shared__ uint64_t sz[16];
     double a0 = 0.0, a1 = 0.0;
-    const double gi = (double)lane;
     for (int base = 0; base < P.n; base += 1024) {
         const int cnt = min(1024, P.n - base);
         __syncthreads();
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) su[i] = u[base + i];
         if (threadIdx.x < 16) {
-            int w = (base >> 6) + threadIdx.x;
-            sz[threadIdx.x] = (z && w < P.words) ? z[w] : 0ull;
+            const int w = (base >> 6) + threadIdx.x;
+            uint64_t zz = 0ull;
+            if (use_z && w < P.words) zz = wrow ? (zold[w] | wrow[w]) : zold[w];
+            sz[threadIdx.x] = zz;
         }
         __syncthreads();
         // four independent exp chains in flight per lane; fixed summation order (s ascending per warp)
@@ -489,8 +578,8 @@ k_ttable(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, const
         for (; s + 3 * nwarps < cnt; s += 4 * nwarps) {
             const int s1 = s + nwarps, s2 = s + 2 * nwarps, s3 = s + 3 * nwarps;
             const double d0 = gi - su[s], d1 = gi - su[s1], d2 = gi - su[s2], d3 = gi - su[s3];
-            const double e0 = rvl_exp_neg(-beta * d0 * d0), e1 = rvl_exp_neg(-beta * d1 * d1), e2 = rvl_exp_neg(-beta * d2 * d2),
-                         e3 = rvl_exp_neg(-beta * d3 * d3);
+            const double e0 = rvl_exp_neg(-beta * d0 * d0), e1 = rvl_exp_neg(-beta * d1 * d1),
+                         e2 = rvl_exp_neg(-beta * d2 * d2), e3 = rvl_exp_neg(-beta * d3 * d3);
             if ((sz[s >> 6] >> (s & 63)) & 1ull) a1 += e0; else a0 += e0;
             if ((sz[s1 >> 6] >> (s1 & 63)) & 1ull) a1 += e1; else a0 += e1;
             if ((sz[s2 >> 6] >> (s2 & 63)) & 1ull) a1 += e2; else a0 += e2;
@@ -553,22 +642,6 @@ __device__ __forceinline__ void rvl_tt_lookup(const RvlParams &P, const double *
     }
 }
 
-// "a is ahead of b" in R's stable order(decreasing = !negative): NaN last, ties by lower row.
-// (value, row) pairs under this relation form a total order, so reductions may be nested freely:
-// warp -> CTA (k_score) -> shard (k_argmax) -> world (k_merge) all give order()[1].
-__device__ __forceinline__ bool rvl_ahead(double va, int64_t ia, double vb, int64_t ib, int negative)
-{
-    if (ib < 0) return ia >= 0;
-    if (ia < 0) return false;
-    bool na = isnan(va), nb = isnan(vb);
-    if (na || nb) {
-        if (na && nb) return ia < ib;
-        return nb;
-    }
-    if (va != vb) return negative ? (va < vb) : (va > vb);
-    return ia < ib;
-}
-
 // ---- k_score --------------------------------------------------------------------------------
 // Persistent kernel: grid = SMs x resident CTAs, block = RVL_SCORE_WARPS warps.  Every warp is an
 // independent worker: it draws the next (target, row) item from a global counter (target-major, so
@@ -577,7 +650,7 @@ __device__ __forceinline__ bool rvl_ahead(double va, int64_t ia, double vb, int6
 // and a barrier or a static row split would leave FP64 pipes idle at every CTA tail.
 // Dynamic smem: per-warp scratch + the row's bits.  Besides the score of every row, each warp leaves
 // its best (score, local row) per target in part[target][global warp id] (pre-set to "none" by
-// k_seed_prep) so that the rank step never re-reads the F scores.
+// k_advance) so that the rank step never re-reads the F scores.
 #ifndef RVL_SCORE_MIN_CTAS
 #define RVL_SCORE_MIN_CTAS 2
 #endif
@@ -709,45 +782,6 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
     if (t >= 0 && lane == 0) { RvlCandHead h; h.score = best_v; h.row = best_i; part[(size_t)t * nslots + slot] = h; }
 }
 
-// ---- seed state ------------------------------------------------------------------------------
-
-// One block per target: popcount(seed) and the cond.assoc dispatch (LIB:2507-2517).
-__device__ void rvl_seed_prep_block(const RvlParams &P, RvlTarget *tg_all, const uint64_t *seeds,
-                                    const double *bcvtab, int t, int *sh_i)
-{
-    RvlTarget &tg = tg_all[t];
-    const uint64_t *z = seeds + (size_t)tg.seed_of * P.words;
-    int c = 0;
-    for (int w = threadIdx.x; w < P.words; w += blockDim.x) c += __popcll(z[w]);
-    c = rvl_warp_sum_i(c);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh_i[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int nz = 0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); i++) nz += sh_i[i];
-        tg.nz = nz;
-        tg.bcv_z = bcvtab[nz];
-        tg.mode = tg.is_const ? RVL_MODE_ZERO : ((nz == 0 || nz == P.n) ? RVL_MODE_IC : RVL_MODE_CIC);
-    }
-    __syncthreads();
-}
-
-// Also re-arms the next k_score launch: work counter to zero, every per-warp best slot to "none".
-__global__ void k_seed_prep(RvlParams P, RvlTarget *tg_all, const uint64_t *seeds, const double *bcvtab,
-                            RvlCandHead *part, int nslots, unsigned long long *work)
-{
-    __shared__ int sh_i[32];
-    rvl_seed_prep_block(P, tg_all, seeds, bcvtab, blockIdx.x, sh_i);
-    for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
-        RvlCandHead h;
-        h.score = 0.0;
-        h.row = -1;
-        part[(size_t)blockIdx.x * nslots + i] = h;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *work = 0ull;
-}
-
 // assoc(x_t, y, "IC") by one block (8 warps): warps split the samples, lanes own grid points.
 // LIB:2491-2501 -> mutual.inf.v2.  Result written by thread 0.
 struct RvlAssocShared {
@@ -864,46 +898,6 @@ __global__ void k_argmax(RvlParams P, const RvlCandHead *__restrict__ part, int 
     uint64_t *rb = reinterpret_cast<uint64_t *>(rec + sizeof(RvlCandHead));
     if (threadIdx.x == 0) { h->score = bv; h->row = (bi < 0) ? -1 : (P.row_offset + bi); }
     for (int i = threadIdx.x; i < P.words; i += blockDim.x) rb[i] = (bi < 0) ? 0ull : bits[(size_t)bi * P.words + i];
-}
-
-// ---- merge: global winner, seed OR-merge, seed IC, next-iteration seed state ---------------------
-// recv holds `world` blocks of T records.  One block per target.  Every rank runs the same
-// deterministic resolution, so the seeds stay replicated without a second exchange.
-// assoc(target, seed) of the merged seed (LIB:2170) is not needed by the next iteration: the host
-// side launches it as k_assoc on a side stream, reading the immutable seed_iter row written here.
-__global__ void __launch_bounds__(128)
-k_merge(RvlParams P, int iter, int iters, int first_null, const unsigned char *__restrict__ recv, size_t rec_bytes,
-        uint64_t *seeds, int64_t *__restrict__ top, double *__restrict__ top_score,
-        uint64_t *__restrict__ seed_iter)
-{
-    __shared__ int win_rank;
-    int t = blockIdx.x;
-    bool is_null = (first_null > 0 && t >= first_null);
-    if (!is_null) {
-        if (threadIdx.x == 0) {
-            double bv = 0.0;
-            int64_t bi = -1;
-            int br = 0;
-            for (int r = 0; r < P.world; r++) {
-                const RvlCandHead *h =
-                    reinterpret_cast<const RvlCandHead *>(recv + ((size_t)r * P.T + t) * rec_bytes);
-                if (rvl_ahead(h->score, h->row, bv, bi, P.negative)) { bv = h->score; bi = h->row; br = r; }
-            }
-            win_rank = br;
-            top[(size_t)t * iters + iter] = bi;
-            top_score[(size_t)t * iters + iter] = bv;
-        }
-        __syncthreads();
-        const uint64_t *rb = reinterpret_cast<const uint64_t *>(recv + ((size_t)win_rank * P.T + t) * rec_bytes +
-                                                                sizeof(RvlCandHead));
-        uint64_t *z = seeds + (size_t)t * P.words;
-        uint64_t *zi = seed_iter + ((size_t)t * iters + iter) * P.words;
-        for (int i = threadIdx.x; i < P.words; i += blockDim.x) {
-            uint64_t v = z[i] | rb[i]; // apply(rbind(seed, m.2[top,]), 2, "max")  LIB:2168
-            z[i] = v;
-            zi[i] = v;
-        }
-    }
 }
 
 // ---- bit packing ------------------------------------------------------------------------------
@@ -1071,12 +1065,16 @@ extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, co
                                                         work, ctr, uniq, U);
 }
 
-extern "C" void rvl_launch_ttable(const RvlParams *P, RvlTarget *tg, const double *u_all, const uint64_t *seeds,
-                                  const double *bcvtab, double *tt, RvlCandHead *slots, int nslots,
-                                  unsigned long long *work, cudaStream_t st)
+extern "C" void rvl_launch_advance(const RvlParams *P, RvlTarget *tg, const double *u_all, const uint64_t *seeds_in,
+                                   uint64_t *seeds_out, const double *bcvtab, double *tt, RvlCandHead *slots,
+                                   int nslots, unsigned long long *work, const unsigned char *recv, size_t rec_bytes,
+                                   int iter, int iters, int first_null, int64_t *top, double *top_score,
+                                   uint64_t *seed_iter, int allow_incr, cudaStream_t st)
 {
-    dim3 grid(P->tt_nodes, P->T);
-    k_ttable<<<grid, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, u_all, seeds, bcvtab, tt, slots, nslots, work);
+    dim3 grid(P->dense_x ? 1 : P->tt_nodes, P->T);
+    k_advance<<<grid, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, u_all, seeds_in, seeds_out, bcvtab, tt, slots, nslots, work,
+                                                     recv, rec_bytes, iter, iters, first_null, top, top_score, seed_iter,
+                                                     allow_incr);
 }
 
 // FP64 FMA peak micro-benchmark (MEASURED_PEAKS.json has no FP64 figure): 8 independent DFMA chains
@@ -1098,13 +1096,6 @@ extern "C" void rvl_launch_fp64_peak(int blocks, int threads, int iters, double 
     k_fp64_peak<<<blocks, threads, 0, st>>>(iters, 1.0, out);
 }
 
-extern "C" void rvl_launch_seed_prep(const RvlParams *P, RvlTarget *tg, const uint64_t *seeds,
-                                     const double *bcvtab, RvlCandHead *part, int nslots, unsigned long long *work,
-                                     cudaStream_t st)
-{
-    k_seed_prep<<<P->T, 128, 0, st>>>(*P, tg, seeds, bcvtab, part, nslots, work);
-}
-
 extern "C" void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of,
                                  const double *u_all, const double *xc_all, const uint64_t *y_all,
                                  const double *bcvtab, double *out, size_t y_stride, size_t out_stride,
@@ -1118,13 +1109,6 @@ extern "C" void rvl_launch_argmax(const RvlParams *P, const RvlCandHead *part, i
                                   unsigned char *send, size_t rec_bytes, cudaStream_t st)
 {
     k_argmax<<<P->T, 1024, 0, st>>>(*P, part, nparts, bits, send, rec_bytes);
-}
-
-extern "C" void rvl_launch_merge(const RvlParams *P, int iter, int iters, int first_null,
-                                 const unsigned char *recv, size_t rec_bytes, uint64_t *seeds, int64_t *top,
-                                 double *top_score, uint64_t *seed_iter, cudaStream_t st)
-{
-    k_merge<<<P->T, 128, 0, st>>>(*P, iter, iters, first_null, recv, rec_bytes, seeds, top, top_score, seed_iter);
 }
 
 extern "C" void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols,
