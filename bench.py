@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="candidate exchange between ranks: peer-memory stores over NVLink (CUDA IPC) or NCCL all-gather")
     return ap.parse_args()
 
 
@@ -196,12 +198,18 @@ def main():
     recv = torch.zeros(nb * world, dtype=torch.uint8, device="cuda") if world > 1 else send
     ctx.set_exchange_buffers(send.data_ptr(), recv.data_ptr())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    use_p2p = world > 1 and args.exchange == "p2p"
+    if use_p2p:   # every rank maps every other rank's exchange buffer (CUDA IPC); NCCL only carries the handles
+        mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
+        allh = torch.empty(64 * world, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh, mine)
+        ctx.p2p_import(allh.cpu().numpy().tobytes())
 
     def one_search():
         ctx.search_begin(iters)
         for it in range(iters):
             ctx.iter_score(it)
-            if world > 1:
+            if world > 1 and not use_p2p:
                 dist.all_gather_into_tensor(recv, send)
             ctx.iter_merge(it)
 
@@ -327,6 +335,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "samples": n, "features": F, "iterations": iters, "targets": T,
                        "sharding": "feature rows, contiguous blocks, %d rank(s)" % world,
+                       "exchange": ("peer-memory stores (CUDA IPC over NVLink)" if use_p2p else
+                                    ("NCCL all_gather" if world > 1 else "none")),
                        "l2": "flushed between timed steps (256 MiB write); bit matrix %.1f MB < L2" % (cnt * words * 8 / 1e6),
                        "step": "one full search: iterations x (score + rank + merge + seed IC)"},
             "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,

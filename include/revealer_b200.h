@@ -136,6 +136,16 @@ int rvl_search(rvl_ctx *ctx, int iters, rvl_result *out);
  * rvl_search_begin resets the iteration state (and computes ic_seed0); rvl_search_fetch copies results out.
  * The exchange buffers are DEVICE memory owned by the caller (so a torch tensor can back them):
  * send: rvl_candidate_bytes(ctx) bytes; recv: world * that. */
+/* Peer-memory exchange instead of the caller's all-gather (ranks = processes on one NVLink/NVSwitch
+ * node): every rank exports a CUDA-IPC handle of its exchange buffer (after the matrix and targets are
+ * set), the host passes all `world` handles (64 bytes each, rank order) to every rank, and from then on
+ * rvl_iter_score stores this rank's candidate record directly into every peer's buffer over NVLink
+ * and rvl_iter_merge waits (bounded) for the peers' stamps -- no collective call between the two.
+ * A stamp that does not arrive within ~2 s is reported as RVL_ERR_CUDA by rvl_search_fetch /
+ * rvl_synchronize.  All ranks must call rvl_search_begin the same number of times. */
+int rvl_p2p_export(rvl_ctx *ctx, unsigned char *handle64);
+int rvl_p2p_import(rvl_ctx *ctx, const unsigned char *handles, int world);
+int rvl_p2p_disable(rvl_ctx *ctx);
 int rvl_search_begin(rvl_ctx *ctx, int iters);
 size_t rvl_candidate_bytes(const rvl_ctx *ctx);
 int rvl_set_exchange_buffers(rvl_ctx *ctx, void *dev_send, void *dev_recv);

@@ -51,6 +51,9 @@ SIGNATURES = {
     "rvl_set_seed": (_i, [_vp, _u8p, _i64, _i]),
     "rvl_score_once": (_i, [_vp, _dp]),
     "rvl_search": (_i, [_vp, _i, C.POINTER(rvl_result)]),
+    "rvl_p2p_export": (_i, [_vp, _u8p]),
+    "rvl_p2p_import": (_i, [_vp, _u8p, _i]),
+    "rvl_p2p_disable": (_i, [_vp]),
     "rvl_search_begin": (_i, [_vp, _i]),
     "rvl_candidate_bytes": (C.c_size_t, [_vp]),
     "rvl_set_exchange_buffers": (_i, [_vp, _vp, _vp]),

@@ -221,6 +221,20 @@ class RevealerContext:
     def set_exchange_buffers(self, send_ptr, recv_ptr):
         self._ck(self._lib.rvl_set_exchange_buffers(self._h, C.c_void_p(int(send_ptr)), C.c_void_p(int(recv_ptr))))
 
+    def p2p_export(self):
+        """64-byte CUDA-IPC handle of this rank's exchange buffer (see rvl_p2p_export)."""
+        h = (C.c_uint8 * 64)()
+        self._ck(self._lib.rvl_p2p_export(self._h, h))
+        return bytes(h)
+
+    def p2p_import(self, handles):
+        """handles: the `world` exported handles concatenated in rank order (world * 64 bytes)."""
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._ck(self._lib.rvl_p2p_import(self._h, buf, len(handles) // 64))
+
+    def p2p_disable(self):
+        self._ck(self._lib.rvl_p2p_disable(self._h))
+
     def iter_score(self, it):
         self._ck(self._lib.rvl_iter_score(self._h, int(it)))
 

@@ -39,13 +39,13 @@ void rvl_launch_advance(const RvlParams *P, RvlTarget *tg, const double *u_all, 
                         uint64_t *seeds_out, const double *bcvtab, double *tt, RvlCandHead *slots, int nslots,
                         unsigned long long *work, const unsigned char *recv, size_t rec_bytes, int iter, int iters,
                         int first_null, int64_t *top, double *top_score, uint64_t *seed_iter, int allow_incr,
-                        cudaStream_t st);
+                        const RvlPeerXchg *X, cudaStream_t st);
 void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaStream_t st);
 void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of, const double *u_all,
                       const double *xc_all, const uint64_t *y_all, const double *bcvtab, double *out,
                       size_t y_stride, size_t out_stride, cudaStream_t st);
 void rvl_launch_argmax(const RvlParams *P, const RvlCandHead *part, int nparts, const uint64_t *bits,
-                       unsigned char *send, size_t rec_bytes, cudaStream_t st);
+                       unsigned char *send, size_t rec_bytes, const RvlPeerXchg *X, cudaStream_t st);
 void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols, int words,
                                   uint64_t *bits, int *flag, cudaStream_t st);
 void rvl_launch_pack_u8_rowmajor(const uint8_t *m, int64_t F0, int64_t Fc, int n, int words, uint64_t *bits,
@@ -118,6 +118,16 @@ struct rvl_ctx {
     unsigned char *d_own_xchg = nullptr;                // owned fallback (world == 1)
     size_t own_xchg_bytes = 0;
 
+    // peer-memory exchange of the candidate records (rvl_p2p_export / rvl_p2p_import)
+    unsigned char *d_xchg = nullptr;   // this rank's buffer: [2][world][T] records + [2][world][T] stamps
+    size_t xchg_bytes = 0, xchg_stamps_off = 0;
+    int xchg_world = 0, xchg_T = 0, xchg_words = 0;
+    unsigned char **d_peers = nullptr; // device array [world] of every rank's buffer
+    std::vector<void *> opened;        // peer mappings to close
+    bool p2p = false;
+    int *d_xerr = nullptr;
+    unsigned int epoch = 0;
+
     // per-CTA bests of the last k_score launch [T][score_grid_x]; side stream for the seed IC
     RvlCandHead *d_part = nullptr;
     size_t part_cap = 0;
@@ -138,6 +148,8 @@ struct rvl_ctx {
     double score_ms = 0.0;
     int64_t score_launches = 0;
 };
+
+static void p2p_release(rvl_ctx *c);
 
 static int fail(rvl_ctx *c, int code, const char *fmt, ...)
 {
@@ -224,6 +236,8 @@ extern "C" int rvl_create(rvl_ctx **out, int device)
     rvl_default_options(&ctx->opts);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->d_xerr, sizeof(int)) != cudaSuccess ||
+        cudaMemset(ctx->d_xerr, 0, sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_ctr, 4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_ctr, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -270,6 +284,8 @@ extern "C" void rvl_destroy(rvl_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_matrix(ctx); free_targets(ctx); free_results(ctx);
+    p2p_release(ctx);
+    dfree(ctx->d_xerr);
     dfree(ctx->d_flag);
     dfree(ctx->d_ctr);
     for (auto &p : ctx->score_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -644,8 +660,10 @@ static int prep_iteration(rvl_ctx *ctx)
     }
     const int nslots = ctx->score_grid_x * rvl_score_warps();
     // no merge here (recv = NULL): seed state + full table build for the seeds as they are
+    RvlPeerXchg Xnone;
+    memset(&Xnone, 0, sizeof Xnone);
     rvl_launch_advance(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_seed_alt, ctx->d_bcvtab, ctx->d_tt, ctx->d_part, nslots,
-                       ctx->d_work, nullptr, 0, 0, 1, ctx->first_null, nullptr, nullptr, nullptr, 0, ctx->stream);
+                       ctx->d_work, nullptr, 0, 0, 1, ctx->first_null, nullptr, nullptr, nullptr, 0, &Xnone, ctx->stream);
     ctx->work_dirty = false;
     ctx->launches++;
     CK(cudaGetLastError());
@@ -659,6 +677,28 @@ static int ready(rvl_ctx *ctx)
     if (!ctx->have_seed) return fail(ctx, RVL_ERR_STATE, "seed not set");
     if (ctx->opts.n_grid != ctx->G_targets) return fail(ctx, RVL_ERR_STATE, "n_grid changed after rvl_set_targets");
     return RVL_OK;
+}
+
+static void p2p_release(rvl_ctx *c)
+{
+    for (void *p : c->opened) cudaIpcCloseMemHandle(p);
+    c->opened.clear();
+    dfree(c->d_xchg);
+    dfree(c->d_peers);
+    c->p2p = false;
+    c->xchg_bytes = 0;
+}
+
+static RvlPeerXchg make_xchg(const rvl_ctx *c, int iter)
+{
+    RvlPeerXchg X;
+    X.peers = c->p2p ? c->d_peers : nullptr;
+    X.local = c->d_xchg;
+    X.stamps_off = c->xchg_stamps_off;
+    X.stamp = (c->epoch << 16) | (unsigned int)(iter + 1);
+    X.parity = iter & 1;
+    X.err = c->d_xerr;
+    return X;
 }
 
 extern "C" size_t rvl_candidate_bytes(const rvl_ctx *ctx)
@@ -731,6 +771,19 @@ static int join_side(rvl_ctx *ctx)
     return RVL_OK;
 }
 
+// A peer-exchange stamp that never arrived (k_advance's bounded wait) is an error, not a silent result.
+static int check_xerr(rvl_ctx *ctx)
+{
+    if (!ctx->p2p) return RVL_OK;
+    int h = 0;
+    CK(cudaMemcpy(&h, ctx->d_xerr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h) {
+        cudaMemset(ctx->d_xerr, 0, sizeof(int));
+        return fail(ctx, RVL_ERR_CUDA, "peer exchange timed out: a rank did not deliver its candidate record");
+    }
+    return RVL_OK;
+}
+
 static int drain_score_events(rvl_ctx *ctx)
 {
     for (size_t i = 0; i < ctx->score_events_used; i++) {
@@ -762,7 +815,11 @@ extern "C" int rvl_search_begin(rvl_ctx *ctx, int iters)
         }
         ctx->d_send = ctx->d_recv = ctx->d_own_xchg; // world of one: the record is its own gather
     }
-    if (!ctx->d_send || !ctx->d_recv) return fail(ctx, RVL_ERR_STATE, "world > 1 needs rvl_set_exchange_buffers");
+    if (ctx->p2p && (ctx->xchg_world != ctx->world || ctx->xchg_T != ctx->T || ctx->xchg_words != ctx->words))
+        return fail(ctx, RVL_ERR_STATE, "peer exchange was set up for another shape: call rvl_p2p_export/import again");
+    if (!ctx->p2p && (!ctx->d_send || !ctx->d_recv))
+        return fail(ctx, RVL_ERR_STATE, "world > 1 needs rvl_set_exchange_buffers or rvl_p2p_import");
+    if (ctx->p2p) ctx->epoch = (ctx->epoch + 1) & 0x7fff;
     RvlParams P = make_params(ctx);
     CK(cudaMemcpyAsync(ctx->d_seed, ctx->d_seed0, sizeof(uint64_t) * (size_t)ctx->T * ctx->words, cudaMemcpyDeviceToDevice, ctx->stream));
     rc = prep_iteration(ctx);
@@ -782,8 +839,9 @@ extern "C" int rvl_iter_score(rvl_ctx *ctx, int iter)
     int rc = launch_score(ctx, ctx->d_scores + (size_t)iter * ctx->T * ctx->F);
     if (rc) return rc;
     RvlParams P2 = make_params(ctx);
+    RvlPeerXchg X = make_xchg(ctx, iter);
     rvl_launch_argmax(&P2, ctx->d_part, ctx->score_grid_x * rvl_score_warps(), ctx->d_bits, ctx->d_send,
-                      sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, ctx->stream);
+                      sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, &X, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     return RVL_OK;
@@ -795,10 +853,11 @@ extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
     if (iter < 0 || iter >= ctx->iters) return fail(ctx, RVL_ERR_ARG, "iter out of range");
     RvlParams P = make_params(ctx);
     // merge + seed state + x-axis table in one launch; seeds ping-pong between the two buffers
+    RvlPeerXchg X = make_xchg(ctx, iter);
     rvl_launch_advance(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_seed_alt, ctx->d_bcvtab, ctx->d_tt, ctx->d_part,
-                       ctx->score_grid_x * rvl_score_warps(), ctx->d_work, ctx->d_recv,
+                       ctx->score_grid_x * rvl_score_warps(), ctx->d_work, ctx->p2p ? ctx->d_xchg : ctx->d_recv,
                        sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, iter, ctx->iters, ctx->first_null,
-                       ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, 1, ctx->stream);
+                       ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, 1, &X, ctx->stream);
     { uint64_t *tmp = ctx->d_seed; ctx->d_seed = ctx->d_seed_alt; ctx->d_seed_alt = tmp; }
     ctx->work_dirty = false;
     ctx->launches += 1;
@@ -824,7 +883,7 @@ extern "C" int rvl_synchronize(rvl_ctx *ctx)
     if (jrc) return jrc;
     CK(cudaStreamSynchronize(ctx->stream));
     drain_score_events(ctx);
-    return RVL_OK;
+    return check_xerr(ctx);
 }
 
 extern "C" int rvl_search_fetch(rvl_ctx *ctx, rvl_result *out)
@@ -837,6 +896,8 @@ extern "C" int rvl_search_fetch(rvl_ctx *ctx, rvl_result *out)
     if (jrc) return jrc;
     CK(cudaStreamSynchronize(ctx->stream));
     drain_score_events(ctx);
+    jrc = check_xerr(ctx);
+    if (jrc) return jrc;
     if (ctx->fill_pending && ctx->F > 0) { // duplicate rows get their group's score, once, for all iterations
         rvl_launch_fill_duplicates(ctx->d_scores, ctx->F, (int64_t)iters * T, ctx->d_rep, ctx->stream);
         ctx->launches++;
@@ -1085,3 +1146,61 @@ extern "C" int rvl_set_dedup(rvl_ctx *ctx, int on)
 }
 
 extern "C" int64_t rvl_unique_rows(const rvl_ctx *ctx) { return ctx ? ctx->U : 0; }
+
+// ---- peer-memory exchange (CUDA IPC over NVLink) ---------------------------------------------------
+
+extern "C" int rvl_p2p_export(rvl_ctx *ctx, unsigned char *handle64)
+{
+    GUARD();
+    if (!handle64) return fail(ctx, RVL_ERR_ARG, "handle is NULL");
+    if (ctx->T <= 0 || ctx->words <= 0) return fail(ctx, RVL_ERR_STATE, "set the matrix/targets before rvl_p2p_export");
+    if (ctx->world < 2) return fail(ctx, RVL_ERR_STATE, "rvl_p2p_export needs rvl_set_shard with world > 1");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaStreamSynchronize(ctx->stream));
+    p2p_release(ctx);
+    size_t rec = sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words;
+    size_t recs = 2 * (size_t)ctx->world * ctx->T * rec;
+    ctx->xchg_stamps_off = (recs + 255) & ~(size_t)255;
+    ctx->xchg_bytes = ctx->xchg_stamps_off + 2 * (size_t)ctx->world * ctx->T * sizeof(unsigned int);
+    CK(cudaMalloc((void **)&ctx->d_xchg, ctx->xchg_bytes));
+    CK(cudaMemset(ctx->d_xchg, 0, ctx->xchg_bytes));
+    ctx->xchg_world = ctx->world; ctx->xchg_T = ctx->T; ctx->xchg_words = ctx->words;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->d_xchg));
+    memcpy(handle64, &h, 64);
+    return RVL_OK;
+}
+
+extern "C" int rvl_p2p_import(rvl_ctx *ctx, const unsigned char *handles, int world)
+{
+    GUARD();
+    if (!handles || world != ctx->world || !ctx->d_xchg) return fail(ctx, RVL_ERR_ARG, "rvl_p2p_import: export first; world must match rvl_set_shard");
+    std::vector<unsigned char *> ptrs(world, nullptr);
+    for (int r = 0; r < world; r++) {
+        if (r == ctx->rank) { ptrs[r] = ctx->d_xchg; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (void *q : ctx->opened) cudaIpcCloseMemHandle(q);
+            ctx->opened.clear();
+            return fail(ctx, RVL_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        ctx->opened.push_back(p);
+        ptrs[r] = (unsigned char *)p;
+    }
+    dfree(ctx->d_peers);
+    CK(dalloc(&ctx->d_peers, (size_t)world));
+    CK(cudaMemcpy(ctx->d_peers, ptrs.data(), sizeof(unsigned char *) * world, cudaMemcpyHostToDevice));
+    ctx->p2p = true;
+    return RVL_OK;
+}
+
+extern "C" int rvl_p2p_disable(rvl_ctx *ctx)
+{
+    GUARD();
+    CK(cudaStreamSynchronize(ctx->stream));
+    p2p_release(ctx);
+    return RVL_OK;
+}

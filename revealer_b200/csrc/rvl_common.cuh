@@ -42,6 +42,20 @@ struct RvlCandHead {
     int64_t row;
 };
 
+// Peer-memory exchange of the candidate records (instead of an NCCL all-gather): every rank owns one
+// buffer  [2 parities][world][T] records  +  [2][world][T] uint32 stamps, mapped into every other
+// rank with CUDA IPC.  k_argmax stores its record into slot [parity][rank][t] of EVERY rank's buffer over
+// NVLink, fences, then stores the stamp; k_advance polls the stamps in its own (local) buffer.
+// peers == NULL disables the path.
+struct RvlPeerXchg {
+    unsigned char *const *peers; // device array [world]: base of every rank's buffer (own entry = local)
+    unsigned char *local;        // this rank's buffer
+    size_t stamps_off;           // byte offset of the stamp array inside a buffer
+    unsigned int stamp;          // (search epoch << 16) | (iteration + 1)
+    int parity;                  // iteration & 1
+    int *err;                    // set to 1 when a stamp did not arrive in time
+};
+
 struct RvlParams {
     int32_t n;        // samples
     int32_t words;    // uint64 per bit row (row stride)

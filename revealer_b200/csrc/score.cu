@@ -448,7 +448,8 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
           uint64_t *__restrict__ seeds_out, const double *__restrict__ bcvtab, double *__restrict__ tt,
           RvlCandHead *__restrict__ slots, int nslots, unsigned long long *__restrict__ work,
           const unsigned char *__restrict__ recv, size_t rec_bytes, int iter, int iters, int first_null,
-          int64_t *__restrict__ top, double *__restrict__ top_score, uint64_t *__restrict__ seed_iter, int allow_incr)
+          int64_t *__restrict__ top, double *__restrict__ top_score, uint64_t *__restrict__ seed_iter, int allow_incr,
+          RvlPeerXchg X)
 {
     __shared__ double part[RVL_SCORE_WARPS][2][RVL_MAXG];
     __shared__ int s_nz_old, s_nz_new, s_win;
@@ -459,6 +460,24 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
     const bool is_null = (first_null > 0 && t >= first_null);
     const uint64_t *zold = seeds_in + (size_t)owner * P.words;
     const uint64_t *wrow = nullptr; // the winner's bit row (merge only)
+    if (recv && X.peers) {
+        // peer exchange: the records of this iteration sit in the local buffer once every rank's stamp
+        // for (parity, rank, owner) has arrived
+        recv = X.local + (size_t)X.parity * P.world * P.T * rec_bytes;
+        if (threadIdx.x < P.world) {
+            volatile unsigned int *st = reinterpret_cast<volatile unsigned int *>(X.local + X.stamps_off) +
+                                        ((size_t)X.parity * P.world + threadIdx.x) * P.T + owner;
+            const long long t0 = clock64();
+            while (*st != X.stamp) {
+                if (clock64() - t0 > 4000000000ll) { // ~2 s: a peer is gone; fail loudly instead of hanging
+                    *X.err = 1;
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+    }
     if (recv) {
         if (threadIdx.x == 0) {
             double bv = 0.0;
@@ -859,8 +878,11 @@ k_assoc(RvlParams P, const RvlTarget *__restrict__ tg_all, const int *__restrict
 
 // One block per target: reduce the per-CTA bests k_score left in part[target][nparts] and write the
 // candidate record [score][global row][bit row] into the send buffer.
+// With a peer exchange (X.peers) the record goes straight into every rank's buffer over NVLink and
+// is followed by a stamp; otherwise into `send` for the caller's all-gather.
 __global__ void k_argmax(RvlParams P, const RvlCandHead *__restrict__ part, int nparts,
-                         const uint64_t *__restrict__ bits, unsigned char *__restrict__ send, size_t rec_bytes)
+                         const uint64_t *__restrict__ bits, unsigned char *__restrict__ send, size_t rec_bytes,
+                         RvlPeerXchg X)
 {
     __shared__ double shv[32];
     __shared__ long long shi[32];
@@ -893,11 +915,24 @@ __global__ void k_argmax(RvlParams P, const RvlCandHead *__restrict__ part, int 
     }
     __syncthreads();
     bv = shv[0]; bi = shi[0];
-    unsigned char *rec = send + (size_t)t * rec_bytes;
-    RvlCandHead *h = reinterpret_cast<RvlCandHead *>(rec);
-    uint64_t *rb = reinterpret_cast<uint64_t *>(rec + sizeof(RvlCandHead));
-    if (threadIdx.x == 0) { h->score = bv; h->row = (bi < 0) ? -1 : (P.row_offset + bi); }
-    for (int i = threadIdx.x; i < P.words; i += blockDim.x) rb[i] = (bi < 0) ? 0ull : bits[(size_t)bi * P.words + i];
+    const int ndst = X.peers ? P.world : 1;
+    const size_t slot = ((size_t)X.parity * P.world + P.rank) * P.T + t;
+    for (int r = 0; r < ndst; r++) {
+        unsigned char *rec = X.peers ? X.peers[r] + slot * rec_bytes : send + (size_t)t * rec_bytes;
+        RvlCandHead *h = reinterpret_cast<RvlCandHead *>(rec);
+        uint64_t *rb = reinterpret_cast<uint64_t *>(rec + sizeof(RvlCandHead));
+        if (threadIdx.x == 0) { h->score = bv; h->row = (bi < 0) ? -1 : (P.row_offset + bi); }
+        for (int i = threadIdx.x; i < P.words; i += blockDim.x) rb[i] = (bi < 0) ? 0ull : bits[(size_t)bi * P.words + i];
+    }
+    if (X.peers) {
+        __threadfence_system(); // records visible to every GPU before any stamp
+        __syncthreads();
+        if (threadIdx.x < P.world) {
+            volatile unsigned int *st =
+                reinterpret_cast<volatile unsigned int *>(X.peers[threadIdx.x] + X.stamps_off) + slot;
+            *st = X.stamp;
+        }
+    }
 }
 
 // ---- bit packing ------------------------------------------------------------------------------
@@ -1069,12 +1104,12 @@ extern "C" void rvl_launch_advance(const RvlParams *P, RvlTarget *tg, const doub
                                    uint64_t *seeds_out, const double *bcvtab, double *tt, RvlCandHead *slots,
                                    int nslots, unsigned long long *work, const unsigned char *recv, size_t rec_bytes,
                                    int iter, int iters, int first_null, int64_t *top, double *top_score,
-                                   uint64_t *seed_iter, int allow_incr, cudaStream_t st)
+                                   uint64_t *seed_iter, int allow_incr, const RvlPeerXchg *X, cudaStream_t st)
 {
     dim3 grid(P->dense_x ? 1 : P->tt_nodes, P->T);
     k_advance<<<grid, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, u_all, seeds_in, seeds_out, bcvtab, tt, slots, nslots, work,
                                                      recv, rec_bytes, iter, iters, first_null, top, top_score, seed_iter,
-                                                     allow_incr);
+                                                     allow_incr, *X);
 }
 
 // FP64 FMA peak micro-benchmark (MEASURED_PEAKS.json has no FP64 figure): 8 independent DFMA chains
@@ -1106,9 +1141,9 @@ extern "C" void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget
 }
 
 extern "C" void rvl_launch_argmax(const RvlParams *P, const RvlCandHead *part, int nparts, const uint64_t *bits,
-                                  unsigned char *send, size_t rec_bytes, cudaStream_t st)
+                                  unsigned char *send, size_t rec_bytes, const RvlPeerXchg *X, cudaStream_t st)
 {
-    k_argmax<<<P->T, 1024, 0, st>>>(*P, part, nparts, bits, send, rec_bytes);
+    k_argmax<<<P->T, 1024, 0, st>>>(*P, part, nparts, bits, send, rec_bytes, *X);
 }
 
 extern "C" void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols,
