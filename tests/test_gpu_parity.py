@@ -522,6 +522,36 @@ def test_two_shards_equal_single_shard():
         c.close()
 
 
+# ------------------------------------------------------------------ config C4's sample count (n = 10 000)
+
+def test_c4_sample_count_rows_match_oracle(oracle):
+    """n = 10 000 (BASELINE config C4): multi-row seed, 157-word bit rows, the n >= 5793 range where the
+    original VR_bcv_bin's int product 64*n*n would overflow (evaluated in double here and in the oracle)."""
+    from revealer_b200 import synth
+    n, F = 10000, 400
+    rng = np.random.Generator(np.random.PCG64(synth.BASE_SEED + 3))
+    x = synth.make_target(n, rng)
+    m2 = synth.make_features(n, F, np.random.Generator(np.random.PCG64(5)))
+    seed = (m2[10] | m2[20] | m2[30]).astype(np.uint8)          # three rows OR-ed (LIB:1697)
+    with _ctx() as ctx:
+        ctx.load_matrix(m2)
+        ctx.set_targets(x)
+        ctx.set_seed(seed)
+        g = ctx.score_once()[0]
+        bw = ctx.target_bandwidth(0)
+        tab = ctx.binary_bandwidth_table()
+        res = ctx.search(2)
+    assert abs(bw - oracle.bcv(x)) <= 1e-12 * bw
+    rows = [0, 57, 123, 399]
+    o = oracle.score_rows(x, m2[rows].astype(float), seed.astype(float))
+    ok, err = score_close(g[rows], o)
+    assert ok, err
+    y = m2[57].astype(float)
+    assert abs(tab[int(y.sum())] - oracle.bcv(y)) <= 1e-12 * oracle.bcv(y)
+    top = int(res["top"][0, 0])
+    assert g[top] == np.nanmax(g) and np.array_equal(res["seed_iter"][0, 0], np.maximum(seed, m2[top]))
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE config C3)
 
 @pytest.fixture(scope="module")
