@@ -559,27 +559,62 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
     // class 0, IC dispatch) whose x bandwidth bcv/4 coincides with bw_mult*bcv when bw_mult = 0.25
     const bool incr = allow_incr && recv && mode == RVL_MODE_CIC &&
                       (mode_old == RVL_MODE_CIC || (mode_old == RVL_MODE_IC && nz_old == 0 && P.bw_mult == 0.25));
+    __shared__ double su[1024];
+    __shared__ uint64_t sz[16];
     if (incr) {
-        if (warp != 0) return;
+        // The words holding newly set bits are compacted, in ascending order, into shared memory by the
+        // whole block (coalesced loads, ballot prefix sums -- no atomics, so the order and with it the
+        // last bit of every sum is the same on every rank and in every run); the warps then share the
+        // samples and their partial sums are added in warp order.
+        __shared__ uint32_t s_idx[1024];
+        __shared__ int s_wcnt[RVL_SCORE_WARPS];
+        uint64_t *sval = reinterpret_cast<uint64_t *>(su); // [<= 1024] the new bits of those words
         double d = 0.0;
-        for (int w = 0; w < P.words; w++) {
-            uint64_t v = wrow[w] & ~zold[w]; // samples entering z-class 1 (warp-uniform word)
-            while (v) {
-                const int b = __ffsll((long long)v) - 1;
-                v &= v - 1;
-                const double dd = gi - u[w * 64 + b];
-                d += rvl_exp_neg(-beta * dd * dd);
+        for (int base = 0; base < P.words; base += 1024) {
+            int total = 0;
+            for (int sub = 0; sub < 1024 && base + sub < P.words; sub += blockDim.x) {
+                const int w = base + sub + threadIdx.x;
+                const uint64_t v = (w < P.words && w < base + 1024) ? (wrow[w] & ~zold[w]) : 0ull; // entering z-class 1
+                const unsigned bal = __ballot_sync(0xffffffffu, v != 0ull);
+                if (lane == 0) s_wcnt[warp] = __popc(bal);
+                __syncthreads();
+                int off = total;
+                for (int q = 0; q < warp; q++) off += s_wcnt[q];
+                int all = 0;
+                for (int q = 0; q < nwarps; q++) all += s_wcnt[q];
+                if (v) {
+                    const int pos = off + __popc(bal & ((1u << lane) - 1u));
+                    s_idx[pos] = (uint32_t)w;
+                    sval[pos] = v;
+                }
+                total += all;
+                __syncthreads();
             }
+            for (int q = warp; q < total; q += nwarps) { // word q: warp-uniform
+                uint64_t v = sval[q];
+                const int w = (int)s_idx[q];
+                while (v) {
+                    const int bb = __ffsll((long long)v) - 1;
+                    v &= v - 1;
+                    const double dd = gi - u[w * 64 + bb];
+                    d += rvl_exp_neg(-beta * dd * dd);
+                }
+            }
+            __syncthreads();
         }
-        out[lane] -= d;
-        out[RVL_MAXG + lane] += d;
+        part[warp][0][lane] = d;
+        __syncthreads();
+        if (warp == 0) {
+            double tot = 0.0;
+            for (int q = 0; q < nwarps; q++) tot += part[q][0][lane];
+            out[lane] -= tot;
+            out[RVL_MAXG + lane] += tot;
+        }
         return;
     }
 
     // full build: samples staged through shared memory in chunks of 1024 (coalesced loads, broadcast reads)
     const bool use_z = (mode == RVL_MODE_CIC);
-    __shared__ double su[1024];
-    __shared__ uint64_t sz[16];
     double a0 = 0.0, a1 = 0.0;
     for (int base = 0; base < P.n; base += 1024) {
         const int cnt = min(1024, P.n - base);
