@@ -150,6 +150,7 @@ struct rvl_ctx {
 };
 
 static void p2p_release(rvl_ctx *c);
+static void quiesce_side(rvl_ctx *c);
 
 static int fail(rvl_ctx *c, int code, const char *fmt, ...)
 {
@@ -402,8 +403,11 @@ static int build_dedup(rvl_ctx *ctx)
 
 static int begin_matrix(rvl_ctx *ctx, int64_t F, int64_t n)
 {
+    quiesce_side(ctx);
     if (F < 0 || n < 2 || n > (1 << 24)) return fail(ctx, RVL_ERR_ARG, "need F >= 0 and 2 <= n <= 2^24 (F=%lld n=%lld)", (long long)F, (long long)n);
     if (ctx->T > 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "matrix has n=%lld but targets have n=%d", (long long)n, ctx->n);
+    if (rvl_score_smem_bytes((int)n, (int)(((n + 63) / 64 + 1) & ~1ll)) > 227 * 1024)
+        return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (8 bit rows of n/8 bytes per block; n <= ~190 000)", (long long)n);
     free_matrix(ctx);
     ctx->n = (int)n;
     ctx->words = (int)(((n + 63) / 64 + 1) & ~1ll); // rows padded to 16 B
@@ -536,8 +540,11 @@ extern "C" int rvl_set_targets_permuted(rvl_ctx *ctx, const double *targets, int
 
 static int set_targets_impl(rvl_ctx *ctx, const double *targets, int64_t n, int64_t n_targets, int permuted)
 {
+    quiesce_side(ctx);
     if (!targets || n < 2 || n_targets < 1 || n_targets > 65535) return fail(ctx, RVL_ERR_ARG, "bad targets (n=%lld, n_targets=%lld; need n >= 2, 1 <= n_targets <= 65535)", (long long)n, (long long)n_targets);
     if (ctx->F >= 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "targets have n=%lld but matrix has n=%d", (long long)n, ctx->n);
+    if (rvl_score_smem_bytes((int)n, (int)(((n + 63) / 64 + 1) & ~1ll)) > 227 * 1024)
+        return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (8 bit rows of n/8 bytes per block; n <= ~190 000)", (long long)n);
     free_targets(ctx);
     if (ctx->F < 0) { ctx->n = (int)n; ctx->words = (int)(((n + 63) / 64 + 1) & ~1ll); }
     int T = (int)n_targets;
@@ -595,6 +602,7 @@ extern "C" int rvl_set_null_targets(rvl_ctx *ctx, int64_t first_null)
 extern "C" int rvl_set_seed(rvl_ctx *ctx, const uint8_t *seed, int64_t n, int per_target)
 {
     GUARD();
+    quiesce_side(ctx);
     if (ctx->T <= 0) return fail(ctx, RVL_ERR_STATE, "set targets before the seed");
     if (!seed || n != ctx->n) return fail(ctx, RVL_ERR_ARG, "seed length %lld != n %d", (long long)n, ctx->n);
     int T = ctx->T, words = ctx->words;
@@ -677,6 +685,15 @@ static int ready(rvl_ctx *ctx)
     if (!ctx->have_seed) return fail(ctx, RVL_ERR_STATE, "seed not set");
     if (ctx->opts.n_grid != ctx->G_targets) return fail(ctx, RVL_ERR_STATE, "n_grid changed after rvl_set_targets");
     return RVL_OK;
+}
+
+// Inputs are about to be replaced: let the side-stream seed ICs that still read them finish.
+static void quiesce_side(rvl_ctx *c)
+{
+    if (c->side_pending) {
+        cudaStreamSynchronize(c->side);
+        c->side_pending = false;
+    }
 }
 
 static void p2p_release(rvl_ctx *c)
@@ -824,9 +841,13 @@ extern "C" int rvl_search_begin(rvl_ctx *ctx, int iters)
     CK(cudaMemcpyAsync(ctx->d_seed, ctx->d_seed0, sizeof(uint64_t) * (size_t)ctx->T * ctx->words, cudaMemcpyDeviceToDevice, ctx->stream));
     rc = prep_iteration(ctx);
     if (rc) return rc;
-    // cmi.seed.iter0 <- assoc(target, seed)  LIB:1833
-    rvl_launch_assoc(&P, ctx->T, ctx->d_tg, nullptr, ctx->d_u, ctx->d_xc, ctx->d_seed, ctx->d_bcvtab, ctx->d_ic0,
-                     (size_t)ctx->words, 1, ctx->stream);
+    // cmi.seed.iter0 <- assoc(target, seed)  LIB:1833 -- off the critical path like the per-iteration seed ICs:
+    // side stream, reading the immutable initial seeds
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    rvl_launch_assoc(&P, ctx->T, ctx->d_tg, nullptr, ctx->d_u, ctx->d_xc, ctx->d_seed0, ctx->d_bcvtab, ctx->d_ic0,
+                     (size_t)ctx->words, 1, ctx->side);
+    ctx->side_pending = true;
     ctx->launches += 1;
     CK(cudaGetLastError());
     return RVL_OK;

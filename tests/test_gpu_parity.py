@@ -287,6 +287,37 @@ def test_invalid_inputs_raise_no_fallback():
         rb.RevealerContext(99)                                      # no such device -> error, not CPU
 
 
+def test_sample_count_limit_is_an_error_not_a_crash():
+    import revealer_b200 as rb
+    from revealer_b200 import _lib
+    n = 200_000                                                  # > the shared-memory budget of k_score
+    with _ctx() as ctx:
+        with pytest.raises(rb.RevealerError) as e:
+            ctx.load_matrix(np.zeros((2, n), dtype=np.uint8))
+        assert e.value.code == _lib.RVL_ERR_ARG
+        with pytest.raises(rb.RevealerError):
+            ctx.set_targets(np.arange(n, dtype=np.float64))
+
+
+def test_many_targets_and_single_row():
+    """Degenerate shapes: one feature row against 300 targets; 2 samples."""
+    rng = np.random.default_rng(31)
+    with _ctx() as ctx:
+        ctx.load_matrix((rng.random((1, 64)) < 0.3).astype(np.uint8))
+        ctx.set_targets(rng.standard_normal((300, 64)))
+        ctx.set_seed((rng.random(64) < 0.3).astype(np.uint8))
+        s = ctx.score_once()
+        assert s.shape == (300, 1) and np.isfinite(s).all()
+        r = ctx.search(2)
+        assert np.all(r["top"] == 0)
+    with _ctx() as ctx:                                           # n = 2: y or z is constant or trivially split
+        ctx.load_matrix(np.array([[0, 1], [1, 1], [0, 0]], dtype=np.uint8))
+        ctx.set_targets(np.array([0.5, -1.0]))
+        ctx.set_seed(np.array([1, 0], dtype=np.uint8))
+        s = ctx.score_once()[0]
+        assert s[1] == 0.0 and s[2] == 0.0 and np.isfinite(s[0]) or np.isnan(s[0])
+
+
 def test_empty_matrix():
     w = _workload(64, 20)
     with _ctx() as ctx:
