@@ -446,17 +446,13 @@ def read_gct(path):
     return dict(ds=np.asarray(data, dtype=np.float64), row_names=rows, descs=descs, names=names)
 
 
-def REVEALER_v1(ds1, target_name, target_match="positive", ds2=None, seed_names=None, exclude_features=None,
-                max_n_iter=5, pdf_output_file=None, count_thres_low=None, count_thres_high=None, n_markers=30,
-                locs_table_file=None, n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75, n_perm=0,
-                r_seed=34578, device=0):
-    """REVEALER.v1 with its 12 formals (LIB:1504-1516) plus the optional grid/bandwidth arguments.
-    ds1 / ds2: GCT path or dict(ds, row_names, names) as MSIG.Gct2Frame returns.  Preprocessing
-    mirrors LIB:1575-1707: drop NA-target samples, intersect samples, sort by target, drop the target
-    row from the features, count filter (seeds always kept), build the seed as the column-wise max of
-    the seed rows and remove those rows.  No plots/PDF (pdf_output_file and locs_table_file are accepted
-    and ignored).  n_perm > 0 adds the permutation null with numpy's PCG64(r_seed) (R's sample() stream is
-    not reproduced)."""
+def prepare_inputs(ds1, target_name, target_match="positive", ds2=None, seed_names=None, exclude_features=None,
+                   count_thres_low=None, count_thres_high=None):
+    """REVEALER.v1's preprocessing, LIB:1575-1720 (host side, numpy): drop NA-target samples, intersect the
+    samples of ds1 and ds2, sort samples by target (decreasing unless target.match == "negative"), drop the
+    target row from the features, count filter (seed rows always kept), seed = column-wise max of the seed
+    rows, seed rows and excluded features removed.  ds1 / ds2: GCT path or dict(ds, row_names, names).
+    Returns dict(target, m2, seed, seed_vectors, feature_names, sample_names, negative)."""
     d1 = read_gct(ds1) if isinstance(ds1, str) else ds1
     d2 = read_gct(ds2) if isinstance(ds2, str) else ds2
     m1 = np.asarray(d1["ds"], dtype=np.float64)
@@ -514,6 +510,25 @@ def REVEALER_v1(ds1, target_name, target_match="positive", ds2=None, seed_names=
         ex = {rows2.index(s) for s in exclude_features if s in rows2}
         m2 = np.delete(m2, sorted(ex), axis=0)
         rows2 = [r for i, r in enumerate(rows2) if i not in ex]
+    return dict(target=target, m2=m2, seed=seed, seed_vectors=seed_vectors, seed_list=seed_list, feature_names=rows2,
+                sample_names=sample_names, negative=negative)
+
+
+def REVEALER_v1(ds1, target_name, target_match="positive", ds2=None, seed_names=None, exclude_features=None,
+                max_n_iter=5, pdf_output_file=None, count_thres_low=None, count_thres_high=None, n_markers=30,
+                locs_table_file=None, n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75, n_perm=0,
+                r_seed=34578, device=0):
+    """REVEALER.v1 with its 12 formals (LIB:1504-1516) plus the optional grid/bandwidth arguments.
+    ds1 / ds2: GCT path or dict(ds, row_names, names) as MSIG.Gct2Frame returns.  Preprocessing
+    mirrors LIB:1575-1707: drop NA-target samples, intersect samples, sort by target, drop the target
+    row from the features, count filter (seeds always kept), build the seed as the column-wise max of
+    the seed rows and remove those rows.  No plots/PDF (pdf_output_file and locs_table_file are accepted
+    and ignored).  n_perm > 0 adds the permutation null with numpy's PCG64(r_seed) (R's sample() stream is
+    not reproduced)."""
+    p = prepare_inputs(ds1, target_name, target_match, ds2, seed_names, exclude_features, count_thres_low,
+                       count_thres_high)
+    target, m2, seed, seed_vectors, seed_list = p["target"], p["m2"], p["seed"], p["seed_vectors"], p["seed_list"]
+    rows2, sample_names, negative = p["feature_names"], p["sample_names"], p["negative"]
     target_rand = None
     if n_perm > 0:                                          # LIB:1843-1844
         rng = np.random.Generator(np.random.PCG64(r_seed))

@@ -130,6 +130,45 @@ def test_reference_formals_are_preserved():
     assert d["bandwidth_mult"] == 0.25 and d["bandwidth_shrink"] == -0.75
 
 
+def test_prepare_inputs_mirrors_reveler_v1_preprocessing(tmp_path):
+    """Host-side preprocessing of REVEALER.v1 (LIB:1575-1720): NA-target samples dropped, samples
+    intersected, sorted by target, target row dropped from the features, count filter with seeds kept,
+    seed = column max of the seed rows, seed rows removed; GCT files read like MSIG.Gct2Frame."""
+    from revealer_b200.api import prepare_inputs, read_gct
+    names1 = ["s%d" % i for i in range(8)]
+    names2 = ["s7", "s5", "s3", "s1", "s0", "s2", "s9"]
+    t = np.array([0.1, np.nan, 2.0, -1.0, 0.5, 3.0, 0.0, 1.5])
+    d1 = dict(ds=np.vstack([t, np.arange(8.0)]), row_names=["TGT", "other"], names=names1)
+    m = np.array([[1, 1, 1, 1, 1, 1, 1],      # TGT row inside ds2: must be dropped
+                  [1, 0, 0, 1, 1, 0, 0],      # A
+                  [0, 0, 0, 0, 0, 0, 0],      # B: fails count.thres.low
+                  [0, 1, 0, 0, 0, 0, 1],      # SEED1 (kept although only 1 one among the common samples)
+                  [1, 1, 1, 0, 1, 1, 0],      # C: 5 ones among common samples -> fails count.thres.high=4
+                  [0, 0, 1, 0, 0, 0, 0]], dtype=float)   # SEED2
+    d2 = dict(ds=m, row_names=["TGT", "A", "B", "SEED1", "C", "SEED2"], names=names2)
+    p = prepare_inputs(d1, "TGT", "positive", d2, seed_names=["SEED1", "SEED2"], count_thres_low=1, count_thres_high=4)
+    assert p["sample_names"] == ["s5", "s2", "s7", "s0", "s3"]          # common samples by decreasing target
+    assert list(p["target"]) == [3.0, 2.0, 1.5, 0.1, -1.0]
+    assert p["feature_names"] == ["A"]
+    assert list(p["seed"]) == [1, 0, 0, 0, 1] and list(p["m2"][0]) == [0, 0, 1, 1, 0]
+    n = prepare_inputs(d1, "TGT", "negative", d2, seed_names=None)
+    assert list(n["target"]) == [-1.0, 0.1, 1.5, 2.0, 3.0] and not n["seed"].any() and n["negative"]
+    assert n["feature_names"] == ["A", "B", "SEED1", "C", "SEED2"]
+    # the same through GCT files
+    def write_gct(path, d):
+        with open(path, "w") as fh:
+            fh.write("#1.2\n%d\t%d\nName\tDescription\t%s\n" % (len(d["row_names"]), len(d["names"]), "\t".join(d["names"])))
+            for r, row in zip(d["row_names"], d["ds"]):
+                fh.write("%s\tna\t%s\n" % (r, "\t".join("" if np.isnan(v) else repr(float(v)) for v in row)))
+    f1, f2 = str(tmp_path / "a.gct"), str(tmp_path / "b.gct")
+    write_gct(f1, d1)
+    write_gct(f2, d2)
+    g = read_gct(f1)
+    assert g["row_names"] == ["TGT", "other"] and np.isnan(g["ds"][0, 1]) and g["names"] == names1
+    q = prepare_inputs(f1, "TGT", "positive", f2, seed_names=["SEED1", "SEED2"], count_thres_low=1, count_thres_high=4)
+    assert q["sample_names"] == p["sample_names"] and np.array_equal(q["m2"], p["m2"]) and np.array_equal(q["seed"], p["seed"])
+
+
 def test_synthetic_workload_is_deterministic_and_shardable():
     from revealer_b200 import synth
     a = synth.make_workload(n=120, F=900)

@@ -206,6 +206,36 @@ def test_reference_shaped_functions(oracle):
         rb.assoc(x, y, "COR")
 
 
+def test_revealer_v1_entry_point_end_to_end(oracle):
+    """REVEALER_v1 with the reference's formals on in-memory GCT-shaped inputs: preprocessing (host) +
+    search (CUDA) against the oracle run on the same prepared inputs; seed baselines as LIB:1817-1833."""
+    import revealer_b200 as rb
+    from revealer_b200.api import prepare_inputs
+    w = _workload(90, 260)
+    rng = np.random.default_rng(6)
+    perm = rng.permutation(90)                                     # unsorted samples: REVEALER.v1 sorts them
+    names = ["S%03d" % i for i in range(90)]
+    rows = ["F%03d" % i for i in range(260)]
+    d1 = dict(ds=w["target"][perm][None, :], row_names=["TARGET"], names=[names[i] for i in perm])
+    d2 = dict(ds=w["m2"][:, perm].astype(float), row_names=rows, names=[names[i] for i in perm])
+    kw = dict(seed_names=["F023", "F047"], count_thres_low=3, count_thres_high=40)
+    out = rb.REVEALER_v1(d1, "TARGET", "positive", d2, max_n_iter=3, **kw)
+    p = prepare_inputs(d1, "TARGET", "positive", d2, **kw)
+    ref = oracle.search(p["target"], p["m2"], p["seed"], 3)
+    assert list(out["top"]) == list(ref["top"])
+    assert out["seed_names_iter"] == [p["feature_names"][i] for i in ref["top"]]
+    assert "F023" not in out["feature_names"] and "F047" not in out["feature_names"]
+    ok, err = score_close(out["cmi"], ref["cmi"].T)
+    assert ok, err
+    ok, err = score_close(out["cmi_seed"], ref["cmi_seed"])
+    assert ok, err
+    ok, err = score_close(out["cmi_orig_seed"], [oracle.assoc(p["target"], v) for v in p["seed_vectors"]])
+    assert ok, err
+    med = np.median(p["target"])
+    want_pct = ref["seed_iter"][:, p["target"] > med].sum(axis=1) / (p["target"] > med).sum()
+    assert np.allclose(out["pct_explained_seed"], want_pct)
+
+
 def test_oracle_golden_fixture_through_cuda(oracle):
     import revealer_b200 as rb
     g = json.load(open(os.path.join(HERE, "golden", "oracle_golden.json")))
