@@ -196,9 +196,11 @@ def main():
     nb = ctx.candidate_bytes()
     send = torch.zeros(nb, dtype=torch.uint8, device="cuda")
     recv = torch.zeros(nb * world, dtype=torch.uint8, device="cuda") if world > 1 else send
-    ctx.set_exchange_buffers(send.data_ptr(), recv.data_ptr())
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     use_p2p = world > 1 and args.exchange == "p2p"
+    use_nccl = world > 1 and not use_p2p
+    if use_nccl:
+        ctx.set_exchange_buffers(send.data_ptr(), recv.data_ptr())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     if use_p2p:   # every rank maps every other rank's exchange buffer (CUDA IPC); NCCL only carries the handles
         mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
         allh = torch.empty(64 * world, dtype=torch.uint8, device="cuda")
@@ -209,7 +211,7 @@ def main():
         ctx.search_begin(iters)
         for it in range(iters):
             ctx.iter_score(it)
-            if world > 1 and not use_p2p:
+            if use_nccl:
                 dist.all_gather_into_tensor(recv, send)
             ctx.iter_merge(it)
 
@@ -258,7 +260,6 @@ def main():
             ctx.load_matrix(m2_r)
             ctx.set_targets(tgt_h)
             ctx.set_seed(seed_h)
-            ctx.set_exchange_buffers(send.data_ptr(), recv.data_ptr())
             one_search()
             return ctx.search_fetch(iters)
 

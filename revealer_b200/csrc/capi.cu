@@ -39,7 +39,7 @@ void rvl_launch_advance(const RvlParams *P, RvlTarget *tg, const double *u_all, 
                         uint64_t *seeds_out, const double *bcvtab, double *tt, RvlCandHead *slots, int nslots,
                         unsigned long long *work, const unsigned char *recv, size_t rec_bytes, int iter, int iters,
                         int first_null, int64_t *top, double *top_score, uint64_t *seed_iter, int allow_incr,
-                        const RvlPeerXchg *X, cudaStream_t st);
+                        const RvlPeerXchg *X, const uint64_t *bits, int fuse_rank, cudaStream_t st);
 void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaStream_t st);
 void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of, const double *u_all,
                       const double *xc_all, const uint64_t *y_all, const double *bcvtab, double *out,
@@ -671,7 +671,7 @@ static int prep_iteration(rvl_ctx *ctx)
     RvlPeerXchg Xnone;
     memset(&Xnone, 0, sizeof Xnone);
     rvl_launch_advance(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_seed_alt, ctx->d_bcvtab, ctx->d_tt, ctx->d_part, nslots,
-                       ctx->d_work, nullptr, 0, 0, 1, ctx->first_null, nullptr, nullptr, nullptr, 0, &Xnone, ctx->stream);
+                       ctx->d_work, nullptr, 0, 0, 1, ctx->first_null, nullptr, nullptr, nullptr, 0, &Xnone, ctx->d_bits, 0, ctx->stream);
     ctx->work_dirty = false;
     ctx->launches++;
     CK(cudaGetLastError());
@@ -824,7 +824,7 @@ extern "C" int rvl_search_begin(rvl_ctx *ctx, int iters)
     if (rc) return rc;
     ctx->iters = iters;
     size_t cb = rvl_candidate_bytes(ctx);
-    if (ctx->world == 1 && (!ctx->d_send || !ctx->d_recv)) {
+    if (ctx->world == 1 && !ctx->p2p && (!ctx->d_send || !ctx->d_recv)) {
         if (ctx->own_xchg_bytes < cb) {
             dfree(ctx->d_own_xchg);
             CK(dalloc(&ctx->d_own_xchg, cb));
@@ -860,6 +860,8 @@ extern "C" int rvl_iter_score(rvl_ctx *ctx, int iter)
     int rc = launch_score(ctx, ctx->d_scores + (size_t)iter * ctx->T * ctx->F);
     if (rc) return rc;
     RvlParams P2 = make_params(ctx);
+    // (fusing this reduction into k_advance -- its `fuse_rank` path -- was measured 9 us per iteration
+    //  slower on one GPU: 363 blocks then spin on the stamp that one 256-thread block has yet to write)
     RvlPeerXchg X = make_xchg(ctx, iter);
     rvl_launch_argmax(&P2, ctx->d_part, ctx->score_grid_x * rvl_score_warps(), ctx->d_bits, ctx->d_send,
                       sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, &X, ctx->stream);
@@ -878,7 +880,7 @@ extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
     rvl_launch_advance(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_seed_alt, ctx->d_bcvtab, ctx->d_tt, ctx->d_part,
                        ctx->score_grid_x * rvl_score_warps(), ctx->d_work, ctx->p2p ? ctx->d_xchg : ctx->d_recv,
                        sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, iter, ctx->iters, ctx->first_null,
-                       ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, 1, &X, ctx->stream);
+                       ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, 1, &X, ctx->d_bits, 0, ctx->stream);
     { uint64_t *tmp = ctx->d_seed; ctx->d_seed = ctx->d_seed_alt; ctx->d_seed_alt = tmp; }
     ctx->work_dirty = false;
     ctx->launches += 1;

@@ -445,6 +445,64 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
 // Node tt_pad is tau = 0 exactly (c = 1: every feature with rho <= 0), so those use it unweighted.
 // Layout: tt[target][node][b][RVL_MAXG].
 
+// Reduce the per-warp bests k_score left in part[nparts] (one target) and publish the candidate
+// record [score][global row][bit row].  With a peer exchange (X.peers) the record goes straight into
+// every rank's buffer over NVLink and is followed by a stamp; otherwise into `send` for the caller's
+// all-gather.  Called by a whole block (any size that is a multiple of 32).
+__device__ void rvl_publish_best(const RvlParams &P, const RvlCandHead *__restrict__ v, int nparts,
+                                 const uint64_t *__restrict__ bits, unsigned char *__restrict__ send, size_t rec_bytes,
+                                 const RvlPeerXchg &X, int t)
+{
+    __shared__ double shv[32];
+    __shared__ long long shi[32];
+    double bv = 0.0;
+    int64_t bi = -1;
+    for (int k = threadIdx.x; k < nparts; k += blockDim.x) {
+        RvlCandHead h = v[k];
+        if (rvl_ahead(h.score, h.row, bv, bi, P.negative)) { bv = h.score; bi = h.row; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, (long long)bi, o);
+        if (rvl_ahead(ov, oi, bv, bi, P.negative)) { bv = ov; bi = oi; }
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { shv[w] = bv; shi[w] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int nw = blockDim.x >> 5;
+        bv = (lane < nw) ? shv[lane] : 0.0;
+        bi = (lane < nw) ? shi[lane] : -1;
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            long long oi = __shfl_xor_sync(0xffffffffu, (long long)bi, o);
+            if (rvl_ahead(ov, oi, bv, bi, P.negative)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { shv[0] = bv; shi[0] = bi; }
+    }
+    __syncthreads();
+    bv = shv[0]; bi = shi[0];
+    const int ndst = X.peers ? P.world : 1;
+    const size_t slot = ((size_t)X.parity * P.world + P.rank) * P.T + t;
+    for (int r = 0; r < ndst; r++) {
+        unsigned char *rec = X.peers ? X.peers[r] + slot * rec_bytes : send + (size_t)t * rec_bytes;
+        RvlCandHead *h = reinterpret_cast<RvlCandHead *>(rec);
+        uint64_t *rb = reinterpret_cast<uint64_t *>(rec + sizeof(RvlCandHead));
+        if (threadIdx.x == 0) { h->score = bv; h->row = (bi < 0) ? -1 : (P.row_offset + bi); }
+        for (int i = threadIdx.x; i < P.words; i += blockDim.x) rb[i] = (bi < 0) ? 0ull : bits[(size_t)bi * P.words + i];
+    }
+    if (X.peers) {
+        __threadfence_system(); // records visible to every GPU before any stamp
+        __syncthreads();
+        if (threadIdx.x < P.world) {
+            volatile unsigned int *st =
+                reinterpret_cast<volatile unsigned int *>(X.peers[threadIdx.x] + X.stamps_off) + slot;
+            *st = X.stamp;
+        }
+    }
+}
+
+
 // k_advance = everything between two scoring passes, in one launch (grid = table nodes x targets):
 //   * merge (when `recv` is given): every block resolves, for its target's seed owner, the same global
 //     winner among the `world` candidate records (max score, ties -> lowest GLOBAL row, NaN last;
@@ -462,7 +520,7 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
           RvlCandHead *__restrict__ slots, int nslots, unsigned long long *__restrict__ work,
           const unsigned char *__restrict__ recv, size_t rec_bytes, int iter, int iters, int first_null,
           int64_t *__restrict__ top, double *__restrict__ top_score, uint64_t *__restrict__ seed_iter, int allow_incr,
-          RvlPeerXchg X)
+          RvlPeerXchg X, const uint64_t *__restrict__ bits, int fuse_rank)
 {
     __shared__ double part[RVL_SCORE_WARPS][2][RVL_MAXG];
     __shared__ int s_nz_old, s_nz_new, s_win;
@@ -473,6 +531,13 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
     const bool is_null = (first_null > 0 && t >= first_null);
     const uint64_t *zold = seeds_in + (size_t)owner * P.words;
     const uint64_t *wrow = nullptr; // the winner's bit row (merge only)
+    if (recv && X.peers && fuse_rank && m == 0 && owner == t) {
+        // rank step fused in: the node-0 block of every seed owner reduces this rank's per-warp bests and
+        // publishes the record + stamp (it is the first block of its target in launch order, so it is
+        // resident before any block that waits for its stamp)
+        rvl_publish_best(P, slots + (size_t)t * nslots, nslots, bits, nullptr, rec_bytes, X, t);
+        __syncthreads();
+    }
     if (recv && X.peers) {
         // peer exchange: the records of this iteration sit in the local buffer once every rank's stamp
         // for (parity, rank, owner) has arrived
@@ -926,61 +991,14 @@ k_assoc(RvlParams P, const RvlTarget *__restrict__ tg_all, const int *__restrict
 
 // One block per target: reduce the per-CTA bests k_score left in part[target][nparts] and write the
 // candidate record [score][global row][bit row] into the send buffer.
-// With a peer exchange (X.peers) the record goes straight into every rank's buffer over NVLink and
-// is followed by a stamp; otherwise into `send` for the caller's all-gather.
+
+// One block per target (the NCCL / caller-driven exchange; with the stamped peer exchange the same
+// reduction runs inside k_advance and this launch disappears).
 __global__ void k_argmax(RvlParams P, const RvlCandHead *__restrict__ part, int nparts,
                          const uint64_t *__restrict__ bits, unsigned char *__restrict__ send, size_t rec_bytes,
                          RvlPeerXchg X)
 {
-    __shared__ double shv[32];
-    __shared__ long long shi[32];
-    int t = blockIdx.x;
-    const RvlCandHead *v = part + (size_t)t * nparts;
-    double bv = 0.0;
-    int64_t bi = -1;
-    for (int k = threadIdx.x; k < nparts; k += blockDim.x) {
-        RvlCandHead h = v[k];
-        if (rvl_ahead(h.score, h.row, bv, bi, P.negative)) { bv = h.score; bi = h.row; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        long long oi = __shfl_xor_sync(0xffffffffu, (long long)bi, o);
-        if (rvl_ahead(ov, oi, bv, bi, P.negative)) { bv = ov; bi = oi; }
-    }
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) { shv[w] = bv; shi[w] = bi; }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        int nw = blockDim.x >> 5;
-        bv = (lane < nw) ? shv[lane] : 0.0;
-        bi = (lane < nw) ? shi[lane] : -1;
-        for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            long long oi = __shfl_xor_sync(0xffffffffu, (long long)bi, o);
-            if (rvl_ahead(ov, oi, bv, bi, P.negative)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) { shv[0] = bv; shi[0] = bi; }
-    }
-    __syncthreads();
-    bv = shv[0]; bi = shi[0];
-    const int ndst = X.peers ? P.world : 1;
-    const size_t slot = ((size_t)X.parity * P.world + P.rank) * P.T + t;
-    for (int r = 0; r < ndst; r++) {
-        unsigned char *rec = X.peers ? X.peers[r] + slot * rec_bytes : send + (size_t)t * rec_bytes;
-        RvlCandHead *h = reinterpret_cast<RvlCandHead *>(rec);
-        uint64_t *rb = reinterpret_cast<uint64_t *>(rec + sizeof(RvlCandHead));
-        if (threadIdx.x == 0) { h->score = bv; h->row = (bi < 0) ? -1 : (P.row_offset + bi); }
-        for (int i = threadIdx.x; i < P.words; i += blockDim.x) rb[i] = (bi < 0) ? 0ull : bits[(size_t)bi * P.words + i];
-    }
-    if (X.peers) {
-        __threadfence_system(); // records visible to every GPU before any stamp
-        __syncthreads();
-        if (threadIdx.x < P.world) {
-            volatile unsigned int *st =
-                reinterpret_cast<volatile unsigned int *>(X.peers[threadIdx.x] + X.stamps_off) + slot;
-            *st = X.stamp;
-        }
-    }
+    rvl_publish_best(P, part + (size_t)blockIdx.x * nparts, nparts, bits, send, rec_bytes, X, blockIdx.x);
 }
 
 // ---- bit packing ------------------------------------------------------------------------------
@@ -1152,12 +1170,13 @@ extern "C" void rvl_launch_advance(const RvlParams *P, RvlTarget *tg, const doub
                                    uint64_t *seeds_out, const double *bcvtab, double *tt, RvlCandHead *slots,
                                    int nslots, unsigned long long *work, const unsigned char *recv, size_t rec_bytes,
                                    int iter, int iters, int first_null, int64_t *top, double *top_score,
-                                   uint64_t *seed_iter, int allow_incr, const RvlPeerXchg *X, cudaStream_t st)
+                                   uint64_t *seed_iter, int allow_incr, const RvlPeerXchg *X, const uint64_t *bits,
+                                   int fuse_rank, cudaStream_t st)
 {
     dim3 grid(P->dense_x ? 1 : P->tt_nodes, P->T);
     k_advance<<<grid, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, u_all, seeds_in, seeds_out, bcvtab, tt, slots, nslots, work,
                                                      recv, rec_bytes, iter, iters, first_null, top, top_score, seed_iter,
-                                                     allow_incr, *X);
+                                                     allow_incr, *X, bits, fuse_rank);
 }
 
 // FP64 FMA peak micro-benchmark (MEASURED_PEAKS.json has no FP64 figure): 8 independent DFMA chains
