@@ -391,6 +391,13 @@ def revealer_search(target, m2, seed=None, max_n_iter=5, target_match="positive"
         if target_rand is not None:
             out["cmi_rand"] = np.transpose(res["cmi"][1:], (1, 2, 0)).copy()  # iters x F x n.perm
             out["p_val"] = np.stack([ctx.pvalues(cmi[:, it], out["cmi_rand"][it]) for it in range(max_n_iter)])
+            # FDR as REVEALER.v1 reports it (LIB:1870-1878): BH on p and on 1-p; rows with a negative score
+            # take the lower-tail pair.  Display-side bookkeeping on F numbers: host numpy, like R's p.adjust.
+            fdr = np.stack([p_adjust_fdr(p) for p in out["p_val"]])
+            fdr_lower = np.stack([p_adjust_fdr(1.0 - p) for p in out["p_val"]])
+            neg = (cmi.T < 0)
+            out["FDR"] = np.where(neg, fdr_lower, fdr)
+            out["p_val_signed"] = np.where(neg, 1.0 - out["p_val"], out["p_val"])
         return out
     finally:
         if own:
@@ -426,6 +433,17 @@ def assess_features(target, features, n_perm=10000, r_seed=5209761, n_grid=25, d
     n_perm = max(1, null.shape[0])
     p = np.where(ic >= 0, (null >= ic[None, :]).sum(axis=0), (null <= ic[None, :]).sum(axis=0)) / n_perm
     return dict(IC=ic, p_val=p, null_IC=null)
+
+
+def p_adjust_fdr(p):
+    """R's p.adjust(p, method = "fdr") (Benjamini-Hochberg): pmin(1, cummin(n / i * p[o]))[ro], o = decreasing order."""
+    p = np.asarray(p, dtype=np.float64)
+    n = len(p)
+    o = np.argsort(-p, kind="stable")
+    q = np.minimum(1.0, np.minimum.accumulate(n / np.arange(n, 0, -1) * p[o]))
+    out = np.empty(n)
+    out[o] = q
+    return out
 
 
 def read_gct(path):

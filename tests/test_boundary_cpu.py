@@ -169,6 +169,20 @@ def test_prepare_inputs_mirrors_reveler_v1_preprocessing(tmp_path):
     assert q["sample_names"] == p["sample_names"] and np.array_equal(q["m2"], p["m2"]) and np.array_equal(q["seed"], p["seed"])
 
 
+def test_p_adjust_fdr_is_benjamini_hochberg():
+    """p.adjust(p, "fdr") as used at LIB:1870-1871, against the textbook definition."""
+    from revealer_b200.api import p_adjust_fdr
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 7, 100):
+        p = np.round(rng.random(n), 2)                        # ties included
+        o = np.argsort(p, kind="stable")
+        s = p[o] * n / np.arange(1, n + 1)
+        q = np.minimum(np.minimum.accumulate(s[::-1])[::-1], 1.0)
+        want = np.empty(n)
+        want[o] = q
+        assert np.allclose(p_adjust_fdr(p), want)
+
+
 def test_synthetic_workload_is_deterministic_and_shardable():
     from revealer_b200 import synth
     a = synth.make_workload(n=120, F=900)

@@ -488,6 +488,8 @@ def test_permutation_null_and_pvalues(oracle):
             assert ok, (it, j, err)
         want = oracle.pvals(out["cmi"][:, it], out["cmi_rand"][it])
         assert np.array_equal(out["p_val"][it], want)
+    assert out["FDR"].shape == out["p_val"].shape and np.all((out["FDR"] >= 0) & (out["FDR"] <= 1))
+    assert np.all(out["FDR"] >= np.where(out["cmi"].T < 0, 1 - out["p_val"], out["p_val"]) - 1e-15)
 
 
 def test_assess_features_matches_oracle(oracle):
