@@ -585,6 +585,34 @@ def test_two_shards_equal_single_shard():
         c.close()
 
 
+# ------------------------------------------------------------------ config C1's shape (gpunit example: 82 x ~17.8k)
+
+def test_c1_shape_full_search_matches_oracle(oracle):
+    """BASELINE config C1 is the reference's own gpunit example (82 samples, ~17.8k features, seed, 2
+    iterations); its inputs are unreachable URLs, so the same shape is run on synthetic data: EVERY row
+    of both iterations against the oracle, winners and seeds exact."""
+    from revealer_b200 import synth
+    w = synth.make_workload("C1_gpunit_like")
+    iters = 2
+    with _ctx() as ctx:
+        ctx.load_matrix(w["m2"].astype(np.float64))              # the R layout path
+        ctx.set_targets(w["target"])
+        ctx.set_seed(w["seed"])
+        res = ctx.search(iters)
+    ref = oracle.search(w["target"], w["m2"].astype(float), w["seed"].astype(float), iters, hoist=True, nthreads=0)
+    assert list(res["top"][0]) == list(ref["top"])
+    assert np.array_equal(res["seed_iter"][0], ref["seed_iter"].astype(np.uint8))
+    ok, err = score_close(res["cmi"][0], ref["cmi"])
+    assert ok, err
+    ok, err = score_close(res["cmi_seed"][0], ref["cmi_seed"])
+    assert ok, err
+    # the full display ranking (R's order()) agrees wherever the oracle's neighbours are separated by
+    # more than the tolerance; exact ties keep row order on both sides
+    for it in range(iters):
+        g_ord = np.argsort(np.where(np.isnan(res["cmi"][0, it]), np.inf, -res["cmi"][0, it]), kind="stable")
+        assert g_ord[0] == ref["top"][it]
+
+
 # ------------------------------------------------------------------ config C4's sample count (n = 10 000)
 
 def test_c4_sample_count_rows_match_oracle(oracle):
