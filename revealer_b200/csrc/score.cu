@@ -35,7 +35,9 @@ struct __align__(16) RvlWarpScratch {
     double gy[2][RVL_MAXG];    // gy[a][j]
     double gz[2][RVL_MAXG];    // gz[b][k]
     uint16_t live[RVL_MAXG * RVL_MAXG];
+    uint32_t list[512];        // minority-class samples of the row being scored (RVL_LIST_MAX)
 };
+#define RVL_LIST_MAX 512
 
 // FAST: rvl_log_pos (normal positive arguments only); otherwise the library log.
 template <bool FAST> __device__ __forceinline__ double rvl_logq(double q) { return FAST ? rvl_log_pos(q) : log(q); }
@@ -872,19 +874,66 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
             double m0 = 0.0, m1 = 0.0;     // minority-class sums split by z
             const double gi = (double)lane;
             const int last = (n - 1) >> 6;
-            for (int w = 0; w <= last; w++) {
-                uint64_t v = yrow[w];
-                if (flip) {
-                    v = ~v;
-                    if (w == last && (n & 63)) v &= (1ull << (n & 63)) - 1ull;
+            const int mc = flip ? n - n1 : n1; // minority-class size
+            const bool use_z = (mode == RVL_MODE_CIC);
+            if (mc <= RVL_LIST_MAX) {
+                // The minority samples as a compact list (sample index, z bit in bit 31): every lane turns the
+                // words it owns into entries at its prefix offset, then all lanes walk the list together --
+                // no per-word loop over the mostly empty words of a sparse row.
+                int mine = 0;
+                for (int w = lane; w <= last; w += 32) {
+                    uint64_t v = yrow[w];
+                    if (flip) { v = ~v; if (w == last && (n & 63)) v &= (1ull << (n & 63)) - 1ull; }
+                    mine += __popcll(v);
                 }
-                const uint64_t zw = (mode == RVL_MODE_CIC) ? zrow[w] : 0ull;
-                while (v) { // warp-uniform loop: every lane sees the same word
-                    int b = __ffsll((long long)v) - 1;
-                    v &= v - 1;
-                    double d = gi - u[w * 64 + b];
-                    double e = rvl_exp_neg(-beta * d * d);
-                    if ((zw >> b) & 1ull) m1 += e; else m0 += e;
+                int off = mine; // inclusive scan over lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, off, o);
+                    if (lane >= o) off += up;
+                }
+                off -= mine;
+                for (int w = lane; w <= last; w += 32) {
+                    uint64_t v = yrow[w];
+                    if (flip) { v = ~v; if (w == last && (n & 63)) v &= (1ull << (n & 63)) - 1ull; }
+                    const uint64_t zw = use_z ? zrow[w] : 0ull;
+                    while (v) {
+                        const int b = __ffsll((long long)v) - 1;
+                        v &= v - 1;
+                        S.list[off++] = (uint32_t)(w * 64 + b) | ((uint32_t)((zw >> b) & 1ull) << 31);
+                    }
+                }
+                __syncwarp();
+                int q = 0;
+                for (; q + 1 < mc; q += 2) { // two exp chains in flight
+                    const uint32_t e0 = S.list[q], e1 = S.list[q + 1];
+                    const double d0 = gi - u[e0 & 0x7fffffffu], d1 = gi - u[e1 & 0x7fffffffu];
+                    const double x0 = rvl_exp_neg(-beta * d0 * d0), x1 = rvl_exp_neg(-beta * d1 * d1);
+                    if (e0 >> 31) m1 += x0; else m0 += x0;
+                    if (e1 >> 31) m1 += x1; else m0 += x1;
+                }
+                if (q < mc) {
+                    const uint32_t e0 = S.list[q];
+                    const double d0 = gi - u[e0 & 0x7fffffffu];
+                    const double x0 = rvl_exp_neg(-beta * d0 * d0);
+                    if (e0 >> 31) m1 += x0; else m0 += x0;
+                }
+                __syncwarp();
+            } else {
+                for (int w = 0; w <= last; w++) {
+                    uint64_t v = yrow[w];
+                    if (flip) {
+                        v = ~v;
+                        if (w == last && (n & 63)) v &= (1ull << (n & 63)) - 1ull;
+                    }
+                    const uint64_t zw = use_z ? zrow[w] : 0ull;
+                    while (v) { // warp-uniform loop: every lane sees the same word
+                        int b = __ffsll((long long)v) - 1;
+                        v &= v - 1;
+                        double d = gi - u[w * 64 + b];
+                        double e = rvl_exp_neg(-beta * d * d);
+                        if ((zw >> b) & 1ull) m1 += e; else m0 += e;
+                    }
                 }
             }
             double r0 = fmax(tot0 - m0, 0.0), r1 = fmax(tot1 - m1, 0.0); // the majority class
