@@ -197,15 +197,28 @@ def main():
     send = torch.zeros(nb, dtype=torch.uint8, device="cuda")
     recv = torch.zeros(nb * world, dtype=torch.uint8, device="cuda") if world > 1 else send
     use_p2p = world > 1 and args.exchange == "p2p"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    if use_p2p:   # every rank maps every other rank's exchange buffer (CUDA IPC); NCCL only carries the handles
+        ok = 1
+        try:
+            mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
+        except rb.RevealerError:
+            ok, mine = 0, torch.zeros(64, dtype=torch.uint8, device="cuda")
+        allh = torch.empty(64 * world, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh, mine)
+        if ok:
+            try:
+                ctx.p2p_import(allh.cpu().numpy().tobytes())
+            except rb.RevealerError:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:      # peer mapping unavailable on some rank: every rank falls back together
+            ctx.p2p_disable()
+            use_p2p = False
     use_nccl = world > 1 and not use_p2p
     if use_nccl:
         ctx.set_exchange_buffers(send.data_ptr(), recv.data_ptr())
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    if use_p2p:   # every rank maps every other rank's exchange buffer (CUDA IPC); NCCL only carries the handles
-        mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
-        allh = torch.empty(64 * world, dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(allh, mine)
-        ctx.p2p_import(allh.cpu().numpy().tobytes())
 
     def one_search():
         ctx.search_begin(iters)
