@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_reference_rate(wl_name, sample_rows, threads=0, budget_s=20.0):
+def cpu_reference_rate(wl_name, sample_rows, threads=0, budget_s=15.0):
     """evaluations/s of the restated reference algorithm (oracle, reference mode) on host cores."""
     from oracle import oracle as O
     from revealer_b200 import synth

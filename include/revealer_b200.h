@@ -146,6 +146,14 @@ int rvl_search(rvl_ctx *ctx, int iters, rvl_result *out);
 int rvl_p2p_export(rvl_ctx *ctx, unsigned char *handle64);
 int rvl_p2p_import(rvl_ctx *ctx, const unsigned char *handles, int world);
 int rvl_p2p_disable(rvl_ctx *ctx);
+/* Several shards driven by ONE host thread (what a single R session does with n.gpus > 1): ctxs[i] is
+ * rank i of n on n distinct devices, each with its row block, the (same) targets and seed set.
+ * rvl_group_connect enables peer access and wires the same stamped peer exchange without IPC;
+ * rvl_group_search enqueues the whole search on every device (all launches asynchronous) and waits;
+ * results are then read per context with rvl_search_fetch (scores for its own rows; winners, seeds and
+ * seed ICs identical on every context). */
+int rvl_group_connect(rvl_ctx **ctxs, int n);
+int rvl_group_search(rvl_ctx **ctxs, int n, int iters);
 int rvl_search_begin(rvl_ctx *ctx, int iters);
 size_t rvl_candidate_bytes(const rvl_ctx *ctx);
 int rvl_set_exchange_buffers(rvl_ctx *ctx, void *dev_send, void *dev_recv);

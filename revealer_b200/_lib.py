@@ -54,6 +54,8 @@ SIGNATURES = {
     "rvl_p2p_export": (_i, [_vp, _u8p]),
     "rvl_p2p_import": (_i, [_vp, _u8p, _i]),
     "rvl_p2p_disable": (_i, [_vp]),
+    "rvl_group_connect": (_i, [C.POINTER(_vp), _i]),
+    "rvl_group_search": (_i, [C.POINTER(_vp), _i, _i]),
     "rvl_search_begin": (_i, [_vp, _i]),
     "rvl_candidate_bytes": (C.c_size_t, [_vp]),
     "rvl_set_exchange_buffers": (_i, [_vp, _vp, _vp]),

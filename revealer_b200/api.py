@@ -435,6 +435,49 @@ def assess_features(target, features, n_perm=10000, r_seed=5209761, n_grid=25, d
     return dict(IC=ic, p_val=p, null_IC=null)
 
 
+def revealer_search_multi_gpu(target, m2, seed=None, max_n_iter=5, target_match="positive", devices=(0, 1),
+                              n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75):
+    """revealer_search with the feature rows sharded over several GPUs of THIS process (one host thread,
+    rvl_group_connect / rvl_group_search): the form an R session uses with n.gpus > 1.  Returns the same
+    dict as revealer_search (without the permutation extras)."""
+    if target_match not in ("positive", "negative"):
+        raise RevealerError(_lib.RVL_ERR_ARG, 'target.match must be "positive" or "negative"')
+    negative = target_match == "negative"
+    target = np.asarray(target, dtype=np.float64)
+    m2 = np.asarray(m2)
+    F, n = m2.shape
+    world = len(devices)
+    ctxs = []
+    try:
+        for r, dev in enumerate(devices):
+            lo, cnt = shard_rows(F, world, r)
+            c = RevealerContext(dev, n_grid=n_grid, bandwidth_mult=bandwidth_mult, bandwidth_shrink=bandwidth_shrink,
+                                negative=negative)
+            ctxs.append(c)
+            c.set_shard(r, world, lo, F)
+            c.load_matrix(m2[lo:lo + cnt])
+            c.set_targets(target)
+            c.set_seed(np.zeros(n, dtype=np.uint8) if seed is None else seed)
+        lib = ctxs[0]._lib
+        arr = (C.c_void_p * world)(*[c._h for c in ctxs])
+        ctxs[0]._ck(lib.rvl_group_connect(arr, world))
+        rc = lib.rvl_group_search(arr, world, int(max_n_iter))
+        if rc != 0:
+            msgs = [lib.rvl_last_error(c._h).decode("utf-8", "replace") for c in ctxs]
+            raise RevealerError(rc, "; ".join(m for m in msgs if m))
+        parts = [c.search_fetch(max_n_iter) for c in ctxs]
+        cmi = np.concatenate([p["cmi"][0] for p in parts], axis=1).T.copy()   # F x iters like R
+        r0 = parts[0]
+        out = dict(cmi=cmi, top=r0["top"][0], top_score=r0["top_score"][0], seed_iter=r0["seed_iter"][0],
+                   cmi_seed=r0["cmi_seed"][0], ic_seed0=float(r0["ic_seed0"][0]))
+        key = np.where(np.isnan(cmi), np.inf, cmi if negative else -cmi)
+        out["order"] = np.stack([np.argsort(key[:, it], kind="stable") for it in range(max_n_iter)])
+        return out
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def p_adjust_fdr(p):
     """R's p.adjust(p, method = "fdr") (Benjamini-Hochberg): pmin(1, cummin(n / i * p[o]))[ro], o = decreasing order."""
     p = np.asarray(p, dtype=np.float64)

@@ -1227,3 +1227,82 @@ extern "C" int rvl_p2p_disable(rvl_ctx *ctx)
     p2p_release(ctx);
     return RVL_OK;
 }
+
+// ---- several shards driven by ONE host thread (the single-process form an R session uses) ------------
+// ctxs[i] must be rank i of n (rvl_set_shard) on n distinct devices, with matrix, targets and seed set.
+// Peer access replaces CUDA IPC: every context's exchange buffer is directly addressable by the others.
+
+extern "C" int rvl_group_connect(rvl_ctx **ctxs, int n)
+{
+    if (!ctxs || n < 1) return RVL_ERR_ARG;
+    for (int i = 0; i < n; i++) {
+        rvl_ctx *ctx = ctxs[i];
+        if (!ctx) return RVL_ERR_ARG;
+        if (ctx->world != n || ctx->rank != i) return fail(ctx, RVL_ERR_ARG, "rvl_group_connect: context %d must be rank %d of %d (rvl_set_shard)", i, i, n);
+        if (ctx->T <= 0 || ctx->words <= 0) return fail(ctx, RVL_ERR_STATE, "set the matrix/targets before rvl_group_connect");
+        for (int j = 0; j < i; j++)
+            if (ctxs[j]->device == ctx->device) return fail(ctx, RVL_ERR_ARG, "rvl_group_connect: contexts %d and %d share device %d", j, i, ctx->device);
+        if (ctx->T != ctxs[0]->T || ctx->words != ctxs[0]->words) return fail(ctx, RVL_ERR_ARG, "rvl_group_connect: targets / sample count differ between contexts");
+    }
+    if (n == 1) return RVL_OK;
+    std::vector<unsigned char *> bufs(n, nullptr);
+    for (int i = 0; i < n; i++) {
+        rvl_ctx *ctx = ctxs[i];
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamSynchronize(ctx->stream));
+        p2p_release(ctx);
+        for (int j = 0; j < n; j++) {
+            if (j == i) continue;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[j]->device));
+            if (!can) return fail(ctx, RVL_ERR_CUDA, "device %d cannot access device %d (no NVLink/PCIe peer path)", ctx->device, ctxs[j]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, RVL_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError(); // clear "already enabled"
+        }
+        size_t rec = sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words;
+        size_t recs = 2 * (size_t)n * ctx->T * rec;
+        ctx->xchg_stamps_off = (recs + 255) & ~(size_t)255;
+        ctx->xchg_bytes = ctx->xchg_stamps_off + 2 * (size_t)n * ctx->T * sizeof(unsigned int);
+        CK(cudaMalloc((void **)&ctx->d_xchg, ctx->xchg_bytes));
+        CK(cudaMemset(ctx->d_xchg, 0, ctx->xchg_bytes));
+        ctx->xchg_world = n; ctx->xchg_T = ctx->T; ctx->xchg_words = ctx->words;
+        bufs[i] = ctx->d_xchg;
+    }
+    for (int i = 0; i < n; i++) {
+        rvl_ctx *ctx = ctxs[i];
+        CK(cudaSetDevice(ctx->device));
+        CK(dalloc(&ctx->d_peers, (size_t)n));
+        CK(cudaMemcpy(ctx->d_peers, bufs.data(), sizeof(unsigned char *) * n, cudaMemcpyHostToDevice));
+        ctx->p2p = true;
+        ctx->epoch = 0;
+    }
+    return RVL_OK;
+}
+
+// The whole search on every shard: all launches are asynchronous, so one host thread keeps n GPUs busy;
+// the shards meet only through the stamped peer exchange inside k_argmax / k_advance.
+extern "C" int rvl_group_search(rvl_ctx **ctxs, int n, int iters)
+{
+    if (!ctxs || n < 1) return RVL_ERR_ARG;
+    for (int i = 0; i < n; i++) {
+        if (n > 1 && !ctxs[i]->p2p) return fail(ctxs[i], RVL_ERR_STATE, "rvl_group_search: call rvl_group_connect first");
+        int rc = rvl_search_begin(ctxs[i], iters);
+        if (rc) return rc;
+    }
+    for (int it = 0; it < iters; it++) {
+        for (int i = 0; i < n; i++) {
+            int rc = rvl_iter_score(ctxs[i], it);
+            if (rc) return rc;
+        }
+        for (int i = 0; i < n; i++) {
+            int rc = rvl_iter_merge(ctxs[i], it);
+            if (rc) return rc;
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        int rc = rvl_synchronize(ctxs[i]);
+        if (rc) return rc;
+    }
+    return RVL_OK;
+}

@@ -156,6 +156,98 @@ SEXP rvlR_search(SEXP sctx, SEXP starget, SEXP sm2, SEXP sseed, SEXP siters, SEX
     return out;
 }
 
+/* .Call("rvlR_search_multi", devices, target, m2, seed, max.n.iter, negative, n.grid, bandwidth.mult,
+ *       bandwidth.shrink)
+ * The same search with the rows of m.2 sharded over several GPUs of this R process (n.gpus > 1):
+ * one context per device, rows [lo, lo+cnt) of the column-major R matrix passed in place (pointer
+ * offset, ld = F: no copy), rvl_group_connect + rvl_group_search, scores scattered back into F x iter.
+ * No permutation targets in this form. */
+SEXP rvlR_search_multi(SEXP sdevices, SEXP starget, SEXP sm2, SEXP sseed, SEXP siters, SEXP snegative, SEXP sngrid,
+                       SEXP smult, SEXP sshrink)
+{
+    if (!Rf_isInteger(sdevices) || !Rf_isReal(starget) || !Rf_isReal(sm2) || !Rf_isMatrix(sm2) || !Rf_isReal(sseed))
+        Rf_error("revealer_b200: bad argument types");
+    const int world = (int)XLENGTH(sdevices);
+    const R_xlen_t n = XLENGTH(starget);
+    const int F = Rf_nrows(sm2);
+    const int iters = Rf_asInteger(siters);
+    if (world < 1 || world > 64 || Rf_ncols(sm2) != n || XLENGTH(sseed) != n) Rf_error("revealer_b200: dimension mismatch");
+    rvl_opts o;
+    rvl_default_options(&o);
+    o.n_grid = Rf_asInteger(sngrid);
+    o.negative = Rf_asLogical(snegative) ? 1 : 0;
+    o.bandwidth_mult = Rf_asReal(smult);
+    o.bandwidth_shrink = Rf_asReal(sshrink);
+    uint8_t *sd = (uint8_t *)R_alloc(n, 1);
+    for (R_xlen_t s = 0; s < n; s++) {
+        double v = REAL(sseed)[s];
+        if (v != 0.0 && v != 1.0) Rf_error("revealer_b200: seed must be 0/1");
+        sd[s] = (uint8_t)v;
+    }
+    rvl_ctx *ctxs[64];
+    int made = 0, rc = 0;
+    const char *msg = "";
+    for (int r = 0; r < world && !rc; r++) {
+        rc = rvl_create(&ctxs[r], INTEGER(sdevices)[r]);
+        if (rc) { msg = "no usable CUDA device"; break; }
+        made++;
+        int64_t lo = ((int64_t)r * F) / world, hi = ((int64_t)(r + 1) * F) / world;
+        rc = rvl_set_options(ctxs[r], &o);
+        if (!rc) rc = rvl_set_shard(ctxs[r], r, world, lo, F);
+        if (!rc) rc = rvl_load_matrix_f64_colmajor(ctxs[r], REAL(sm2) + lo, hi - lo, n, F);
+        if (!rc) rc = rvl_set_targets(ctxs[r], REAL(starget), n, 1);
+        if (!rc) rc = rvl_set_seed(ctxs[r], sd, n, 0);
+        if (rc) msg = rvl_last_error(ctxs[r]);
+    }
+    if (!rc) { rc = rvl_group_connect(ctxs, world); if (rc) msg = rvl_last_error(ctxs[0]); }
+    if (!rc) { rc = rvl_group_search(ctxs, world, iters); if (rc) msg = rvl_last_error(ctxs[0]); }
+    SEXP out = R_NilValue;
+    if (!rc) {
+        out = PROTECT(Rf_allocVector(VECSXP, 5));
+        SEXP names = PROTECT(Rf_allocVector(STRSXP, 5));
+        const char *nm[5] = { "cmi", "top", "seed.iter", "cmi.seed", "cmi.seed.iter0" };
+        for (int i = 0; i < 5; i++) SET_STRING_ELT(names, i, Rf_mkChar(nm[i]));
+        Rf_setAttrib(out, R_NamesSymbol, names);
+        SEXP cmi = PROTECT(Rf_allocMatrix(REALSXP, F, iters));
+        SEXP rtop = PROTECT(Rf_allocVector(INTSXP, iters));
+        SEXP rcs = PROTECT(Rf_allocVector(REALSXP, iters));
+        SEXP rsi = PROTECT(Rf_allocMatrix(REALSXP, iters, (int)n));
+        for (int r = 0; r < world && !rc; r++) {
+            int64_t lo = ((int64_t)r * F) / world, cnt = ((int64_t)(r + 1) * F) / world - lo;
+            double *loc = (double *)R_alloc((size_t)iters * (cnt ? cnt : 1), sizeof(double));
+            int64_t *top = (int64_t *)R_alloc(iters, sizeof(int64_t));
+            uint8_t *si = (uint8_t *)R_alloc((size_t)iters * n, 1);
+            double *cs = (double *)R_alloc(iters, sizeof(double));
+            double ic0 = 0.0;
+            rvl_result res = { loc, top, NULL, si, cs, &ic0 };
+            rc = rvl_search_fetch(ctxs[r], &res);
+            if (rc) { msg = rvl_last_error(ctxs[r]); break; }
+            for (int it = 0; it < iters; it++)
+                memcpy(REAL(cmi) + (size_t)F * it + lo, loc + (size_t)it * cnt, sizeof(double) * (size_t)cnt);
+            if (r == 0) {
+                for (int it = 0; it < iters; it++) {
+                    INTEGER(rtop)[it] = (int)top[it] + 1;
+                    REAL(rcs)[it] = cs[it];
+                    for (R_xlen_t s = 0; s < n; s++) REAL(rsi)[it + (size_t)iters * s] = (double)si[(size_t)it * n + s];
+                }
+                SET_VECTOR_ELT(out, 4, Rf_ScalarReal(ic0));
+            }
+        }
+        SET_VECTOR_ELT(out, 0, cmi);
+        SET_VECTOR_ELT(out, 1, rtop);
+        SET_VECTOR_ELT(out, 2, rsi);
+        SET_VECTOR_ELT(out, 3, rcs);
+        UNPROTECT(6);
+    }
+    /* copy the message before the contexts that own it go away, then raise */
+    char buf[512];
+    strncpy(buf, msg, sizeof buf - 1);
+    buf[sizeof buf - 1] = 0;
+    for (int r = 0; r < made; r++) rvl_destroy(ctxs[r]);
+    if (rc) Rf_error("revealer_b200: %s (status %d)", buf, rc);
+    return out;
+}
+
 /* .Call("rvlR_assoc", ctx, target, y) -> assoc(target, y, "IC")   LIB:2491-2501 */
 SEXP rvlR_assoc(SEXP sctx, SEXP starget, SEXP sy)
 {
