@@ -169,6 +169,16 @@ def test_prepare_inputs_mirrors_reveler_v1_preprocessing(tmp_path):
     assert q["sample_names"] == p["sample_names"] and np.array_equal(q["m2"], p["m2"]) and np.array_equal(q["seed"], p["seed"])
 
 
+def test_r_shim_compiles_against_stub_r_headers():
+    """R is absent from this image, so the .Call shim cannot be built for real; it must at least be valid
+    C against the R API declarations it uses (tests/rstub/) and the real C-ABI header."""
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    r = subprocess.run([gcc, "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "tests", "rstub"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "revealer_b200", "r", "r_shim.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_p_adjust_fdr_is_benjamini_hochberg():
     """p.adjust(p, "fdr") as used at LIB:1870-1871, against the textbook definition."""
     from revealer_b200.api import p_adjust_fdr
