@@ -214,29 +214,56 @@ __global__ void k_pair_histogram(const int *__restrict__ bin_all, int n, int *__
         if (hist[i]) atomicAdd(&cnt[i], hist[i]);
 }
 
+// VR_bcv_bin over the 1000-bin histogram, evaluated by one block: the threads compute the products
+// term_i * cnt_i side by side, then one thread adds them in bin order -- the same operands in the
+// same order as the original's sequential loop, so the value (and with it the Brent path) is the
+// one a single thread would get.  delta grows with i, so "break at the first delta >= DELMAX" is
+// "sum the bins below the first such i".
 struct RvlHistBcvObjective {
     double n, d;
     const int *cnt;
+    double *prod; // shared [RVL_NB]
+    int *stop;    // shared: first bin with delta >= DELMAX
+    double *res;  // shared: the sum
     __device__ double operator()(double h) const
     {
-        double hh = h / 4, sum = 0.0;
-        for (int i = 0; i < RVL_NB; i++) {
+        double hh = h / 4;
+        if (threadIdx.x == 0) *stop = RVL_NB;
+        __syncthreads();
+        for (int i = threadIdx.x; i < RVL_NB; i += blockDim.x) {
             double delta = i * d / hh;
             delta *= delta;
-            if (delta >= RVL_DELMAX) break;
-            double term = exp(-delta / 4) * (delta * delta - 12 * delta + 12);
-            sum += term * cnt[i];
+            if (delta >= RVL_DELMAX) { atomicMin(stop, i); continue; }
+            int c = cnt[i];
+            // an empty bin adds term*0 = +0.0, which leaves the running sum as it is: skip its exp
+            prod[i] = c ? exp(-delta / 4) * (delta * delta - 12 * delta + 12) * c : 0.0;
         }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sum = 0.0;
+            int m = *stop;
+            for (int i = 0; i < m; i++) sum += prod[i];
+            *res = sum;
+        }
+        __syncthreads();
+        double sum = *res;
         return 1 / (2 * n * hh * sqrt(RVL_PI)) + sum / (64 * n * n * hh * sqrt(RVL_PI));
     }
 };
 
-// One thread per target runs the sequential Brent search on its 1000-bin histogram.
-__global__ void k_bcv_target(int n, int T, const int *__restrict__ cnt_all, RvlTarget *__restrict__ tg)
+// One block per target runs the Brent search on its 1000-bin histogram; every thread follows the
+// same (uniform) control flow, the objective is the block-wide evaluation above.
+__global__ void __launch_bounds__(256) k_bcv_target(int n, int T, const int *__restrict__ cnt_all, RvlTarget *__restrict__ tg)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double prod[RVL_NB];
+    __shared__ int cnt[RVL_NB];
+    __shared__ int stop;
+    __shared__ double res;
+    int t = blockIdx.x;
     if (t >= T) return;
-    if (tg[t].is_const) { tg[t].bcv = 0.0; return; }
+    if (tg[t].is_const) { if (threadIdx.x == 0) tg[t].bcv = 0.0; return; }
+    for (int i = threadIdx.x; i < RVL_NB; i += blockDim.x) cnt[i] = cnt_all[(size_t)t * RVL_NB + i];
+    __syncthreads();
     double dn = (double)n;
     double var = tg[t].sxx / (dn - 1.0);
     double hmax = 1.144 * sqrt(var) * pow(dn, -1.0 / 5) * 4;
@@ -244,8 +271,12 @@ __global__ void k_bcv_target(int n, int T, const int *__restrict__ cnt_all, RvlT
     RvlHistBcvObjective f;
     f.n = dn;
     f.d = (tg[t].xmax - tg[t].xmin) * 1.01 / RVL_NB;
-    f.cnt = cnt_all + (size_t)t * RVL_NB;
-    tg[t].bcv = rvl_brent_fmin(lower, upper, f, 0.1 * lower);
+    f.cnt = cnt;
+    f.prod = prod;
+    f.stop = &stop;
+    f.res = &res;
+    double h = rvl_brent_fmin(lower, upper, f, 0.1 * lower);
+    if (threadIdx.x == 0) tg[t].bcv = h;
 }
 
 // ---- host-callable launchers (called from capi.cu) --------------------------------------
@@ -278,6 +309,6 @@ extern "C" void rvl_launch_target_setup(const double *x_all, int n, int T, int G
     if (chunks < 1) chunks = 1;
     dim3 grid(chunks, Th);
     k_pair_histogram<<<grid, 256, 0, st>>>(bin_all, n, cnt_all);
-    k_bcv_target<<<(Th + 31) / 32, 32, 0, st>>>(n, Th, cnt_all, tg);
+    k_bcv_target<<<Th, 256, 0, st>>>(n, Th, cnt_all, tg);
     if (permuted && T > 1) k_bcv_copy_permuted<<<(T + 127) / 128, 128, 0, st>>>(T, tg, nonfinite);
 }

@@ -78,7 +78,18 @@ struct rvl_ctx {
     int64_t F = -1;
     int n = 0, words = 0;
     uint64_t *d_bits = nullptr;
-    bool own_bits = true;
+    size_t bits_cap = 0;   // capacity of d_bits in uint64 (buffers are kept across loads: a context that is
+    size_t rows_cap = 0;   // re-loaded -- an R session, bench.py's e2e loop -- does not re-allocate)
+    // upload staging (two halves, filled by the copy stream while the main stream packs the other)
+    unsigned char *d_stage[2] = {nullptr, nullptr};
+    size_t stage_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr};
+    // scratch of the duplicate-row grouping + pooled temporary storage for thrust
+    uint64_t *d_hash = nullptr;
+    int64_t *d_idx = nullptr, *d_head = nullptr;
+    struct pool_block { char *p; size_t bytes; bool used; };
+    std::vector<pool_block> pool;
     // exact-duplicate rows: rep[f] = first identical row; uniq = rows with rep[f] == f
     int64_t *d_rep = nullptr, *d_uniq = nullptr;
     int64_t U = 0;
@@ -253,15 +264,19 @@ extern "C" int rvl_create(rvl_ctx **out, int device)
     return RVL_OK;
 }
 
-static void free_matrix(rvl_ctx *c)
+// Forget the loaded matrix; the device buffers stay for the next load unless `release`.
+static void free_matrix(rvl_ctx *c, bool release = false)
 {
-    if (c->own_bits) dfree(c->d_bits);
-    c->d_bits = nullptr;
-    dfree(c->d_rep); dfree(c->d_uniq);
     c->U = 0;
     c->rho_dirty = true;
-    c->own_bits = true;
     c->F = -1;
+    if (!release) return;
+    dfree(c->d_bits); c->bits_cap = 0;
+    dfree(c->d_rep); dfree(c->d_uniq); dfree(c->d_hash); dfree(c->d_idx); dfree(c->d_head);
+    c->rows_cap = 0;
+    dfree(c->d_stage[0]); dfree(c->d_stage[1]); c->stage_cap = 0;
+    for (auto &b : c->pool) cudaFree(b.p);
+    c->pool.clear();
 }
 static void free_targets(rvl_ctx *c)
 {
@@ -284,8 +299,13 @@ extern "C" void rvl_destroy(rvl_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    free_matrix(ctx); free_targets(ctx); free_results(ctx);
+    free_matrix(ctx, true); free_targets(ctx); free_results(ctx);
     p2p_release(ctx);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_packed[i]) cudaEventDestroy(ctx->ev_packed[i]);
+    }
     dfree(ctx->d_xerr);
     dfree(ctx->d_flag);
     dfree(ctx->d_ctr);
@@ -353,23 +373,43 @@ struct rvl_is_rep {
     __host__ __device__ bool operator()(int64_t f) const { return rep[f] == f; }
 };
 
+// Temporary storage of the thrust calls below comes from a small pool kept in the context
+// (cudaMalloc / cudaFree per call would cost more than the sorts themselves).
+struct rvl_pool_alloc {
+    typedef char value_type;
+    rvl_ctx *c;
+    char *allocate(std::ptrdiff_t n)
+    {
+        size_t need = n > 0 ? (size_t)n : 1;
+        rvl_ctx::pool_block *best = nullptr;
+        for (auto &b : c->pool)
+            if (!b.used && b.bytes >= need && (!best || b.bytes < best->bytes)) best = &b;
+        if (best) { best->used = true; return best->p; }
+        char *p = nullptr;
+        size_t bytes = (need + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        if (cudaMalloc((void **)&p, bytes) != cudaSuccess) throw std::bad_alloc();
+        c->pool.push_back({p, bytes, true});
+        return p;
+    }
+    void deallocate(char *p, size_t)
+    {
+        for (auto &b : c->pool)
+            if (b.p == p) { b.used = false; return; }
+    }
+};
+
 // Group identical rows (hash -> stable sort -> exact compare); see score.cu "exact-duplicate rows".
 static int build_dedup(rvl_ctx *ctx)
 {
     int64_t F = ctx->F;
-    dfree(ctx->d_rep); dfree(ctx->d_uniq);
     ctx->U = F;
     if (F <= 0) return RVL_OK;
-    uint64_t *d_hash = nullptr;
-    int64_t *d_idx = nullptr, *d_head = nullptr;
-    CK(dalloc(&ctx->d_rep, (size_t)F));
-    CK(dalloc(&ctx->d_uniq, (size_t)F));
-    CK(dalloc(&d_hash, (size_t)F));
-    CK(dalloc(&d_idx, (size_t)F));
-    CK(dalloc(&d_head, (size_t)F));
+    uint64_t *d_hash = ctx->d_hash;
+    int64_t *d_idx = ctx->d_idx, *d_head = ctx->d_head;
     int rc = RVL_OK;
     try {
-        auto pol = thrust::cuda::par.on(ctx->stream);
+        rvl_pool_alloc alloc{ctx};
+        auto pol = thrust::cuda::par(alloc).on(ctx->stream);
         rvl_launch_row_hash(ctx->d_bits, F, ctx->words, d_hash, d_idx, ctx->stream);
         thrust::stable_sort_by_key(pol, thrust::device_ptr<uint64_t>(d_hash), thrust::device_ptr<uint64_t>(d_hash) + F,
                                    thrust::device_ptr<int64_t>(d_idx));
@@ -395,10 +435,53 @@ static int build_dedup(rvl_ctx *ctx)
     } catch (...) {
         rc = fail(ctx, RVL_ERR_CUDA, "duplicate-row grouping failed on the device");
     }
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_hash); cudaFree(d_idx); cudaFree(d_head);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (!rc && e != cudaSuccess) rc = fail(ctx, RVL_ERR_CUDA, "duplicate-row grouping: %s", cudaGetErrorString(e));
     if (rc) free_matrix(ctx);
     return rc;
+}
+
+// Device buffers for an F x words matrix and its per-row side arrays (grown, never shrunk).
+static int reserve_matrix(rvl_ctx *ctx, int64_t F)
+{
+    size_t need = (size_t)F * ctx->words;
+    if (need > ctx->bits_cap || !ctx->d_bits) {
+        dfree(ctx->d_bits);
+        ctx->bits_cap = 0;
+        CK(dalloc(&ctx->d_bits, need));
+        ctx->bits_cap = need ? need : 1;
+    }
+    if ((size_t)F > ctx->rows_cap || !ctx->d_rep) {
+        dfree(ctx->d_rep); dfree(ctx->d_uniq); dfree(ctx->d_hash); dfree(ctx->d_idx); dfree(ctx->d_head);
+        ctx->rows_cap = 0;
+        CK(dalloc(&ctx->d_rep, (size_t)F));
+        CK(dalloc(&ctx->d_uniq, (size_t)F));
+        CK(dalloc(&ctx->d_hash, (size_t)F));
+        CK(dalloc(&ctx->d_idx, (size_t)F));
+        CK(dalloc(&ctx->d_head, (size_t)F));
+        ctx->rows_cap = F > 0 ? (size_t)F : 1;
+    }
+    return RVL_OK;
+}
+
+// Two staging halves of `bytes` each + the copy stream and events that pipeline H2D against packing.
+static int reserve_stage(rvl_ctx *ctx, size_t bytes)
+{
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_packed[i], cudaEventDisableTiming));
+        }
+    }
+    if (bytes > ctx->stage_cap) {
+        dfree(ctx->d_stage[0]); dfree(ctx->d_stage[1]);
+        ctx->stage_cap = 0;
+        CK(dalloc(&ctx->d_stage[0], bytes));
+        CK(dalloc(&ctx->d_stage[1], bytes));
+        ctx->stage_cap = bytes;
+    }
+    return RVL_OK;
 }
 
 static int begin_matrix(rvl_ctx *ctx, int64_t F, int64_t n)
@@ -430,29 +513,35 @@ extern "C" int rvl_load_matrix_f64_colmajor(rvl_ctx *ctx, const double *m2, int6
     if (ld < F) return fail(ctx, RVL_ERR_ARG, "ld < F");
     int rc = begin_matrix(ctx, F, n);
     if (rc) return rc;
-    CK(dalloc(&ctx->d_bits, (size_t)F * ctx->words));
+    rc = reserve_matrix(ctx, F);
+    if (rc) return rc;
     CK(cudaMemsetAsync(ctx->d_bits, 0, sizeof(uint64_t) * (size_t)F * ctx->words, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     ctx->F = F;
     if (F == 0) return RVL_OK;
-    // column chunks of a multiple of 64 samples, <= ~256 MB staging
-    int64_t cols = (256ll << 20) / (8 * ld);
+    // column chunks of a multiple of 64 samples (whole bit words), ~64 MB each, through two staging
+    // halves: the copy stream fills one while the main stream packs the other, so the DMA engine
+    // never waits for a pack kernel and only the last chunk's pack is exposed
+    int64_t cols = (64ll << 20) / (8 * ld);
     cols = (cols / 64) * 64;
     if (cols < 64) cols = 64;
-    double *stage = nullptr;
-    int64_t stage_cols = cols < n ? cols : ((n + 63) / 64) * 64;
-    CK(dalloc(&stage, (size_t)ld * stage_cols));
-    for (int64_t s0 = 0; s0 < n; s0 += cols) {
+    int64_t stage_cols = cols < n ? cols : n;
+    rc = reserve_stage(ctx, sizeof(double) * (size_t)ld * stage_cols);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_packed[0], ctx->stream)); // staging halves are free once earlier work is done
+    CK(cudaEventRecord(ctx->ev_packed[1], ctx->stream));
+    int half = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += cols, half ^= 1) {
         int64_t nc = (n - s0 < cols) ? (n - s0) : cols;
-        cudaError_t e = cudaMemcpyAsync(stage, m2 + ld * s0, sizeof(double) * (size_t)ld * nc, cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) { cudaFree(stage); return fail(ctx, RVL_ERR_CUDA, "H2D: %s", cudaGetErrorString(e)); }
+        double *stage = reinterpret_cast<double *>(ctx->d_stage[half]);
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[half], 0));
+        CK(cudaMemcpyAsync(stage, m2 + ld * s0, sizeof(double) * (size_t)ld * nc, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copied[half], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[half], 0));
         rvl_launch_pack_f64_colmajor(stage, F, ld, (int)s0, (int)nc, ctx->words, ctx->d_bits, ctx->d_flag, ctx->stream);
+        CK(cudaEventRecord(ctx->ev_packed[half], ctx->stream));
         ctx->launches++;
-        // the staging buffer is reused by the next chunk: stream order makes that safe
     }
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(stage);
-    if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "pack: %s", cudaGetErrorString(e));
     rc = check_flag(ctx, "feature matrix has an entry that is not 0 or 1 (binary features only; no fallback)");
     if (rc) { free_matrix(ctx); return rc; }
     return build_dedup(ctx);
@@ -464,25 +553,30 @@ extern "C" int rvl_load_matrix_u8_rowmajor(rvl_ctx *ctx, const uint8_t *m2, int6
     if (!m2 && F > 0) return fail(ctx, RVL_ERR_ARG, "m2 is NULL");
     int rc = begin_matrix(ctx, F, n);
     if (rc) return rc;
-    CK(dalloc(&ctx->d_bits, (size_t)F * ctx->words));
+    rc = reserve_matrix(ctx, F);
+    if (rc) return rc;
     CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     ctx->F = F;
     if (F == 0) return RVL_OK;
-    int64_t rows = (256ll << 20) / n;
+    int64_t rows = (64ll << 20) / n; // row blocks of ~64 MB through the two staging halves (as above)
     if (rows < 1) rows = 1;
     if (rows > F) rows = F;
-    uint8_t *stage = nullptr;
-    CK(dalloc(&stage, (size_t)rows * n));
-    for (int64_t f0 = 0; f0 < F; f0 += rows) {
+    rc = reserve_stage(ctx, (size_t)rows * n);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_packed[0], ctx->stream));
+    CK(cudaEventRecord(ctx->ev_packed[1], ctx->stream));
+    int half = 0;
+    for (int64_t f0 = 0; f0 < F; f0 += rows, half ^= 1) {
         int64_t fc = (F - f0 < rows) ? (F - f0) : rows;
-        cudaError_t e = cudaMemcpyAsync(stage, m2 + (size_t)f0 * n, (size_t)fc * n, cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) { cudaFree(stage); return fail(ctx, RVL_ERR_CUDA, "H2D: %s", cudaGetErrorString(e)); }
+        uint8_t *stage = ctx->d_stage[half];
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[half], 0));
+        CK(cudaMemcpyAsync(stage, m2 + (size_t)f0 * n, (size_t)fc * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copied[half], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[half], 0));
         rvl_launch_pack_u8_rowmajor(stage, f0, fc, (int)n, ctx->words, ctx->d_bits, ctx->d_flag, ctx->stream);
+        CK(cudaEventRecord(ctx->ev_packed[half], ctx->stream));
         ctx->launches++;
     }
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(stage);
-    if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "pack: %s", cudaGetErrorString(e));
     rc = check_flag(ctx, "feature matrix has an entry that is not 0 or 1 (binary features only; no fallback)");
     if (rc) { free_matrix(ctx); return rc; }
     return build_dedup(ctx);
@@ -494,7 +588,8 @@ static int load_bits_common(rvl_ctx *ctx, const void *src, bool src_device, int6
     int rc = begin_matrix(ctx, F, n);
     if (rc) return rc;
     if (words < (n + 63) / 64) return fail(ctx, RVL_ERR_ARG, "words < ceil(n/64)");
-    CK(dalloc(&ctx->d_bits, (size_t)F * ctx->words));
+    rc = reserve_matrix(ctx, F);
+    if (rc) return rc;
     CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     ctx->F = F;
     if (F == 0) return RVL_OK;
