@@ -33,8 +33,8 @@ UNIT = "evaluations/s"
 
 # FP64 work convention for the roofline numerator (DESIGN.md "Roofline"): FP64-pipe instructions
 # the kernel issues per transcendental, counted in the SASS of this build (profiles/), 2 flop each.
-FLOP_PER_EXP = 2 * 18   # CUDA exp(): 14 DFMA + 2 DMUL + 2 DADD in the SASS of score.o
-FLOP_PER_LOG = 2 * 18   # rvl_log_pos: 12 DFMA + 3 DMUL + 3 DADD (rvl_common.cuh)
+FLOP_PER_EXP = 2 * 18   # rvl_exp_neg: 14 DFMA + 2 DMUL + 2 DADD in the SASS of score.o
+FLOP_PER_LOG = 2 * 8    # rvl_log_pos (table-driven): 6 DFMA + 1 DMUL + 1 DADD (rvl_common.cuh)
 
 
 def parse():

@@ -23,8 +23,13 @@
 #include <thrust/functional.h>
 #include <thrust/iterator/counting_iterator.h>
 
+// dynamic shared memory k_score may ask for: 227 KB per block minus its static part (the 32 KB log table
+// of rvl_log_pos + 1 KB of slack)
+#define RVL_SCORE_DYN_SMEM_MAX ((size_t)(227 - 33) * 1024)
+
 // launchers (score.cu, bandwidth.cu)
 extern "C" {
+cudaError_t rvl_upload_log_table(void);
 void rvl_launch_bcv_binary_table(int n, double *table, cudaStream_t st);
 void rvl_launch_target_setup(const double *x_all, int n, int T, int G, RvlTarget *tg, double *u_all, double *xc_all,
                              int *bin_all, int *cnt_all, int *nonfinite, int permuted, cudaStream_t st);
@@ -246,7 +251,8 @@ extern "C" int rvl_create(rvl_ctx **out, int device)
     if (!ctx) return RVL_ERR_ARG;
     ctx->device = device;
     rvl_default_options(&ctx->opts);
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaSetDevice(device) != cudaSuccess || rvl_upload_log_table() != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_xerr, sizeof(int)) != cudaSuccess ||
         cudaMemset(ctx->d_xerr, 0, sizeof(int)) != cudaSuccess ||
@@ -489,8 +495,8 @@ static int begin_matrix(rvl_ctx *ctx, int64_t F, int64_t n)
     quiesce_side(ctx);
     if (F < 0 || n < 2 || n > (1 << 24)) return fail(ctx, RVL_ERR_ARG, "need F >= 0 and 2 <= n <= 2^24 (F=%lld n=%lld)", (long long)F, (long long)n);
     if (ctx->T > 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "matrix has n=%lld but targets have n=%d", (long long)n, ctx->n);
-    if (rvl_score_smem_bytes((int)n, (int)(((n + 63) / 64 + 1) & ~1ll)) > 227 * 1024)
-        return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (8 bit rows of n/8 bytes per block; n <= ~190 000)", (long long)n);
+    if (rvl_score_smem_bytes((int)n, (int)(((n + 63) / 64 + 1) & ~1ll)) > RVL_SCORE_DYN_SMEM_MAX)
+        return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (8 bit rows of n/8 bytes per block; n <= ~150 000)", (long long)n);
     free_matrix(ctx);
     ctx->n = (int)n;
     ctx->words = (int)(((n + 63) / 64 + 1) & ~1ll); // rows padded to 16 B
@@ -638,8 +644,8 @@ static int set_targets_impl(rvl_ctx *ctx, const double *targets, int64_t n, int6
     quiesce_side(ctx);
     if (!targets || n < 2 || n_targets < 1 || n_targets > 65535) return fail(ctx, RVL_ERR_ARG, "bad targets (n=%lld, n_targets=%lld; need n >= 2, 1 <= n_targets <= 65535)", (long long)n, (long long)n_targets);
     if (ctx->F >= 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "targets have n=%lld but matrix has n=%d", (long long)n, ctx->n);
-    if (rvl_score_smem_bytes((int)n, (int)(((n + 63) / 64 + 1) & ~1ll)) > 227 * 1024)
-        return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (8 bit rows of n/8 bytes per block; n <= ~190 000)", (long long)n);
+    if (rvl_score_smem_bytes((int)n, (int)(((n + 63) / 64 + 1) & ~1ll)) > RVL_SCORE_DYN_SMEM_MAX)
+        return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (8 bit rows of n/8 bytes per block; n <= ~150 000)", (long long)n);
     free_targets(ctx);
     if (ctx->F < 0) { ctx->n = (int)n; ctx->words = (int)(((n + 63) / 64 + 1) & ~1ll); }
     int T = (int)n_targets;
@@ -722,7 +728,7 @@ extern "C" int rvl_set_seed(rvl_ctx *ctx, const uint8_t *seed, int64_t n, int pe
 static int configure_score(rvl_ctx *ctx)
 {
     size_t smem = rvl_score_smem_bytes(ctx->n, ctx->words);
-    if (smem > 227 * 1024) return fail(ctx, RVL_ERR_ARG, "n=%d needs %zu B of shared memory per block (> 227 KB)", ctx->n, smem);
+    if (smem > RVL_SCORE_DYN_SMEM_MAX) return fail(ctx, RVL_ERR_ARG, "n=%d needs %zu B of dynamic shared memory per block (> 194 KB)", ctx->n, smem);
     if (smem != ctx->score_smem || ctx->score_grid_x <= 0) {
         int grid = 0;
         CK(rvl_score_configure(smem, ctx->device, &grid));

@@ -82,44 +82,52 @@ struct RvlParams {
 
 #define RVL_DBL_EPS 2.220446049250313e-16
 
-// Coefficients of rvl_log_pos in constant memory so that DFMA takes them as c[bank][offset] operands
-// (no per-use UMOV pair): R(z) = Lg1 z + ... + Lg7 z^7 ~ (log(1+s) - log(1-s) - 2s)/s on
-// z = s^2 <= 0.0295 (the minimax fit published with fdlibm's e_log.c, |error| < 2^-58.45), then ln 2.
-static __constant__ double RVL_LG[8] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
-                                 2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
-                                 1.479819860511658591e-01, 0.6931471805599453094};
-
+// ---- log for the entropy epilogue ----------------------------------------------------------------
 // log(q) for a positive, finite, NORMAL double (callers guarantee the range once per evaluation).
-// Branch-free: mantissa folded to [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1) by a MUFU reciprocal seed
-// + two Newton steps, log m = 2s + s R(s^2), k*ln2 added last.
-// <= 4 ulp against numpy's log over [1e-87, 1e17] (emulated in tests/test_fastlog.py);
-// 18 FP64-pipe instructions, no special-case branches.
+// Table-driven and branch-free: the mantissa is folded to m in [sqrt(1/2), sqrt(2)); the top 8 bits of
+// the folded mantissa field select c_i (midpoint of the 256 sub-intervals) with rc_i = fl(1/c_i) and
+// lc_i = -log(rc_i) (rounded from an 80-bit evaluation on the host, rvl_upload_log_table); then
+//   r = fma(m, rc_i, -1), |r| <= 2^-9,   log q = k ln2 + lc_i + (r - r^2/2 + r^3/3 - r^4/4 + r^5/5)
+// (truncation r^6/6 <= 9e-18).  Error: <= 2 ulp for |log q| > 0.5, <= 8e-17 absolute below (emulated in
+// tests/test_fastlog.py).  9 FP64-pipe instructions (was 18 with the division-based form), dependency
+// depth 5.  The table sits in shared memory, every entry replicated 8 times ([entry][lane & 7], 16 B
+// each = 32 KB per block): the 8 lanes of each quarter-warp of an LDS.128 then hit 8 distinct 16-byte
+// bank groups whatever their entries, so the gather is conflict-free.
+#define RVL_LOGTAB_ENTRIES 256
+#define RVL_LOGTAB_COPIES 8
+static __constant__ double RVL_LG[5] = {1.0 / 3, -0.5, 1.0 / 5, -0.25, 0.6931471805599453094};
+
+// The block's copy of the table (one instance per kernel that calls it).
+__device__ __forceinline__ double2 *rvl_logtab_smem()
+{
+    __shared__ __align__(16) double2 tab[RVL_LOGTAB_ENTRIES * RVL_LOGTAB_COPIES];
+    return tab;
+}
+
+// Whole block: replicate the 256-entry global table into shared memory.  Ends with a barrier.
+__device__ __forceinline__ void rvl_logtab_fill(const double2 *__restrict__ g)
+{
+    double2 *tab = rvl_logtab_smem();
+    for (int i = threadIdx.x; i < RVL_LOGTAB_ENTRIES * RVL_LOGTAB_COPIES; i += blockDim.x)
+        tab[i] = g[i / RVL_LOGTAB_COPIES];
+    __syncthreads();
+}
+
 __device__ __forceinline__ double rvl_log_pos(double q)
 {
-    int hi = __double2hiint(q);
-    const int lo = __double2loint(q);
-    hi += 0x3ff00000 - 0x3fe6a09e;
-    const int k = (hi >> 20) - 0x3ff;
-    hi = (hi & 0x000fffff) + 0x3fe6a09e;
-    const double m = __hiloint2double(hi, lo);
-    const double f = m - 1.0, t = m + 1.0;
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(t));
-    double e = fma(-t, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-t, r, 1.0);
-    r = fma(r, e, r);
-    const double s = f * r;
-    const double z = s * s;
-    double p = RVL_LG[6];
-    p = fma(p, z, RVL_LG[5]);
-    p = fma(p, z, RVL_LG[4]);
-    p = fma(p, z, RVL_LG[3]);
-    p = fma(p, z, RVL_LG[2]);
-    p = fma(p, z, RVL_LG[1]);
-    p = fma(p, z, RVL_LG[0]);
-    const double lm = fma(s * z, p, s + s);
-    return fma((double)k, RVL_LG[7], lm);
+    const int hi = __double2hiint(q);
+    const int hs = hi + (0x3ff00000 - 0x3fe6a09e);
+    const int k = (hs >> 20) - 0x3ff;
+    const double m = __hiloint2double(hi - (k << 20), __double2loint(q)); // hi word in [0x3fe6a09e, 0x3ff6a09e)
+    const char *base = reinterpret_cast<const char *>(rvl_logtab_smem()) + (threadIdx.x & (RVL_LOGTAB_COPIES - 1)) * 16;
+    const double2 e = *reinterpret_cast<const double2 *>(base + ((hs >> 5) & 0x7f80)); // entry (hs >> 12) & 255, 128 B apart
+    const double r = fma(m, e.x, -1.0);
+    const double r2 = r * r;
+    const double pa = fma(r, RVL_LG[0], RVL_LG[1]);
+    const double pb = fma(r, RVL_LG[2], RVL_LG[3]);
+    const double p = fma(pb, r2, pa);
+    const double lm = fma(r2, p, r);
+    return fma((double)k, RVL_LG[4], e.y) + lm;
 }
 
 // exp(a) for a <= 0 (Gaussian kernel weights).  Branch-free: k = round(a log2 e) by the 1.5*2^52 trick,

@@ -25,9 +25,16 @@
 #include "rvl_common.cuh"
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 
-#define RVL_SCORE_WARPS 8
+#define RVL_SCORE_WARPS 8 // warps per block of k_advance / k_assoc (fixes their summation order)
+#ifndef RVL_KSCORE_WARPS
+#define RVL_KSCORE_WARPS 8 // independent worker warps per block of k_score
+#endif
 #define RVL_TWO_PI 6.283185307179586476925286766559
+
+// (rc_i, -log rc_i) of rvl_log_pos, filled per device by rvl_upload_log_table
+__device__ double2 rvl_logtab_g[RVL_LOGTAB_ENTRIES];
 
 // ---- per-warp scratch in shared memory ----------------------------------------------------
 struct __align__(16) RvlWarpScratch {
@@ -213,14 +220,18 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
     const double gz0 = S.gz[0][kk], gz1 = S.gz[1][kk];
 
     // ---- pass A: per-k tables over i, and the x-z marginal
-    double SV = 0.0, LV = 0.0, LLV = 0.0, minV = INFINITY, maxV = 0.0, maxW = 0.0, accxz = 0.0;
+    // min / max of V and max of W are only used in the (conservative) column tests of pass B, so they are
+    // tracked on the high words (non-negative doubles order like their bit patterns: one integer min/max
+    // instead of a NaN-aware FP64 compare-select) and widened outwards afterwards.
+    double SV = 0.0, LV = 0.0, LLV = 0.0, accxz = 0.0;
+    int minVh = 0x7ff00000, maxVh = 0, maxWh = 0;
 #pragma unroll 2
     for (int i = 0; i < G; i++) {
         const double V = fma(S.A[i][M0], gz0, S.A[i][M1] * gz1);
         const double W = fma(S.A[i][m0], gz0, S.A[i][m1] * gz1);
-        minV = fmin(minV, V);
-        maxV = fmax(maxV, V);
-        maxW = fmax(maxW, W);
+        minVh = min(minVh, __double2hiint(V));
+        maxVh = max(maxVh, __double2hiint(V));
+        maxWh = max(maxWh, __double2hiint(W));
         const double Vs = fmax(V, 1e-290); // keeps the fast log in range; such a column is never factorised
         const double lv = rvl_logq<FAST>(Vs);
         SV += V;
@@ -229,6 +240,9 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
         const double qxz = fma(Gy, V + W, gE);
         accxz = fma(qxz, rvl_logq<FAST>(qxz), accxz);
     }
+    const double minV = __hiloint2double(minVh, 0);                 // <= the true minimum
+    const double maxV = __hiloint2double(maxVh, (int)0xffffffff);   // >= the true maxima
+    const double maxW = __hiloint2double(maxWh, (int)0xffffffff);
     if (!active) accxz = 0.0;
     const double sM = fma(sa[M0], gz0, sa[M1] * gz1), sm = fma(sa[m0], gz0, sa[m1] * gz1);
 
@@ -777,7 +791,7 @@ __device__ __forceinline__ void rvl_tt_lookup(const RvlParams &P, const double *
 }
 
 // ---- k_score --------------------------------------------------------------------------------
-// Persistent kernel: grid = SMs x resident CTAs, block = RVL_SCORE_WARPS warps.  Every warp is an
+// Persistent kernel: grid = SMs x resident CTAs, block = RVL_KSCORE_WARPS warps.  Every warp is an
 // independent worker: it draws the next (target, row) item from a global counter (target-major, so
 // neighbouring items share the target's small arrays in L1), scores it, and keeps its running best per
 // target.  No block barrier anywhere: evaluation cost varies with the number of live density columns,
@@ -788,7 +802,7 @@ __device__ __forceinline__ void rvl_tt_lookup(const RvlParams &P, const double *
 #ifndef RVL_SCORE_MIN_CTAS
 #define RVL_SCORE_MIN_CTAS 2
 #endif
-__global__ void __launch_bounds__(RVL_SCORE_WARPS * 32, RVL_SCORE_MIN_CTAS)
+__global__ void __launch_bounds__(RVL_KSCORE_WARPS * 32, RVL_SCORE_MIN_CTAS)
 k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict__ u_all,
         const double *__restrict__ xc_all, const RvlTarget *__restrict__ tg_all,
         const uint64_t *__restrict__ seeds, const double *__restrict__ bcvtab, const double *__restrict__ tt,
@@ -799,10 +813,12 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n, words = P.words, G = P.G;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * RVL_SCORE_WARPS + warp, nslots = gridDim.x * RVL_SCORE_WARPS;
+    const int slot = blockIdx.x * RVL_KSCORE_WARPS + warp, nslots = gridDim.x * RVL_KSCORE_WARPS;
+
+    rvl_logtab_fill(rvl_logtab_g); // the only block barrier of the kernel
 
     RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
-    uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_SCORE_WARPS);
+    uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_KSCORE_WARPS);
     RvlWarpScratch &S = scr[warp];
     uint64_t *yrow = yrows + (size_t)warp * words;
 
@@ -1029,6 +1045,7 @@ k_assoc(RvlParams P, const RvlTarget *__restrict__ tg_all, const int *__restrict
         const double *__restrict__ bcvtab, double *__restrict__ out, size_t y_stride, size_t out_stride)
 {
     __shared__ RvlAssocShared sh;
+    rvl_logtab_fill(rvl_logtab_g);
     int q = blockIdx.x;
     int t = target_of ? target_of[q] : q;
     double v = rvl_assoc_block(P, tg_all[t], u_all + (size_t)t * P.n, xc_all + (size_t)t * P.n,
@@ -1182,10 +1199,28 @@ __global__ void k_pvalues(const double *__restrict__ cmi, int64_t F, const doubl
 
 // ---- launchers ---------------------------------------------------------------------------------
 
+// Host side of rvl_log_pos's table for the current device: c_i = midpoint of sub-interval i of the folded
+// mantissa range, rc_i = fl(1/c_i), lc_i = fl(-log rc_i) from the 80-bit logl.
+extern "C" cudaError_t rvl_upload_log_table(void)
+{
+    double2 h[RVL_LOGTAB_ENTRIES];
+    for (int i = 0; i < RVL_LOGTAB_ENTRIES; i++) {
+        const uint64_t a_hi = 0x3fe6a09eull + (uint64_t)i * 4096ull, b_hi = a_hi + 4096ull;
+        const uint64_t ab = a_hi << 32, bb = b_hi << 32;
+        double a, b;
+        memcpy(&a, &ab, 8);
+        memcpy(&b, &bb, 8);
+        const double c = 0.5 * (a + b);
+        h[i].x = 1.0 / c;
+        h[i].y = (double)(-logl((long double)h[i].x));
+    }
+    return cudaMemcpyToSymbol(rvl_logtab_g, h, sizeof h);
+}
+
 extern "C" size_t rvl_score_smem_bytes(int n, int words)
 {
     (void)n;
-    return sizeof(RvlWarpScratch) * RVL_SCORE_WARPS + sizeof(uint64_t) * (size_t)words * RVL_SCORE_WARPS;
+    return sizeof(RvlWarpScratch) * RVL_KSCORE_WARPS + sizeof(uint64_t) * (size_t)words * RVL_KSCORE_WARPS;
 }
 
 // Sets the dynamic shared memory limit and returns the persistent grid: SMs x resident CTAs per SM.
@@ -1194,7 +1229,7 @@ extern "C" cudaError_t rvl_score_configure(size_t smem, int device, int *grid_ou
     cudaError_t e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score, RVL_SCORE_WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score, RVL_KSCORE_WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -1203,7 +1238,7 @@ extern "C" cudaError_t rvl_score_configure(size_t smem, int device, int *grid_ou
     return cudaSuccess;
 }
 
-extern "C" int rvl_score_warps(void) { return RVL_SCORE_WARPS; }
+extern "C" int rvl_score_warps(void) { return RVL_KSCORE_WARPS; }
 
 extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits,
                                  const double *u_all, const double *xc_all, const RvlTarget *tg,
@@ -1211,7 +1246,7 @@ extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, co
                                  RvlCandHead *part, unsigned long long *work, unsigned long long *ctr,
                                  const int64_t *uniq, int64_t U, cudaStream_t st)
 {
-    k_score<<<grid_x, RVL_SCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, part,
+    k_score<<<grid_x, RVL_KSCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, part,
                                                         work, ctr, uniq, U);
 }
 

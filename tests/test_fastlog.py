@@ -1,9 +1,24 @@
-"""CPU emulation of rvl_log_pos (revealer_b200/csrc/rvl_common.cuh): the branch-free log the entropy
-epilogue uses for positive normal doubles.  Same bit manipulations, same operation order (numpy float64
-has no FMA, which only makes this emulation slightly *less* accurate than the device code); the MUFU
-reciprocal seed is modelled by a float32 reciprocal (2^-24; the PTX rcp.approx.ftz.f64 guarantees 2^-23,
-and two Newton steps square that twice).  Must stay within 4 ulp of numpy's log over the range of Q."""
+"""CPU emulation of rvl_log_pos / rvl_exp_neg (revealer_b200/csrc/rvl_common.cuh): the branch-free log and
+exp the score kernel uses.  Same bit manipulations and operation order.  numpy float64 has no FMA: the one
+FMA whose single rounding matters (r = fma(m, rc, -1)) is emulated through an 80-bit product, the others
+only make this emulation slightly *less* accurate than the device code.  The log must stay within 2 ulp
+of the correctly rounded value for |log q| > 0.5 and within 1e-16 absolute below."""
 import numpy as np
+
+LD = np.longdouble
+
+
+def rvl_log_table():
+    """(rc_i, -log rc_i) as rvl_upload_log_table (score.cu) builds them."""
+    idx = np.arange(256, dtype=np.uint64)
+    a_hi = np.uint64(0x3FE6A09E) + idx * np.uint64(4096)
+    a = (a_hi << np.uint64(32)).view(np.float64)
+    b = ((a_hi + np.uint64(4096)) << np.uint64(32)).view(np.float64)
+    rc = 1.0 / (0.5 * (a + b))
+    return rc, (-np.log(rc.astype(LD))).astype(np.float64)
+
+
+_RC, _LC = rvl_log_table()
 
 
 def rvl_log_pos(q):
@@ -12,22 +27,16 @@ def rvl_log_pos(q):
     lo = bits & np.uint64(0xFFFFFFFF)
     hi = hi + (0x3FF00000 - 0x3FE6A09E)
     k = (hi >> 20) - 0x3FF
-    hi = (hi & 0x000FFFFF) + 0x3FE6A09E
-    m = ((hi.astype(np.uint64) << np.uint64(32)) | lo).view(np.float64)
-    f, t = m - 1.0, m + 1.0
-    r = (np.float32(1.0) / t.astype(np.float32)).astype(np.float64)
-    e = 1.0 - t * r
-    r = r + r * e
-    e = 1.0 - t * r
-    r = r + r * e
-    s = f * r
-    z = s * s
-    lg = (6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
-          1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01)
-    p = np.full_like(z, lg[6])
-    for c in lg[5::-1]:
-        p = p * z + c
-    return k * 0.6931471805599453094 + ((s * z) * p + (s + s))
+    off = hi & 0x000FFFFF
+    m = (((off + 0x3FE6A09E).astype(np.uint64) << np.uint64(32)) | lo).view(np.float64)
+    rc, lc = _RC[off >> 12], _LC[off >> 12]
+    r = (m.astype(LD) * rc.astype(LD) - 1).astype(np.float64)
+    r2 = r * r
+    pa = r * (1.0 / 3) + (-0.5)
+    pb = r * (1.0 / 5) + (-0.25)
+    p = pb * r2 + pa
+    lm = r2 * p + r
+    return (k * 0.6931471805599453094 + lc) + lm
 
 
 def rvl_exp_neg(a):
@@ -60,10 +69,22 @@ def test_fast_exp_within_a_few_ulp():
 def test_fast_log_within_a_few_ulp():
     rng = np.random.default_rng(0)
     q = np.concatenate([np.exp(rng.uniform(-200, 40, 1_000_000)), np.exp(rng.uniform(-1e-3, 1e-3, 200_000)),
+                        np.exp(rng.uniform(-0.8, 0.8, 500_000)),
                         np.array([1.0, 2.0, 0.5, np.sqrt(0.5), np.sqrt(2.0), 2.220446049250313e-16, 1e-290])])
-    got, ref = rvl_log_pos(q), np.log(q)
-    ulp = np.spacing(np.maximum(np.abs(ref), 1e-300))
-    big = np.abs(ref) > 1e-3
-    assert np.max(np.abs(got - ref)[big] / ulp[big]) <= 4.0
-    assert np.max(np.abs(got - ref)[~big]) <= 1e-18
-    assert rvl_log_pos(np.array([1.0]))[0] == 0.0
+    got, ref = rvl_log_pos(q), np.log(q.astype(LD))
+    err = np.abs(got.astype(LD) - ref).astype(np.float64)
+    refd = ref.astype(np.float64)
+    ulp = np.spacing(np.maximum(np.abs(refd), 1e-300))
+    big = np.abs(refd) > 0.5
+    assert np.max(err[big] / ulp[big]) <= 2.0
+    assert np.max(err[~big]) <= 1e-16
+
+
+def test_log_table_intervals():
+    """|r| = |m * rc_i - 1| <= 2^-9 over every sub-interval (the bound the degree-5 series relies on)."""
+    idx = np.arange(256, dtype=np.uint64)
+    a_hi = np.uint64(0x3FE6A09E) + idx * np.uint64(4096)
+    a = (a_hi << np.uint64(32)).view(np.float64)
+    b = ((a_hi + np.uint64(4096)) << np.uint64(32)).view(np.float64)
+    assert np.all(np.abs(a * _RC - 1) <= 2.0 ** -9) and np.all(np.abs(b * _RC - 1) <= 2.0 ** -9)
+    assert a[0] < np.sqrt(0.5) < a[1] and b[-1] == 2.0 * a[0]  # the fold covers exactly one octave
