@@ -99,6 +99,40 @@ int rvl_load_matrix_bits(rvl_ctx *ctx, const uint64_t *bits, int64_t F, int64_t 
 /* As rvl_load_matrix_bits, but `bits` is a DEVICE pointer on this ctx's device (no H2D). */
 int rvl_load_matrix_bits_device(rvl_ctx *ctx, const void *dev_bits, int64_t F, int64_t n, int64_t words);
 
+/* ---- GCT ingest (replaces MSIG.Gct2Frame + data.matrix for ds2: LIB:2616-2626, LIB:1582) ------------
+ * A GCT v1.2 file is memory-mapped; the host reads only the header and, on request, the name columns.
+ * rvl_load_matrix_gct ships the data lines as text (about 2 bytes per entry instead of the 8 of an R
+ * double matrix) and tokenises them on the device straight into the bit-packed matrix: no F x n
+ * array of doubles ever exists.  Works without a context (and without a GPU) up to the load call. */
+typedef struct rvl_gct rvl_gct;
+int rvl_gct_open(const char *path, rvl_gct **out);
+void rvl_gct_close(rvl_gct *gct);
+/* Message of the last failed rvl_gct_* call on this handle (gct == NULL: of the last failed rvl_gct_open
+ * on this thread). */
+const char *rvl_gct_last_error(const rvl_gct *gct);
+int rvl_gct_dims(const rvl_gct *gct, int64_t *n_rows, int64_t *n_cols);
+/* Names: copy at most cap-1 bytes + NUL into buf, return the full length (< 0: bad index / malformed row). */
+int rvl_gct_sample_name(const rvl_gct *gct, int64_t col, char *buf, size_t cap);
+int rvl_gct_row_name(rvl_gct *gct, int64_t row, char *buf, size_t cap);
+int rvl_gct_row_description(rvl_gct *gct, int64_t row, char *buf, size_t cap);
+/* All row names (field 0) or descriptions (field 1) joined by '\n' into buf; returns the bytes needed
+ * (call with cap = 0 to size the buffer), < 0 on error. */
+int64_t rvl_gct_row_names(rvl_gct *gct, int field, char *buf, size_t cap);
+/* One row as doubles, out[n_cols] (the continuous target row of ds1, LIB:1586); empty / "NA" -> NaN. */
+int rvl_gct_row_values(rvl_gct *gct, int64_t row, double *out);
+/* Rows [first_row, first_row + n_rows) of the file become the matrix of this ctx (a shard loads its own
+ * block); output sample s is file column cols[s] (0-based, no repeats) -- the sample intersection and the
+ * sort-by-target permutation of LIB:1596-1633 applied while parsing.  Every value must be 0 or 1
+ * ("0", "1", "0.0", "1.00" ...), else RVL_ERR_NOT_BINARY; wrong field counts -> RVL_ERR_ARG. */
+int rvl_load_matrix_gct(rvl_ctx *ctx, rvl_gct *gct, const int32_t *cols, int64_t n, int64_t first_row, int64_t n_rows);
+
+/* Row selection on the device: keep rows[0..k) (local indices) of the loaded matrix, in that order --
+ * m.2 <- m.2[retain, ] of the count filter (LIB:1655-1671), of the seed rows (LIB:1704-1706) and of the
+ * excluded features (LIB:1716-1720) without re-uploading.  rvl_get_row_counts supplies rowSums(m.2). */
+int rvl_select_rows(rvl_ctx *ctx, const int64_t *rows, int64_t k);
+/* Rows rows[0..k) as one byte per sample, out[k][n] (the seed rows m.2[seed.names, ], LIB:1693-1700). */
+int rvl_get_rows_u8(rvl_ctx *ctx, const int64_t *rows, int64_t k, uint8_t *out);
+
 /* n_targets target profiles, row-major [n_targets][n].  Computes, on the device, per target:
  * mean, range, bcv(target) (MASS::bcv; pair histogram + Brent), and the (n-1)-entry table of
  * bcv() for binary vectors.  n_targets > 1 = a batch of independent searches (config C5), or,

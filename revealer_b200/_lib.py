@@ -45,6 +45,18 @@ SIGNATURES = {
     "rvl_load_matrix_u8_rowmajor": (_i, [_vp, _u8p, _i64, _i64]),
     "rvl_load_matrix_bits": (_i, [_vp, _u64p, _i64, _i64, _i64]),
     "rvl_load_matrix_bits_device": (_i, [_vp, _vp, _i64, _i64, _i64]),
+    "rvl_gct_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "rvl_gct_close": (None, [_vp]),
+    "rvl_gct_last_error": (C.c_char_p, [_vp]),
+    "rvl_gct_dims": (_i, [_vp, _i64p, _i64p]),
+    "rvl_gct_sample_name": (_i, [_vp, _i64, C.c_char_p, C.c_size_t]),
+    "rvl_gct_row_name": (_i, [_vp, _i64, C.c_char_p, C.c_size_t]),
+    "rvl_gct_row_description": (_i, [_vp, _i64, C.c_char_p, C.c_size_t]),
+    "rvl_gct_row_names": (_i64, [_vp, _i, C.c_char_p, C.c_size_t]),
+    "rvl_gct_row_values": (_i, [_vp, _i64, _dp]),
+    "rvl_load_matrix_gct": (_i, [_vp, _vp, _i32p, _i64, _i64, _i64]),
+    "rvl_select_rows": (_i, [_vp, _i64p, _i64]),
+    "rvl_get_rows_u8": (_i, [_vp, _i64p, _i64, _u8p]),
     "rvl_set_targets": (_i, [_vp, _dp, _i64, _i64]),
     "rvl_set_targets_permuted": (_i, [_vp, _dp, _i64, _i64]),
     "rvl_set_null_targets": (_i, [_vp, _i64]),

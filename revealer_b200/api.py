@@ -76,6 +76,85 @@ def resolve_winner(scores, rows, negative=False):
     return best
 
 
+class GctFile:
+    """A memory-mapped GCT v1.2 file (rvl_gct): what MSIG.Gct2Frame (LIB:2616-2626) returns, without the
+    data frame -- dims, sample names, row names / descriptions and single rows are read on the host; the
+    matrix itself goes to the device as text through RevealerContext.load_gct.  Needs no GPU."""
+
+    def __init__(self, path):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._lib.rvl_gct_open(str(path).encode(), C.byref(self._h))
+        if rc != 0:
+            self._h = None
+            raise RevealerError(rc, self._lib.rvl_gct_last_error(None).decode("utf-8", "replace"))
+        r, c = C.c_int64(), C.c_int64()
+        self._lib.rvl_gct_dims(self._h, C.byref(r), C.byref(c))
+        self.n_rows, self.n_cols = r.value, c.value
+        self.path = str(path)
+        self._names = {}
+
+    def _err(self, rc=_lib.RVL_ERR_ARG):
+        return RevealerError(rc, self._lib.rvl_gct_last_error(self._h).decode("utf-8", "replace") or "bad GCT request")
+
+    @property
+    def names(self):
+        """Sample (column) names, header line 3 without Name / Description."""
+        if "s" not in self._names:
+            buf = C.create_string_buffer(4096)
+            out = []
+            for j in range(self.n_cols):
+                ln = self._lib.rvl_gct_sample_name(self._h, j, buf, len(buf))
+                if ln >= len(buf):
+                    buf = C.create_string_buffer(ln + 1)
+                    self._lib.rvl_gct_sample_name(self._h, j, buf, len(buf))
+                out.append(buf.value.decode("utf-8", "replace"))
+            self._names["s"] = out
+        return self._names["s"]
+
+    def _rows(self, field):
+        if field not in self._names:
+            need = self._lib.rvl_gct_row_names(self._h, field, None, 0)
+            if need < 0:
+                raise self._err()
+            buf = C.create_string_buffer(max(int(need), 1))
+            self._lib.rvl_gct_row_names(self._h, field, buf, len(buf))
+            self._names[field] = buf.raw[:max(int(need) - 1, 0)].decode("utf-8", "replace").split("\n") if self.n_rows else []
+        return self._names[field]
+
+    @property
+    def row_names(self):
+        return self._rows(0)
+
+    @property
+    def descs(self):
+        return self._rows(1)
+
+    def row_values(self, i):
+        """Row i as float64[n_cols] (empty / NA cells -> NaN)."""
+        out = np.empty(self.n_cols, dtype=np.float64)
+        if self._lib.rvl_gct_row_values(self._h, int(i), _dp(out)) != 0:
+            raise self._err()
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rvl_gct_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 class RevealerContext:
     """One GPU, one feature-row shard.  Thin object wrapper over rvl_ctx."""
 
@@ -146,6 +225,30 @@ class RevealerContext:
         else:
             raise RevealerError(_lib.RVL_ERR_ARG, "feature matrix dtype must be float64, uint8 or bool")
         self.F, self.n = F, n
+
+    def load_gct(self, gct, cols=None, first_row=0, n_rows=None):
+        """Rows [first_row, first_row + n_rows) of a GctFile, tokenised on the device; output sample s is file
+        column cols[s] (default: all columns in file order)."""
+        cols = np.arange(gct.n_cols, dtype=np.int32) if cols is None else np.ascontiguousarray(cols, dtype=np.int32)
+        n_rows = gct.n_rows - first_row if n_rows is None else int(n_rows)
+        self.F = None
+        self._ck(self._lib.rvl_load_matrix_gct(self._h, gct._h, cols.ctypes.data_as(C.POINTER(C.c_int32)), len(cols),
+                                               int(first_row), n_rows))
+        self.F, self.n = n_rows, len(cols)
+
+    def select_rows(self, rows):
+        """m.2 <- m.2[rows, ] on the device (count filter, seed / excluded rows removed)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        self._ck(self._lib.rvl_select_rows(self._h, rows.ctypes.data_as(C.POINTER(C.c_int64)), len(rows)))
+        self.F = len(rows)
+
+    def get_rows(self, rows):
+        """Rows of the loaded matrix as uint8[k][n]."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.empty((len(rows), self.n), dtype=np.uint8)
+        self._ck(self._lib.rvl_get_rows_u8(self._h, rows.ctypes.data_as(C.POINTER(C.c_int64)), len(rows),
+                                           out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
 
     def load_matrix_bits(self, bits, n):
         bits = np.ascontiguousarray(bits, dtype=np.uint64)
@@ -278,7 +381,7 @@ class RevealerContext:
         return out
 
     def row_counts(self):
-        out = np.empty(self.F, dtype=np.int32)
+        out = np.empty(self.F or 0, dtype=np.int32)   # no matrix: the core reports the state error
         self._ck(self._lib.rvl_get_row_counts(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
 
@@ -575,28 +678,128 @@ def prepare_inputs(ds1, target_name, target_match="positive", ds2=None, seed_nam
                 sample_names=sample_names, negative=negative)
 
 
+def prepare_inputs_device(ctx, ds1, target_name, target_match="positive", ds2=None, seed_names=None,
+                          exclude_features=None, count_thres_low=None, count_thres_high=None):
+    """prepare_inputs with ds2 read by the GCT ingest (GctFile + rvl_load_matrix_gct): the feature matrix goes
+    from the file to the bit-packed device matrix of `ctx` without an F x n host array.  The sample
+    intersection and the sort-by-target permutation become the column map of the device tokeniser; the
+    count filter uses the device row counts; seed / target / excluded rows are dropped with one device-side
+    row selection.  Same return dict as prepare_inputs, with m2 = None (the matrix is resident in ctx)."""
+    d1 = GctFile(ds1) if isinstance(ds1, str) else ds1
+    g2 = ds2 if isinstance(ds2, GctFile) else GctFile(ds2)
+    if isinstance(d1, GctFile):
+        rows1, names1 = d1.row_names, list(d1.names)
+        if target_name not in rows1:
+            raise RevealerError(_lib.RVL_ERR_ARG, "target %r not found in ds1" % target_name)
+        tgt = d1.row_values(rows1.index(target_name))
+    else:
+        rows1, names1 = list(d1["row_names"]), list(d1["names"])
+        if target_name not in rows1:
+            raise RevealerError(_lib.RVL_ERR_ARG, "target %r not found in ds1" % target_name)
+        tgt = np.asarray(d1["ds"], dtype=np.float64)[rows1.index(target_name)]
+    keep = ~np.isnan(tgt)                                   # LIB:1589-1594
+    names1k = [s for s, k in zip(names1, keep) if k]
+    tgt = tgt[keep]
+    names2 = g2.names
+    pos2 = {s: i for i, s in enumerate(names2)}             # LIB:1596-1601 intersect
+    pos1 = {}
+    for i, s in enumerate(names1k):
+        pos1.setdefault(s, i)
+    overlap = [s for s in names1k if s in pos2]
+    target = tgt[[pos1[s] for s in overlap]]
+    i2 = np.array([pos2[s] for s in overlap], dtype=np.int32)
+    negative = target_match == "negative"                   # LIB:1626-1633
+    ind = np.argsort(target if negative else -target, kind="stable")
+    target = target[ind]
+    sample_names = [overlap[i] for i in ind]
+    ctx.load_gct(g2, cols=i2[ind])                          # every row of ds2, samples selected and ordered
+    rows2 = list(g2.row_names)
+    alive = np.ones(len(rows2), dtype=bool)
+    if target_name in rows2:                                # LIB:1635-1638
+        alive[rows2.index(target_name)] = False
+    if seed_names is None or (isinstance(seed_names, str) and seed_names in ("NULL", "NULLSEED")):
+        seed_list = []
+    elif isinstance(seed_names, str):
+        seed_list = [seed_names]
+    else:
+        seed_list = list(seed_names)
+
+    def find(name):  # first live row with that name (R's match())
+        for i, r in enumerate(rows2):
+            if alive[i] and r == name:
+                return i
+        return -1
+
+    if count_thres_low is not None and count_thres_high is not None:   # LIB:1655-1671
+        sums = ctx.row_counts()
+        retain = (sums >= count_thres_low) & (sums <= count_thres_high)
+        for s in seed_list:
+            i = find(s)
+            if i >= 0:
+                retain[i] = True
+        alive &= retain
+    if seed_list:                                           # LIB:1690-1707
+        locs = [find(s) for s in seed_list]
+        missing = [s for s, i in zip(seed_list, locs) if i < 0]
+        if missing:
+            raise RevealerError(_lib.RVL_ERR_ARG, "seed(s) not found in ds2: %s" % ", ".join(missing))
+        seed_vectors = ctx.get_rows(locs).astype(np.float64)
+        seed = seed_vectors.max(axis=0)
+        alive[locs] = False
+    else:
+        seed = np.zeros(len(target))
+        seed_vectors = seed[None, :]
+    if exclude_features is not None:                        # LIB:1716-1720
+        for s in exclude_features:
+            i = find(s)
+            if i >= 0:
+                alive[i] = False
+    idx = np.flatnonzero(alive)
+    ctx.select_rows(idx)
+    return dict(target=target, m2=None, seed=seed, seed_vectors=seed_vectors, seed_list=seed_list,
+                feature_names=[rows2[i] for i in idx], sample_names=sample_names, negative=negative)
+
+
 def REVEALER_v1(ds1, target_name, target_match="positive", ds2=None, seed_names=None, exclude_features=None,
                 max_n_iter=5, pdf_output_file=None, count_thres_low=None, count_thres_high=None, n_markers=30,
                 locs_table_file=None, n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75, n_perm=0,
-                r_seed=34578, device=0):
+                r_seed=34578, device=0, ingest=None):
     """REVEALER.v1 with its 12 formals (LIB:1504-1516) plus the optional grid/bandwidth arguments.
     ds1 / ds2: GCT path or dict(ds, row_names, names) as MSIG.Gct2Frame returns.  Preprocessing
     mirrors LIB:1575-1707: drop NA-target samples, intersect samples, sort by target, drop the target
     row from the features, count filter (seeds always kept), build the seed as the column-wise max of
     the seed rows and remove those rows.  No plots/PDF (pdf_output_file and locs_table_file are accepted
-    and ignored).  n_perm > 0 adds the permutation null with numpy's PCG64(r_seed) (R's sample() stream is
+    and ignored).  ingest: "device" reads ds2 with the device GCT tokeniser (default when ds2 is a path),
+    "host" builds the F x n host matrix first (default for in-memory ds2).  n_perm > 0 adds the permutation null with numpy's PCG64(r_seed) (R's sample() stream is
     not reproduced)."""
-    p = prepare_inputs(ds1, target_name, target_match, ds2, seed_names, exclude_features, count_thres_low,
-                       count_thres_high)
+    ctx = None
+    if ingest is None:
+        ingest = "device" if isinstance(ds2, (str, GctFile)) else "host"
+    if ingest == "device":   # ds2: file -> text on the device -> bit matrix (no F x n host array)
+        ctx = RevealerContext(device, n_grid=n_grid, bandwidth_mult=bandwidth_mult, bandwidth_shrink=bandwidth_shrink,
+                              negative=(target_match == "negative"))
+        try:
+            p = prepare_inputs_device(ctx, ds1, target_name, target_match, ds2, seed_names, exclude_features,
+                                      count_thres_low, count_thres_high)
+        except Exception:
+            ctx.close()
+            raise
+    else:
+        p = prepare_inputs(ds1, target_name, target_match, ds2, seed_names, exclude_features, count_thres_low,
+                           count_thres_high)
     target, m2, seed, seed_vectors, seed_list = p["target"], p["m2"], p["seed"], p["seed_vectors"], p["seed_list"]
     rows2, sample_names, negative = p["feature_names"], p["sample_names"], p["negative"]
     target_rand = None
     if n_perm > 0:                                          # LIB:1843-1844
         rng = np.random.Generator(np.random.PCG64(r_seed))
         target_rand = np.stack([rng.permutation(target) for _ in range(n_perm)])
-    out = revealer_search(target, m2, seed, max_n_iter=max_n_iter, target_match=target_match, n_grid=n_grid,
-                          bandwidth_mult=bandwidth_mult, bandwidth_shrink=bandwidth_shrink,
-                          target_rand=target_rand, n_markers=n_markers, device=device)
+    try:
+        out = revealer_search(target, m2, seed, max_n_iter=max_n_iter, target_match=target_match, n_grid=n_grid,
+                              bandwidth_mult=bandwidth_mult, bandwidth_shrink=bandwidth_shrink,
+                              target_rand=target_rand, n_markers=n_markers, device=device, ctx=ctx)
+    finally:
+        if ctx is not None:
+            ctx.close()
     out["feature_names"] = rows2
     out["sample_names"] = sample_names
     out["target"] = target

@@ -13,6 +13,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = [
     ("bandwidth.cu", ["-fmad=false"]),
     ("score.cu", []),
+    ("gct.cu", []),
     ("capi.cu", []),
 ]
 DEPS = ["rvl_common.cuh", os.path.join("..", "..", "include", "revealer_b200.h")]

@@ -30,6 +30,19 @@
 // launchers (score.cu, bandwidth.cu)
 extern "C" {
 cudaError_t rvl_upload_log_table(void);
+// gct.cu
+int64_t rvl_gct_row_names_impl(rvl_gct *g, int field, char *buf, size_t cap);
+int rvl_gct_open_impl(const char *path, rvl_gct **out, char *errbuf, size_t errcap);
+void rvl_gct_close_impl(rvl_gct *g);
+int rvl_gct_dims_impl(const rvl_gct *g, int64_t *nrow, int64_t *ncol);
+int rvl_gct_sample_name_impl(const rvl_gct *g, int64_t j, char *buf, size_t cap);
+int rvl_gct_row_field_impl(rvl_gct *g, int64_t i, int field, char *buf, size_t cap);
+int rvl_gct_row_values_impl(rvl_gct *g, int64_t i, double *out);
+const char *rvl_gct_error_impl(const rvl_gct *g);
+int rvl_gct_parse_to_bits(rvl_gct *g, const int32_t *cols, int64_t n, int64_t first_row, int64_t n_rows, int words,
+                          uint64_t *d_bits, int *d_flag, cudaStream_t st, int64_t *launches, char *errbuf, size_t errcap);
+void rvl_launch_gather_rows(const uint64_t *src, const int64_t *rows, int64_t k, int words, uint64_t *dst, cudaStream_t st);
+void rvl_launch_unpack_rows(const uint64_t *src, const int64_t *rows, int64_t k, int n, int words, uint8_t *dst, cudaStream_t st);
 void rvl_launch_bcv_binary_table(int n, double *table, cudaStream_t st);
 void rvl_launch_target_setup(const double *x_all, int n, int T, int G, RvlTarget *tg, double *u_all, double *xc_all,
                              int *bin_all, int *cnt_all, int *nonfinite, int permuted, cudaStream_t st);
@@ -621,6 +634,109 @@ extern "C" int rvl_load_matrix_bits_device(rvl_ctx *ctx, const void *dev_bits, i
 {
     GUARD();
     return load_bits_common(ctx, dev_bits, true, F, n, words);
+}
+
+// ---- GCT ingest, row selection ---------------------------------------------
+
+static thread_local std::string g_gct_err;
+
+extern "C" int rvl_gct_open(const char *path, rvl_gct **out)
+{
+    char buf[512] = {0};
+    int rc = rvl_gct_open_impl(path, out, buf, sizeof buf);
+    g_gct_err = buf;
+    return rc ? RVL_ERR_ARG : RVL_OK;
+}
+extern "C" void rvl_gct_close(rvl_gct *g) { rvl_gct_close_impl(g); }
+extern "C" const char *rvl_gct_last_error(const rvl_gct *g)
+{
+    if (!g) return g_gct_err.c_str();
+    return rvl_gct_error_impl(g);
+}
+extern "C" int rvl_gct_dims(const rvl_gct *g, int64_t *nrow, int64_t *ncol) { return rvl_gct_dims_impl(g, nrow, ncol) ? RVL_ERR_ARG : RVL_OK; }
+extern "C" int rvl_gct_sample_name(const rvl_gct *g, int64_t j, char *buf, size_t cap) { return rvl_gct_sample_name_impl(g, j, buf, cap); }
+extern "C" int rvl_gct_row_name(rvl_gct *g, int64_t i, char *buf, size_t cap) { return rvl_gct_row_field_impl(g, i, 0, buf, cap); }
+extern "C" int rvl_gct_row_description(rvl_gct *g, int64_t i, char *buf, size_t cap) { return rvl_gct_row_field_impl(g, i, 1, buf, cap); }
+extern "C" int64_t rvl_gct_row_names(rvl_gct *g, int field, char *buf, size_t cap) { return rvl_gct_row_names_impl(g, field, buf, cap); }
+extern "C" int rvl_gct_row_values(rvl_gct *g, int64_t i, double *out) { return rvl_gct_row_values_impl(g, i, out) ? RVL_ERR_ARG : RVL_OK; }
+
+extern "C" int rvl_load_matrix_gct(rvl_ctx *ctx, rvl_gct *g, const int32_t *cols, int64_t n, int64_t first_row, int64_t n_rows)
+{
+    GUARD();
+    if (!g || !cols) return fail(ctx, RVL_ERR_ARG, "gct / cols is NULL");
+    int rc = begin_matrix(ctx, n_rows, n);
+    if (rc) return rc;
+    rc = reserve_matrix(ctx, n_rows);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    ctx->F = n_rows;
+    char buf[512] = {0};
+    int prc = rvl_gct_parse_to_bits(g, cols, n, first_row, n_rows, ctx->words, ctx->d_bits, ctx->d_flag, ctx->stream,
+                                    &ctx->launches, buf, sizeof buf);
+    if (prc) {
+        free_matrix(ctx);
+        return fail(ctx, prc == -1 ? RVL_ERR_CUDA : (prc == -3 ? RVL_ERR_NOT_BINARY : RVL_ERR_ARG), "GCT ingest: %s", buf);
+    }
+    if (n_rows == 0) return RVL_OK;
+    return build_dedup(ctx);
+}
+
+// Keep rows `rows[0..k)` (local indices, any order, no repeats required) of the loaded matrix, in that
+// order: the device-side form of m.2 <- m.2[retain, ] (count filter LIB:1655-1671, seed rows LIB:1704-1706,
+// excluded features LIB:1716-1720).
+extern "C" int rvl_select_rows(rvl_ctx *ctx, const int64_t *rows, int64_t k)
+{
+    GUARD();
+    if (ctx->F < 0) return fail(ctx, RVL_ERR_STATE, "feature matrix not loaded");
+    if (k < 0 || (!rows && k > 0)) return fail(ctx, RVL_ERR_ARG, "bad row selection");
+    for (int64_t i = 0; i < k; i++)
+        if (rows[i] < 0 || rows[i] >= ctx->F) return fail(ctx, RVL_ERR_ARG, "row %lld out of range", (long long)rows[i]);
+    quiesce_side(ctx);
+    uint64_t *d_new = nullptr;
+    int64_t *d_rows = nullptr;
+    CK(dalloc(&d_new, (size_t)k * ctx->words));
+    CK(dalloc(&d_rows, (size_t)k));
+    if (k > 0) {
+        CK(cudaMemcpyAsync(d_rows, rows, sizeof(int64_t) * (size_t)k, cudaMemcpyHostToDevice, ctx->stream));
+        rvl_launch_gather_rows(ctx->d_bits, d_rows, k, ctx->words, d_new, ctx->stream);
+        ctx->launches++;
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_rows);
+    if (e != cudaSuccess) { cudaFree(d_new); return fail(ctx, RVL_ERR_CUDA, "row selection: %s", cudaGetErrorString(e)); }
+    dfree(ctx->d_bits);
+    ctx->d_bits = d_new;
+    ctx->bits_cap = (size_t)k * ctx->words;
+    if (ctx->bits_cap == 0) ctx->bits_cap = 1;
+    ctx->F = k;
+    ctx->rho_dirty = true;
+    int rc = reserve_matrix(ctx, k);
+    if (rc) return rc;
+    return build_dedup(ctx);
+}
+
+// Rows `rows[0..k)` of the loaded matrix as one byte per sample, out[k][n] (the seed rows m.2[seed.names, ],
+// LIB:1693-1700).
+extern "C" int rvl_get_rows_u8(rvl_ctx *ctx, const int64_t *rows, int64_t k, uint8_t *out)
+{
+    GUARD();
+    if (ctx->F < 0) return fail(ctx, RVL_ERR_STATE, "feature matrix not loaded");
+    if (k < 0 || (k > 0 && (!rows || !out))) return fail(ctx, RVL_ERR_ARG, "bad row request");
+    if (k == 0) return RVL_OK;
+    for (int64_t i = 0; i < k; i++)
+        if (rows[i] < 0 || rows[i] >= ctx->F) return fail(ctx, RVL_ERR_ARG, "row %lld out of range", (long long)rows[i]);
+    uint8_t *d_out = nullptr;
+    int64_t *d_rows = nullptr;
+    CK(dalloc(&d_out, (size_t)k * ctx->n));
+    CK(dalloc(&d_rows, (size_t)k));
+    cudaMemcpyAsync(d_rows, rows, sizeof(int64_t) * (size_t)k, cudaMemcpyHostToDevice, ctx->stream);
+    rvl_launch_unpack_rows(ctx->d_bits, d_rows, k, ctx->n, ctx->words, d_out, ctx->stream);
+    ctx->launches++;
+    cudaMemcpyAsync(out, d_out, (size_t)k * ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out); cudaFree(d_rows);
+    if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "rvl_get_rows_u8: %s", cudaGetErrorString(e));
+    return RVL_OK;
 }
 
 // ---- targets and seeds -----------------------------------------------------------------------

@@ -1130,6 +1130,30 @@ __global__ void k_row_counts(const uint64_t *__restrict__ bits, int64_t F, int w
     out[k] = c;
 }
 
+// dst[i] = src[rows[i]]: row selection (count filter, seed / excluded rows removed) without leaving the device.
+__global__ void k_gather_rows(const uint64_t *__restrict__ src, const int64_t *__restrict__ rows, int64_t k, int words,
+                              uint64_t *__restrict__ dst)
+{
+    const int64_t tot = k * words;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / words;
+        const int w = (int)(i - r * words);
+        dst[i] = src[(size_t)rows[r] * words + w];
+    }
+}
+
+// dst[i][s] = bit s of row rows[i], one byte per sample.
+__global__ void k_unpack_rows(const uint64_t *__restrict__ src, const int64_t *__restrict__ rows, int64_t k, int n, int words,
+                              uint8_t *__restrict__ dst)
+{
+    const int64_t tot = k * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n;
+        const int s = (int)(i - r * n);
+        dst[i] = (uint8_t)((src[(size_t)rows[r] * words + (s >> 6)] >> (s & 63)) & 1ull);
+    }
+}
+
 // ---- exact-duplicate rows (amplicon blocks of identical rows are normal) --
 // Identical rows have identical scores, and R's stable order() ranks the lowest index first, so only the
 // first row of every group of identical rows is scored; the others receive a copy of its score.
@@ -1308,6 +1332,24 @@ extern "C" void rvl_launch_pack_u8_rowmajor(const uint8_t *m, int64_t F0, int64_
                                             uint64_t *bits, int *flag, cudaStream_t st)
 {
     k_pack_u8_rowmajor<<<(unsigned)Fc, 64, 0, st>>>(m, Fc, n, words, bits + (size_t)F0 * words, flag);
+}
+
+extern "C" void rvl_launch_gather_rows(const uint64_t *src, const int64_t *rows, int64_t k, int words, uint64_t *dst,
+                                       cudaStream_t st)
+{
+    int64_t tot = k * words;
+    int blocks = (int)((tot + 255) / 256 < 148 * 16 ? (tot + 255) / 256 : 148 * 16);
+    if (blocks < 1) blocks = 1;
+    k_gather_rows<<<blocks, 256, 0, st>>>(src, rows, k, words, dst);
+}
+
+extern "C" void rvl_launch_unpack_rows(const uint64_t *src, const int64_t *rows, int64_t k, int n, int words, uint8_t *dst,
+                                       cudaStream_t st)
+{
+    int64_t tot = k * n;
+    int blocks = (int)((tot + 255) / 256 < 148 * 16 ? (tot + 255) / 256 : 148 * 16);
+    if (blocks < 1) blocks = 1;
+    k_unpack_rows<<<blocks, 256, 0, st>>>(src, rows, k, n, words, dst);
 }
 
 extern "C" void rvl_launch_check_padding(const uint64_t *bits, int64_t F, int n, int words, int *flag,
