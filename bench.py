@@ -294,6 +294,43 @@ def main():
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
                "call": "rvl_load_matrix_f64_colmajor + rvl_set_targets + rvl_set_seed + search + rvl_search_fetch"}
 
+    # ---- the same search fed from a GCT v1.2 text file on local disk (rvl_load_matrix_gct: text over PCIe,
+    # tokenised on the device) instead of the R double matrix -- informational, single rank only
+    e2e_gct = None
+    if not args.no_e2e and world == 1 and cnt * n <= 200_000_000:
+        import tempfile
+        import revealer_b200 as rb
+        with tempfile.TemporaryDirectory() as td:
+            gpath = os.path.join(td, "m2.gct")
+            body = np.empty((cnt, 2 * n), dtype=np.uint8)
+            body[:, 0::2] = 9
+            body[:, 1::2] = m2_u8 + 48
+            with open(gpath, "wb") as fh:
+                fh.write(("#1.2\n%d\t%d\nName\tDescription\t%s\n" % (cnt, n, "\t".join("S%d" % j for j in range(n)))).encode())
+                for i in range(cnt):
+                    fh.write(b"f%d\tna" % i + body[i].tobytes() + b"\n")
+            del body
+            gbytes = os.path.getsize(gpath)
+
+            def one_gct():
+                with rb.GctFile(gpath) as g:
+                    ctx.load_gct(g)
+                ctx.set_targets(tgt_h)
+                ctx.set_seed(seed_h)
+                one_search()
+                return ctx.search_fetch(iters)
+
+            one_gct()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                one_gct()
+            barrier()
+            dtg = (time.perf_counter() - t0) / reps
+            e2e_gct = {"value": F * T * iters / dtg, "unit": UNIT, "ms_per_step": dtg * 1e3, "file_bytes": int(gbytes),
+                       "call": "rvl_gct_open + rvl_load_matrix_gct (page-cached file) + rvl_set_targets + rvl_set_seed + "
+                               "search + rvl_search_fetch"}
+
     # ---- roofline of the dominant kernel (k_score)
     peaks = {}
     try:
@@ -353,7 +390,7 @@ def main():
                                     ("NCCL all_gather" if world > 1 else "none")),
                        "l2": "flushed between timed steps (256 MiB write); bit matrix %.1f MB < L2" % (cnt * words * 8 / 1e6),
                        "step": "one full search: iterations x (score + rank + merge + seed IC)"},
-            "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
+            "e2e": e2e, "e2e_gct": e2e_gct, "gpu_launches": int(gpu_launches), "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

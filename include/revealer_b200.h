@@ -211,6 +211,8 @@ int rvl_pvalues(rvl_ctx *ctx, const double *cmi, int64_t F, const double *cmi_ra
 int rvl_get_target_bandwidth(rvl_ctx *ctx, int64_t target_index, double *out_bcv);
 /* bcv() of a binary vector of length n with n1 ones, n1 = 0..n (entries 0 and n are 0). out[n+1]. */
 int rvl_get_binary_bandwidth_table(rvl_ctx *ctx, double *out_table);
+/* Shape of the loaded matrix: rows of this shard and samples (dim(m.2)). */
+int rvl_get_matrix_dims(rvl_ctx *ctx, int64_t *out_rows, int64_t *out_samples);
 /* Row popcounts (rowSums(m.2), LIB:1656) of the local shard. out[F_local]. */
 int rvl_get_row_counts(rvl_ctx *ctx, int32_t *out_counts);
 /* Kernel launches issued by this ctx since creation (bench.py's gpu_launches claim). */

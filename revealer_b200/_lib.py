@@ -79,6 +79,7 @@ SIGNATURES = {
     "rvl_pvalues": (_i, [_vp, _dp, _i64, _dp, _i64, _dp]),
     "rvl_get_target_bandwidth": (_i, [_vp, _i64, _dp]),
     "rvl_get_binary_bandwidth_table": (_i, [_vp, _dp]),
+    "rvl_get_matrix_dims": (_i, [_vp, _i64p, _i64p]),
     "rvl_get_row_counts": (_i, [_vp, _i32p]),
     "rvl_launch_count": (_i64, [_vp]),
     "rvl_score_kernel_time": (_i, [_vp, _dp, _i64p, _i]),

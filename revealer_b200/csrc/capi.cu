@@ -40,7 +40,9 @@ int rvl_gct_row_field_impl(rvl_gct *g, int64_t i, int field, char *buf, size_t c
 int rvl_gct_row_values_impl(rvl_gct *g, int64_t i, double *out);
 const char *rvl_gct_error_impl(const rvl_gct *g);
 int rvl_gct_parse_to_bits(rvl_gct *g, const int32_t *cols, int64_t n, int64_t first_row, int64_t n_rows, int words,
-                          uint64_t *d_bits, int *d_flag, cudaStream_t st, int64_t *launches, char *errbuf, size_t errcap);
+                          uint64_t *d_bits, int *d_flag, cudaStream_t st, int64_t *launches, void **scratch_io,
+                          char *errbuf, size_t errcap);
+void rvl_gct_scratch_free(void *p);
 void rvl_launch_gather_rows(const uint64_t *src, const int64_t *rows, int64_t k, int words, uint64_t *dst, cudaStream_t st);
 void rvl_launch_unpack_rows(const uint64_t *src, const int64_t *rows, int64_t k, int n, int words, uint8_t *dst, cudaStream_t st);
 void rvl_launch_bcv_binary_table(int n, double *table, cudaStream_t st);
@@ -108,6 +110,7 @@ struct rvl_ctx {
     int64_t *d_idx = nullptr, *d_head = nullptr;
     struct pool_block { char *p; size_t bytes; bool used; };
     std::vector<pool_block> pool;
+    void *gct_scratch = nullptr; // staging of the GCT ingest (gct.cu), kept across loads
     // exact-duplicate rows: rep[f] = first identical row; uniq = rows with rep[f] == f
     int64_t *d_rep = nullptr, *d_uniq = nullptr;
     int64_t U = 0;
@@ -296,6 +299,8 @@ static void free_matrix(rvl_ctx *c, bool release = false)
     dfree(c->d_stage[0]); dfree(c->d_stage[1]); c->stage_cap = 0;
     for (auto &b : c->pool) cudaFree(b.p);
     c->pool.clear();
+    if (c->gct_scratch) rvl_gct_scratch_free(c->gct_scratch);
+    c->gct_scratch = nullptr;
 }
 static void free_targets(rvl_ctx *c)
 {
@@ -672,7 +677,7 @@ extern "C" int rvl_load_matrix_gct(rvl_ctx *ctx, rvl_gct *g, const int32_t *cols
     ctx->F = n_rows;
     char buf[512] = {0};
     int prc = rvl_gct_parse_to_bits(g, cols, n, first_row, n_rows, ctx->words, ctx->d_bits, ctx->d_flag, ctx->stream,
-                                    &ctx->launches, buf, sizeof buf);
+                                    &ctx->launches, &ctx->gct_scratch, buf, sizeof buf);
     if (prc) {
         free_matrix(ctx);
         return fail(ctx, prc == -1 ? RVL_ERR_CUDA : (prc == -3 ? RVL_ERR_NOT_BINARY : RVL_ERR_ARG), "GCT ingest: %s", buf);
@@ -1292,6 +1297,15 @@ extern "C" int rvl_get_binary_bandwidth_table(rvl_ctx *ctx, double *out)
     if (!out) return fail(ctx, RVL_ERR_ARG, "out is NULL");
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(out, ctx->d_bcvtab, sizeof(double) * ((size_t)ctx->n + 1), cudaMemcpyDeviceToHost));
+    return RVL_OK;
+}
+
+extern "C" int rvl_get_matrix_dims(rvl_ctx *ctx, int64_t *out_rows, int64_t *out_samples)
+{
+    GUARD();
+    if (ctx->F < 0) return fail(ctx, RVL_ERR_STATE, "feature matrix not loaded");
+    if (out_rows) *out_rows = ctx->F;
+    if (out_samples) *out_samples = ctx->n;
     return RVL_OK;
 }
 

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <fcntl.h>
@@ -363,7 +364,7 @@ struct RvlGctScratch {
     long long *d_rowbase = nullptr;
     int32_t *d_inv = nullptr;
     void *d_tmp = nullptr;
-    size_t tmp_bytes = 0;
+    size_t tmp_bytes = 0, inv_cap = 0;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     cudaStream_t copy = nullptr;
     ~RvlGctScratch()
@@ -383,6 +384,24 @@ struct RvlGctScratch {
     }
 };
 
+#define RVL_GCT_CHUNK ((size_t)32 << 20)
+
+extern "C" void rvl_gct_scratch_free(void *p) { delete static_cast<RvlGctScratch *>(p); }
+
+// memcpy split over a few threads: one core moves page-cache text at ~5 GB/s, PCIe takes ten times that
+static void parallel_copy(char *dst, const char *src, size_t len)
+{
+    const int T = 4;
+    if (len < ((size_t)4 << 20)) { memcpy(dst, src, len); return; }
+    std::thread th[T];
+    const size_t per = (len + T - 1) / T;
+    for (int i = 0; i < T; i++) {
+        const size_t lo = (size_t)i * per, hi = lo + per < len ? lo + per : len;
+        th[i] = std::thread([=] { if (hi > lo) memcpy(dst + lo, src + lo, hi - lo); });
+    }
+    for (int i = 0; i < T; i++) th[i].join();
+}
+
 #define GCK(call)                                                                                          \
     do {                                                                                                   \
         cudaError_t e_ = (call);                                                                           \
@@ -397,7 +416,7 @@ struct RvlGctScratch {
 // *launches is incremented by the number of kernels launched.
 extern "C" int rvl_gct_parse_to_bits(rvl_gct *g, const int32_t *cols, int64_t n, int64_t first_row, int64_t n_rows,
                                      int words, uint64_t *d_bits, int *d_flag, cudaStream_t st, int64_t *launches,
-                                     char *errbuf, size_t errcap)
+                                     void **scratch_io, char *errbuf, size_t errcap)
 {
     if (!g || !cols || n < 1 || first_row < 0 || n_rows < 0 || first_row + n_rows > g->nrow) {
         snprintf(errbuf, errcap, "bad GCT load arguments (rows [%lld, %lld) of %lld)", (long long)first_row,
@@ -412,29 +431,36 @@ extern "C" int rvl_gct_parse_to_bits(rvl_gct *g, const int32_t *cols, int64_t n,
         }
         inv[cols[s]] = (int32_t)s;
     }
-    const size_t CH = (size_t)64 << 20; // text per chunk (whole lines)
-    RvlGctScratch S;
-    GCK(cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        GCK(cudaMalloc((void **)&S.d_text[i], CH + 64));
-        GCK(cudaMallocHost((void **)&S.h_stage[i], CH + 64));
-        GCK(cudaEventCreateWithFlags(&S.ev_h2d[i], cudaEventDisableTiming));
-        GCK(cudaEventCreateWithFlags(&S.ev_done[i], cudaEventDisableTiming));
-    }
+    const size_t CH = RVL_GCT_CHUNK; // text per chunk (whole lines)
+    if (!*scratch_io) *scratch_io = new RvlGctScratch();
+    RvlGctScratch &S = *static_cast<RvlGctScratch *>(*scratch_io); // kept by the context across loads
     const size_t max_lines = CH / 2 + 2;
-    GCK(cudaMalloc((void **)&S.d_ends, sizeof(int64_t) * max_lines));
-    GCK(cudaMalloc((void **)&S.d_nlines, sizeof(int)));
-    GCK(cudaMalloc((void **)&S.d_rowbase, sizeof(long long)));
-    GCK(cudaMalloc((void **)&S.d_inv, sizeof(int32_t) * (size_t)g->ncol));
-    GCK(cudaMemsetAsync(S.d_rowbase, 0, sizeof(long long), st));
-    GCK(cudaMemcpyAsync(S.d_inv, inv.data(), sizeof(int32_t) * (size_t)g->ncol, cudaMemcpyHostToDevice, st));
-    GCK(cudaMemsetAsync(d_bits, 0, sizeof(uint64_t) * (size_t)n_rows * words, st)); // rows the file lacks stay empty
-    {
+    if (!S.copy) {
+        GCK(cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            GCK(cudaMalloc((void **)&S.d_text[i], CH + 64));
+            GCK(cudaMallocHost((void **)&S.h_stage[i], CH + 64));
+            GCK(cudaEventCreateWithFlags(&S.ev_h2d[i], cudaEventDisableTiming));
+            GCK(cudaEventCreateWithFlags(&S.ev_done[i], cudaEventDisableTiming));
+        }
+        GCK(cudaMalloc((void **)&S.d_ends, sizeof(int64_t) * max_lines));
+        GCK(cudaMalloc((void **)&S.d_nlines, sizeof(int)));
+        GCK(cudaMalloc((void **)&S.d_rowbase, sizeof(long long)));
         RvlLineEnd pred{S.d_text[0]};
         thrust::counting_iterator<int64_t> it(0);
         GCK(cub::DeviceSelect::If(nullptr, S.tmp_bytes, it, S.d_ends, S.d_nlines, (int64_t)(CH + 1), pred, st));
         GCK(cudaMalloc(&S.d_tmp, S.tmp_bytes ? S.tmp_bytes : 1));
     }
+    if (S.inv_cap < (size_t)g->ncol) {
+        if (S.d_inv) cudaFree(S.d_inv);
+        S.d_inv = nullptr;
+        S.inv_cap = 0;
+        GCK(cudaMalloc((void **)&S.d_inv, sizeof(int32_t) * (size_t)g->ncol));
+        S.inv_cap = (size_t)g->ncol;
+    }
+    GCK(cudaMemsetAsync(S.d_rowbase, 0, sizeof(long long), st));
+    GCK(cudaMemcpyAsync(S.d_inv, inv.data(), sizeof(int32_t) * (size_t)g->ncol, cudaMemcpyHostToDevice, st));
+    GCK(cudaMemsetAsync(d_bits, 0, sizeof(uint64_t) * (size_t)n_rows * words, st)); // rows the file lacks stay empty
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -455,7 +481,7 @@ extern "C" int rvl_gct_parse_to_bits(rvl_gct *g, const int32_t *cols, int64_t n,
             len = (size_t)(cut - p) + 1;
         } else if (fend[-1] != '\n') add_nl = true; // last line without a newline
         GCK(cudaEventSynchronize(S.ev_done[half])); // the staging half is free again
-        memcpy(S.h_stage[half], p, len);
+        parallel_copy(S.h_stage[half], p, len);
         if (add_nl) S.h_stage[half][len] = '\n';
         const size_t tot = len + (add_nl ? 1 : 0);
         memset(S.h_stage[half] + tot, '\n', 32); // padding the 16-byte loads may touch

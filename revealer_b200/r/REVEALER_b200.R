@@ -23,7 +23,7 @@ revealer.b200.search <- function(target, m.2, seed, max.n.iter = 5, target.match
                                  target.rand = NULL, n.grid = 25, bandwidth.mult = 0.25,
                                  bandwidth.shrink = -0.75, device = 0, ctx = NULL) {
    if (is.null(ctx)) ctx <- .Call("rvlR_create", as.integer(device))
-   storage.mode(m.2) <- "double"
+   if (!is.null(m.2)) storage.mode(m.2) <- "double"        # NULL: the matrix is already resident in ctx
    res <- .Call("rvlR_search", ctx, as.double(target), m.2, as.double(seed), as.integer(max.n.iter),
                 identical(target.match, "negative"), as.integer(n.grid), as.double(bandwidth.mult),
                 as.double(bandwidth.shrink), target.rand)
@@ -35,9 +35,13 @@ REVEALER.v1.b200 <- function(
    ds1, target.name, target.match = "positive", ds2, seed.names = NULL, exclude.features = NULL,
    max.n.iter = 5, pdf.output.file = NULL, count.thres.low = NULL, count.thres.high = NULL,
    n.markers = 30, locs.table.file = NULL,
-   n.grid = 25, bandwidth.mult = 0.25, bandwidth.shrink = -0.75, n.perm = 10, r.seed = 34578, device = 0)
+   n.grid = 25, bandwidth.mult = 0.25, bandwidth.shrink = -0.75, n.perm = 10, r.seed = 34578, device = 0,
+   gct.ingest = TRUE)
 {
    set.seed(r.seed)                                        # LIB:1557
+   if (gct.ingest) return(REVEALER.v1.b200.gct(ds1, target.name, target.match, ds2, seed.names, exclude.features,
+                                               max.n.iter, count.thres.low, count.thres.high, n.markers, n.grid,
+                                               bandwidth.mult, bandwidth.shrink, n.perm, device))
    read.gct <- function(f) {                               # same on-disk format as MSIG.Gct2Frame
       d <- read.delim(f, header = TRUE, sep = "\t", skip = 2, row.names = 1, blank.lines.skip = TRUE,
                       comment.char = "", as.is = TRUE, na.strings = "")
@@ -81,6 +85,66 @@ REVEALER.v1.b200 <- function(
    res$target <- target
    res$cmi.names <- apply(res$cmi, 2, function(v)          # display ranking, as order() at LIB:1858-1864
       rownames(m.2)[order(v, decreasing = !identical(target.match, "negative"))][1:min(n.markers, nrow(m.2))])
+   if (n.perm > 0) {
+      res$p.val <- sapply(1:max.n.iter, function(it)
+         .Call("rvlR_pvalues", res$ctx, res$cmi[, it], as.double(res$cmi.rand[, , it])))
+   }
+   res
+}
+
+# The same function with ds2 read by the device GCT ingest: the file is memory-mapped, its text goes over
+# PCIe and is tokenised on the GPU straight into the bit matrix -- no read.delim, no F x n matrix of doubles
+# (MSIG.Gct2Frame + data.matrix, LIB:2616-2626 / 1582).  R keeps only names, row counts and the seed rows.
+REVEALER.v1.b200.gct <- function(ds1, target.name, target.match, ds2, seed.names, exclude.features, max.n.iter,
+                                 count.thres.low, count.thres.high, n.markers, n.grid, bandwidth.mult,
+                                 bandwidth.shrink, n.perm, device)
+{
+   ctx <- .Call("rvlR_create", as.integer(device))
+   g1 <- .Call("rvlR_gct_open", ds1); i1 <- .Call("rvlR_gct_info", g1)
+   g2 <- .Call("rvlR_gct_open", ds2); i2 <- .Call("rvlR_gct_info", g2)
+   t.row <- match(target.name, i1$row.names)
+   if (is.na(t.row)) stop("target not found in ds1: ", target.name)
+   target <- .Call("rvlR_gct_row", g1, as.integer(t.row))
+   names(target) <- i1$names
+   target <- target[!is.na(target)]                        # LIB:1589-1594
+   common <- intersect(names(target), i2$names)            # LIB:1596-1601
+   target <- target[common]
+   ord <- order(target, decreasing = !identical(target.match, "negative"))   # LIB:1626-1633
+   target <- target[ord]
+   cols <- match(common, i2$names)[ord]
+   counts <- .Call("rvlR_load_gct", ctx, g2, as.integer(cols))   # rowSums(m.2) of the resident matrix
+   rows <- i2$row.names
+   alive <- rows != target.name | duplicated(rows)          # LIB:1635-1638 (first match only)
+   null.seed <- is.null(seed.names) || identical(seed.names, "NULLSEED")
+   if (!is.null(count.thres.low) && !is.null(count.thres.high)) {          # LIB:1655-1671
+      keep <- (counts >= count.thres.low & counts <= count.thres.high)
+      if (!null.seed) keep <- keep | (rows %in% seed.names)
+      alive <- alive & keep
+   }
+   if (null.seed) {
+      seed <- rep(0, length(target))
+   } else {                                                 # LIB:1690-1707
+      locs <- match(seed.names, ifelse(alive, rows, NA))
+      if (any(is.na(locs))) stop("seed(s) not found in ds2: ", paste(seed.names[is.na(locs)], collapse = ", "))
+      seed <- apply(.Call("rvlR_get_rows", ctx, as.integer(locs)), 2, max)
+      alive[locs] <- FALSE
+   }
+   if (!is.null(exclude.features)) alive <- alive & !(rows %in% exclude.features)   # LIB:1716-1720
+   idx <- which(alive)
+   .Call("rvlR_select_rows", ctx, as.integer(idx))
+   target.rand <- NULL
+   if (n.perm > 0) {
+      target.rand <- matrix(target, nrow = n.perm, ncol = length(target), byrow = TRUE)
+      for (i in 1:n.perm) target.rand[i, ] <- sample(target.rand[i, ])
+   }
+   res <- revealer.b200.search(as.double(target), NULL, seed, max.n.iter, target.match, target.rand, n.grid,
+                               bandwidth.mult, bandwidth.shrink, device, ctx = ctx)
+   feature.names <- rows[idx]
+   res$feature.names <- feature.names
+   res$seed.names.iter <- feature.names[res$top]
+   res$target <- target
+   res$cmi.names <- apply(res$cmi, 2, function(v)
+      feature.names[order(v, decreasing = !identical(target.match, "negative"))][1:min(n.markers, length(idx))])
    if (n.perm > 0) {
       res$p.val <- sapply(1:max.n.iter, function(it)
          .Call("rvlR_pvalues", res$ctx, res$cmi[, it], as.double(res$cmi.rand[, , it])))

@@ -54,7 +54,8 @@ SEXP rvlR_create(SEXP device)
 /* .Call("rvlR_search", ctx, target, m2, seed, max.n.iter, negative, n.grid, bandwidth.mult,
  *       bandwidth.shrink, target.rand)
  *   target       double[n]          (already sorted as LIB:1626-1633)
- *   m2           double F x n matrix, R's column-major layout, entries 0/1   (m.2)
+ *   m2           double F x n matrix, R's column-major layout, entries 0/1   (m.2); or NULL: use the matrix
+ *                already resident in ctx (rvlR_load_gct + rvlR_select_rows)
  *   seed         double[n] of 0/1                                            (seed)
  *   target.rand  NULL or double n.perm x n matrix                            (LIB:1843-1844)
  * Returns list(cmi = F x iter (unsorted, rows of m.2), top = int[iter] (1-based), top.score,
@@ -64,11 +65,21 @@ SEXP rvlR_search(SEXP sctx, SEXP starget, SEXP sm2, SEXP sseed, SEXP siters, SEX
                  SEXP smult, SEXP sshrink, SEXP srand)
 {
     rvl_ctx *ctx = get_ctx(sctx);
-    if (!Rf_isReal(starget) || !Rf_isReal(sm2) || !Rf_isMatrix(sm2) || !Rf_isReal(sseed))
-        Rf_error("revealer_b200: target, m2 and seed must be double (m2 a matrix)");
+    const int resident = Rf_isNull(sm2);
+    if (!Rf_isReal(starget) || !Rf_isReal(sseed) || (!resident && (!Rf_isReal(sm2) || !Rf_isMatrix(sm2))))
+        Rf_error("revealer_b200: target, m2 and seed must be double (m2 a matrix or NULL)");
     const R_xlen_t n = XLENGTH(starget);
-    const int F = Rf_nrows(sm2);
-    if (Rf_ncols(sm2) != n || XLENGTH(sseed) != n) Rf_error("revealer_b200: dimension mismatch (n = %ld)", (long)n);
+    int F;
+    if (resident) {
+        int64_t rows = 0, samples = 0;
+        if (rvl_get_matrix_dims(ctx, &rows, &samples)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+        if (samples != n) Rf_error("revealer_b200: resident matrix has %ld samples, target %ld", (long)samples, (long)n);
+        F = (int)rows;
+    } else {
+        F = Rf_nrows(sm2);
+        if (Rf_ncols(sm2) != n) Rf_error("revealer_b200: dimension mismatch (n = %ld)", (long)n);
+    }
+    if (XLENGTH(sseed) != n) Rf_error("revealer_b200: dimension mismatch (n = %ld)", (long)n);
     const int iters = Rf_asInteger(siters);
     int nperm = 0;
     if (!Rf_isNull(srand)) {
@@ -97,7 +108,7 @@ SEXP rvlR_search(SEXP sctx, SEXP starget, SEXP sm2, SEXP sseed, SEXP siters, SEX
     }
 
     int rc = rvl_set_options(ctx, &o);
-    if (!rc) rc = rvl_load_matrix_f64_colmajor(ctx, REAL(sm2), F, n, F); /* validates 0/1, packs on device */
+    if (!rc && !resident) rc = rvl_load_matrix_f64_colmajor(ctx, REAL(sm2), F, n, F); /* validates 0/1, packs on device */
     if (!rc) rc = rvl_set_targets(ctx, tg, n, T);
     if (!rc && nperm) rc = rvl_set_null_targets(ctx, 1);
     if (!rc) rc = rvl_set_seed(ctx, sd, n, 0);
@@ -277,4 +288,144 @@ SEXP rvlR_pvalues(SEXP sctx, SEXP scmi, SEXP srand)
     UNPROTECT(1);
     if (rc) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
     return out;
+}
+
+/* ---- GCT ingest (replaces MSIG.Gct2Frame + data.matrix for ds2, LIB:2616-2626 / 1582) -------------------- */
+
+static void rvl_r_gct_finalizer(SEXP ptr)
+{
+    rvl_gct *g = (rvl_gct *)R_ExternalPtrAddr(ptr);
+    if (g) {
+        rvl_gct_close(g);
+        R_ClearExternalPtr(ptr);
+    }
+}
+
+static rvl_gct *get_gct(SEXP ptr)
+{
+    rvl_gct *g = (rvl_gct *)R_ExternalPtrAddr(ptr);
+    if (!g) Rf_error("revealer_b200: GCT handle already released");
+    return g;
+}
+
+/* .Call("rvlR_gct_open", path) -> external pointer (the file stays memory-mapped until it is collected) */
+SEXP rvlR_gct_open(SEXP spath)
+{
+    if (!Rf_isString(spath) || XLENGTH(spath) != 1) Rf_error("revealer_b200: path must be one string");
+    rvl_gct *g = NULL;
+    if (rvl_gct_open(CHAR(STRING_ELT(spath, 0)), &g)) Rf_error("revealer_b200: %s", rvl_gct_last_error(NULL));
+    SEXP ptr = PROTECT(R_MakeExternalPtr(g, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, rvl_r_gct_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
+/* names joined by '\n' in buf -> character vector of length k */
+static SEXP split_names(char *buf, int64_t k)
+{
+    SEXP out = PROTECT(Rf_allocVector(STRSXP, (R_xlen_t)k));
+    char *p = buf;
+    for (int64_t i = 0; i < k; i++) {
+        char *e = strchr(p, '\n');
+        if (e) *e = 0;
+        SET_STRING_ELT(out, (R_xlen_t)i, Rf_mkChar(p));
+        p = e ? e + 1 : p + strlen(p);
+    }
+    UNPROTECT(1);
+    return out;
+}
+
+/* .Call("rvlR_gct_info", gct) -> list(row.names, descs, names): what MSIG.Gct2Frame returns besides ds */
+SEXP rvlR_gct_info(SEXP sgct)
+{
+    rvl_gct *g = get_gct(sgct);
+    int64_t F = 0, n = 0;
+    rvl_gct_dims(g, &F, &n);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SEXP names = PROTECT(Rf_allocVector(STRSXP, 3));
+    const char *nm[3] = { "row.names", "descs", "names" };
+    for (int i = 0; i < 3; i++) SET_STRING_ELT(names, i, Rf_mkChar(nm[i]));
+    Rf_setAttrib(out, R_NamesSymbol, names);
+    for (int field = 0; field < 2; field++) {
+        int64_t need = rvl_gct_row_names(g, field, NULL, 0);
+        if (need < 0) Rf_error("revealer_b200: %s", rvl_gct_last_error(g));
+        char *buf = (char *)R_alloc((size_t)need + 1, 1);
+        buf[0] = 0;
+        rvl_gct_row_names(g, field, buf, (size_t)need + 1);
+        SET_VECTOR_ELT(out, field, split_names(buf, F));
+    }
+    SEXP cols = PROTECT(Rf_allocVector(STRSXP, (R_xlen_t)n));
+    for (int64_t j = 0; j < n; j++) {
+        int len = rvl_gct_sample_name(g, j, NULL, 0);
+        char *buf = (char *)R_alloc((size_t)len + 1, 1);
+        rvl_gct_sample_name(g, j, buf, (size_t)len + 1);
+        SET_STRING_ELT(cols, (R_xlen_t)j, Rf_mkChar(buf));
+    }
+    SET_VECTOR_ELT(out, 2, cols);
+    UNPROTECT(3);
+    return out;
+}
+
+/* .Call("rvlR_gct_row", gct, i) -> numeric[n.cols], row i (1-based): the target row of ds1 */
+SEXP rvlR_gct_row(SEXP sgct, SEXP si)
+{
+    rvl_gct *g = get_gct(sgct);
+    int64_t F = 0, n = 0;
+    rvl_gct_dims(g, &F, &n);
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)n));
+    int rc = rvl_gct_row_values(g, (int64_t)Rf_asInteger(si) - 1, REAL(out));
+    UNPROTECT(1);
+    if (rc) Rf_error("revealer_b200: %s", rvl_gct_last_error(g));
+    return out;
+}
+
+/* .Call("rvlR_load_gct", ctx, gct, cols) : every row of the file, samples cols (1-based file columns, in the
+ * order REVEALER.v1 wants them) -> the resident bit matrix of ctx.  Returns rowSums(m.2) (LIB:1656). */
+SEXP rvlR_load_gct(SEXP sctx, SEXP sgct, SEXP scols)
+{
+    rvl_ctx *ctx = get_ctx(sctx);
+    rvl_gct *g = get_gct(sgct);
+    if (!Rf_isInteger(scols)) Rf_error("revealer_b200: cols must be integer");
+    const R_xlen_t n = XLENGTH(scols);
+    int64_t F = 0, nc = 0;
+    rvl_gct_dims(g, &F, &nc);
+    int32_t *cols = (int32_t *)R_alloc((size_t)n, sizeof(int32_t));
+    for (R_xlen_t s = 0; s < n; s++) cols[s] = INTEGER(scols)[s] - 1;
+    if (rvl_load_matrix_gct(ctx, g, cols, (int64_t)n, 0, F)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)F));
+    int rc = rvl_get_row_counts(ctx, (int32_t *)INTEGER(out));
+    UNPROTECT(1);
+    if (rc) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    return out;
+}
+
+/* .Call("rvlR_get_rows", ctx, rows) -> length(rows) x n numeric matrix of the resident rows (1-based) */
+SEXP rvlR_get_rows(SEXP sctx, SEXP srows)
+{
+    rvl_ctx *ctx = get_ctx(sctx);
+    if (!Rf_isInteger(srows)) Rf_error("revealer_b200: rows must be integer");
+    const R_xlen_t k = XLENGTH(srows);
+    int64_t F = 0, n = 0;
+    if (rvl_get_matrix_dims(ctx, &F, &n)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    int64_t *rows = (int64_t *)R_alloc((size_t)k + 1, sizeof(int64_t));
+    for (R_xlen_t i = 0; i < k; i++) rows[i] = (int64_t)INTEGER(srows)[i] - 1;
+    uint8_t *buf = (uint8_t *)R_alloc((size_t)k * (size_t)n + 1, 1);
+    if (rvl_get_rows_u8(ctx, rows, (int64_t)k, buf)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)k, (int)n));
+    for (R_xlen_t i = 0; i < k; i++)
+        for (int64_t s = 0; s < n; s++) REAL(out)[i + (size_t)k * s] = (double)buf[(size_t)i * n + s];
+    UNPROTECT(1);
+    return out;
+}
+
+/* .Call("rvlR_select_rows", ctx, rows) : m.2 <- m.2[rows, ] on the device (rows 1-based) */
+SEXP rvlR_select_rows(SEXP sctx, SEXP srows)
+{
+    rvl_ctx *ctx = get_ctx(sctx);
+    if (!Rf_isInteger(srows)) Rf_error("revealer_b200: rows must be integer");
+    const R_xlen_t k = XLENGTH(srows);
+    int64_t *rows = (int64_t *)R_alloc((size_t)k + 1, sizeof(int64_t));
+    for (R_xlen_t i = 0; i < k; i++) rows[i] = (int64_t)INTEGER(srows)[i] - 1;
+    if (rvl_select_rows(ctx, rows, (int64_t)k)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    return R_NilValue;
 }

@@ -21,3 +21,4 @@ double *REAL(SEXP); int *INTEGER(SEXP);
 SEXP Rf_allocVector(int, R_xlen_t); SEXP Rf_allocMatrix(int, int, int); SEXP Rf_mkChar(const char*);
 void SET_STRING_ELT(SEXP, R_xlen_t, SEXP); void SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
 SEXP Rf_setAttrib(SEXP, SEXP, SEXP); SEXP Rf_ScalarReal(double);
+int Rf_isString(SEXP); SEXP STRING_ELT(SEXP, R_xlen_t); const char *CHAR(SEXP);
