@@ -155,6 +155,26 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa(index):
+    """One process per GPU: run on the cores NVML reports as local to that GPU, so that the pinned host
+    buffers of the e2e path (first touch) sit on the NUMA node the GPU's PCIe link hangs off."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -171,6 +191,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_cores = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -269,12 +290,20 @@ def main():
         m2_r = m2_f64.T                           # F x n view, Fortran-contiguous, pinned
         tgt_h, seed_h = targets.copy(), w["seed"].copy()
 
+        phases = {}
+
         def one_e2e():
+            t0 = time.perf_counter()
             ctx.load_matrix(m2_r)
+            t1 = time.perf_counter()
             ctx.set_targets(tgt_h)
             ctx.set_seed(seed_h)
+            t2 = time.perf_counter()
             one_search()
-            return ctx.search_fetch(iters)
+            r = ctx.search_fetch(iters)
+            t3 = time.perf_counter()
+            phases.update(load_matrix=(t1 - t0) * 1e3, targets_seed=(t2 - t1) * 1e3, search_fetch=(t3 - t2) * 1e3)
+            return r
 
         one_e2e()
         barrier()
@@ -292,6 +321,7 @@ def main():
         d2h = sum(v.nbytes for v in res.values() if v is not None)
         e2e = {"value": F * T * iters / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
+               "phases_ms_rank0_last_step": {k: round(v, 3) for k, v in phases.items()},
                "call": "rvl_load_matrix_f64_colmajor + rvl_set_targets + rvl_set_seed + search + rvl_search_fetch"}
 
     # ---- the same search fed from a GCT v1.2 text file on local disk (rvl_load_matrix_gct: text over PCIe,
@@ -389,7 +419,8 @@ def main():
                        "exchange": ("peer-memory stores (CUDA IPC over NVLink)" if use_p2p else
                                     ("NCCL all_gather" if world > 1 else "none")),
                        "l2": "flushed between timed steps (256 MiB write); bit matrix %.1f MB < L2" % (cnt * words * 8 / 1e6),
-                       "step": "one full search: iterations x (score + rank + merge + seed IC)"},
+                       "step": "one full search: iterations x (score + rank + merge + seed IC)",
+                       "host_affinity": ("%d NUMA-local cores of the GPU (NVML)" % numa_cores) if numa_cores else "unbound"},
             "e2e": e2e, "e2e_gct": e2e_gct, "gpu_launches": int(gpu_launches), "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu,
         }
