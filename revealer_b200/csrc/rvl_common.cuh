@@ -130,6 +130,42 @@ __device__ __forceinline__ double rvl_log_pos(double q)
     return fma((double)k, RVL_LG[4], e.y) + lm;
 }
 
+// Four logs at once, written stage by stage (all index computations, all table loads, all r, ...): the
+// four dependency chains are independent, and laying them out side by side is what lets the scheduler
+// issue one chain's FP64 instruction while the others wait out their ~9-cycle latency.  Same arithmetic
+// as rvl_log_pos, bit for bit.
+__device__ __forceinline__ void rvl_log_pos4(const double q0, const double q1, const double q2, const double q3,
+                                             double &l0, double &l1, double &l2, double &l3)
+{
+    const char *base = reinterpret_cast<const char *>(rvl_logtab_smem()) + (threadIdx.x & (RVL_LOGTAB_COPIES - 1)) * 16;
+    const int h0 = __double2hiint(q0), h1 = __double2hiint(q1), h2 = __double2hiint(q2), h3 = __double2hiint(q3);
+    const int s0 = h0 + (0x3ff00000 - 0x3fe6a09e), s1 = h1 + (0x3ff00000 - 0x3fe6a09e),
+              s2 = h2 + (0x3ff00000 - 0x3fe6a09e), s3 = h3 + (0x3ff00000 - 0x3fe6a09e);
+    const double2 e0 = *reinterpret_cast<const double2 *>(base + ((s0 >> 5) & 0x7f80));
+    const double2 e1 = *reinterpret_cast<const double2 *>(base + ((s1 >> 5) & 0x7f80));
+    const double2 e2 = *reinterpret_cast<const double2 *>(base + ((s2 >> 5) & 0x7f80));
+    const double2 e3 = *reinterpret_cast<const double2 *>(base + ((s3 >> 5) & 0x7f80));
+    const int k0 = (s0 >> 20) - 0x3ff, k1 = (s1 >> 20) - 0x3ff, k2 = (s2 >> 20) - 0x3ff, k3 = (s3 >> 20) - 0x3ff;
+    const double m0 = __hiloint2double(h0 - (k0 << 20), __double2loint(q0));
+    const double m1 = __hiloint2double(h1 - (k1 << 20), __double2loint(q1));
+    const double m2 = __hiloint2double(h2 - (k2 << 20), __double2loint(q2));
+    const double m3 = __hiloint2double(h3 - (k3 << 20), __double2loint(q3));
+    const double r0 = fma(m0, e0.x, -1.0), r1 = fma(m1, e1.x, -1.0), r2 = fma(m2, e2.x, -1.0), r3 = fma(m3, e3.x, -1.0);
+    const double b0 = fma((double)k0, RVL_LG[4], e0.y), b1 = fma((double)k1, RVL_LG[4], e1.y),
+                 b2 = fma((double)k2, RVL_LG[4], e2.y), b3 = fma((double)k3, RVL_LG[4], e3.y);
+    const double z0 = r0 * r0, z1 = r1 * r1, z2 = r2 * r2, z3 = r3 * r3;
+    const double a0 = fma(r0, RVL_LG[0], RVL_LG[1]), a1 = fma(r1, RVL_LG[0], RVL_LG[1]),
+                 a2 = fma(r2, RVL_LG[0], RVL_LG[1]), a3 = fma(r3, RVL_LG[0], RVL_LG[1]);
+    const double c0 = fma(r0, RVL_LG[2], RVL_LG[3]), c1 = fma(r1, RVL_LG[2], RVL_LG[3]),
+                 c2 = fma(r2, RVL_LG[2], RVL_LG[3]), c3 = fma(r3, RVL_LG[2], RVL_LG[3]);
+    const double p0 = fma(c0, z0, a0), p1 = fma(c1, z1, a1), p2 = fma(c2, z2, a2), p3 = fma(c3, z3, a3);
+    const double t0 = fma(z0, p0, r0), t1 = fma(z1, p1, r1), t2 = fma(z2, p2, r2), t3 = fma(z3, p3, r3);
+    l0 = b0 + t0;
+    l1 = b1 + t1;
+    l2 = b2 + t2;
+    l3 = b3 + t3;
+}
+
 // exp(a) for a <= 0 (Gaussian kernel weights).  Branch-free: k = round(a log2 e) by the 1.5*2^52 trick,
 // r = a - k ln2 (hi/lo split, FMA), degree-12 Taylor polynomial on |r| <= 0.347, 2^k by an integer add
 // to the exponent field.  Results below ~2e-307 are flushed to 0 (they are > 280 orders of magnitude

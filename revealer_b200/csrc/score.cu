@@ -28,6 +28,20 @@
 #include <cstring>
 
 #define RVL_SCORE_WARPS 8 // warps per block of k_advance / k_assoc (fixes their summation order)
+#ifndef RVL_EPI_CALL
+#define RVL_EPI_CALL 0 // 1: the production entropy epilogue is a real call with its own register budget
+#endif
+#define RVL_STR(x) #x
+#define RVL_UNROLL(n) _Pragma(RVL_STR(unroll n))
+#ifndef RVL_UNROLL_A
+#define RVL_UNROLL_A 1 // unroll of the entropy epilogue's pass A (per-k tables over the x grid)
+#endif
+#ifndef RVL_UNROLL_B
+#define RVL_UNROLL_B 1 // unroll of pass B (column classification over the y grid)
+#endif
+#ifndef RVL_C_ILP
+#define RVL_C_ILP 4 // logs in flight per lane in pass C of the entropy epilogue (4 or 2)
+#endif
 #ifndef RVL_KSCORE_WARPS
 #define RVL_KSCORE_WARPS 8 // independent worker warps per block of k_score
 #endif
@@ -39,6 +53,7 @@ __device__ double2 rvl_logtab_g[RVL_LOGTAB_ENTRIES];
 // ---- per-warp scratch in shared memory ----------------------------------------------------
 struct __align__(16) RvlWarpScratch {
     double A[RVL_MAXG][4];     // A[i][a*2+b]
+    double AT[4][RVL_MAXG];    // the same numbers class-major (pass C loads four consecutive grid points per class)
     double gy[2][RVL_MAXG];    // gy[a][j]
     double gz[2][RVL_MAXG];    // gz[b][k]
     uint16_t live[RVL_MAXG * RVL_MAXG];
@@ -225,7 +240,7 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
     // instead of a NaN-aware FP64 compare-select) and widened outwards afterwards.
     double SV = 0.0, LV = 0.0, LLV = 0.0, accxz = 0.0;
     int minVh = 0x7ff00000, maxVh = 0, maxWh = 0;
-#pragma unroll 2
+RVL_UNROLL(RVL_UNROLL_A)
     for (int i = 0; i < G; i++) {
         const double V = fma(S.A[i][M0], gz0, S.A[i][M1] * gz1);
         const double W = fma(S.A[i][m0], gz0, S.A[i][m1] * gz1);
@@ -250,7 +265,7 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
     double accF = 0.0, accyz = 0.0;
     int ndirect = 0, nfact = 0, ndead = 0;
     const double inv = 1.0 / ((double)(G - 1) * hy);
-#pragma unroll 1
+RVL_UNROLL(RVL_UNROLL_B)
     for (int j = 0; j < G; j++) {
         const double g0 = S.gy[0][j], g1 = S.gy[1][j];
         const double gM = am ? g1 : g0, gm = am ? g0 : g1;
@@ -290,15 +305,36 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
         const double w10 = S.gy[1][j] * S.gz[0][k], w11 = S.gy[1][j] * S.gz[1][k];
 #define RVL_CELL(ii) fma(S.A[ii][0], w00, fma(S.A[ii][1], w01, fma(S.A[ii][2], w10, fma(S.A[ii][3], w11, epsq))))
         int i = 0;
+#if RVL_C_ILP == 4
+        // four grid points per trip, level by level: the four cells' FMA chains and the four logs advance
+        // side by side (class-major AT: two 16-byte loads fetch one class for all four points)
 #pragma unroll 1
         for (; i + 3 < G; i += 4) {
-            double q0 = RVL_CELL(i), q1 = RVL_CELL(i + 1), q2 = RVL_CELL(i + 2), q3 = RVL_CELL(i + 3);
-            double l0 = rvl_logq<FAST>(q0), l1 = rvl_logq<FAST>(q1), l2 = rvl_logq<FAST>(q2), l3 = rvl_logq<FAST>(q3);
+            double2 lo = *reinterpret_cast<const double2 *>(&S.AT[3][i]), hi = *reinterpret_cast<const double2 *>(&S.AT[3][i + 2]);
+            double q0 = fma(lo.x, w11, epsq), q1 = fma(lo.y, w11, epsq), q2 = fma(hi.x, w11, epsq), q3 = fma(hi.y, w11, epsq);
+            lo = *reinterpret_cast<const double2 *>(&S.AT[2][i]); hi = *reinterpret_cast<const double2 *>(&S.AT[2][i + 2]);
+            q0 = fma(lo.x, w10, q0); q1 = fma(lo.y, w10, q1); q2 = fma(hi.x, w10, q2); q3 = fma(hi.y, w10, q3);
+            lo = *reinterpret_cast<const double2 *>(&S.AT[1][i]); hi = *reinterpret_cast<const double2 *>(&S.AT[1][i + 2]);
+            q0 = fma(lo.x, w01, q0); q1 = fma(lo.y, w01, q1); q2 = fma(hi.x, w01, q2); q3 = fma(hi.y, w01, q3);
+            lo = *reinterpret_cast<const double2 *>(&S.AT[0][i]); hi = *reinterpret_cast<const double2 *>(&S.AT[0][i + 2]);
+            q0 = fma(lo.x, w00, q0); q1 = fma(lo.y, w00, q1); q2 = fma(hi.x, w00, q2); q3 = fma(hi.y, w00, q3);
+            double l0, l1, l2, l3;
+            if (FAST) rvl_log_pos4(q0, q1, q2, q3, l0, l1, l2, l3);
+            else { l0 = log(q0); l1 = log(q1); l2 = log(q2); l3 = log(q3); }
             acc0 = fma(q0, l0, acc0);
             acc1 = fma(q1, l1, acc1);
             acc2 = fma(q2, l2, acc2);
             acc3 = fma(q3, l3, acc3);
         }
+#else
+#pragma unroll 1
+        for (; i + 1 < G; i += 2) {
+            double q0 = RVL_CELL(i), q1 = RVL_CELL(i + 1);
+            double l0 = rvl_logq<FAST>(q0), l1 = rvl_logq<FAST>(q1);
+            acc0 = fma(q0, l0, acc0);
+            acc1 = fma(q1, l1, acc1);
+        }
+#endif
 #pragma unroll 1
         for (; i < G; i++) {
             double q0 = RVL_CELL(i);
@@ -316,6 +352,25 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
     }
     const double Lz = rvl_warp_sum(accz);
     return (L3 - Lxz - Lyz + Lz) / Stot;
+}
+
+// The production epilogue as a real call (one per evaluation): the callee gets a register budget of its own
+// instead of sharing 128 registers with everything k_score keeps live across an evaluation, which is what
+// lets pass C hold four cells and four logs in flight.  The scratch is re-derived from the dynamic shared
+// memory base so that its loads stay LDS (a reference parameter would make them generic).
+struct RvlEpiResult {
+    double cmi;
+    int ndirect, nfact;
+};
+template <bool FAST>
+__device__ __noinline__ RvlEpiResult rvl_cmi_epilogue_f_call(int warp_slot, int G, double epsq, double theta, double hy, int am,
+                                                             int lane)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RvlWarpScratch &S = reinterpret_cast<RvlWarpScratch *>(smem_raw)[warp_slot];
+    RvlEpiResult r;
+    r.cmi = rvl_cmi_epilogue_f<FAST>(S, G, epsq, theta, hy, am, lane, &r.ndirect, &r.nfact);
+    return r;
 }
 
 // 2-D epilogue (mutual.inf.v2, LIB:2536-2550): MI from B_a[i] = A[i][a*2] and gy.  Whole warp.
@@ -422,7 +477,7 @@ __global__ void k_rho_max(RvlParams P, const uint64_t *__restrict__ bits, const 
 // am: majority y-class (0 unless the row has more ones than zeros).  nlive_out: columns evaluated
 // cell by cell; nfact_out: columns handled by the O(1) factorised form.
 __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, double rho, double c, double hx,
-                             double bcv_y, double bcv_z, int am, int lane, int *nlive_out, int *nfact_out)
+                             double bcv_y, double bcv_z, int am, int lane, int *nlive_out, int *nfact_out, int dyn_slot = -1)
 {
     *nlive_out = 0;
     *nfact_out = 0;
@@ -445,7 +500,12 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
     double cmi;
     if (epsq < 1e-290) cmi = rvl_cmi_epilogue<false>(S, G, epsq, P.prune_theta, lane, nlive_out);
     else if (P.literal) cmi = rvl_cmi_epilogue<true>(S, G, epsq, P.prune_theta, lane, nlive_out); // literal mode
-    else cmi = rvl_cmi_epilogue_f<true>(S, G, epsq, P.prune_theta, hy, am, lane, nlive_out, nfact_out);
+    else if (dyn_slot >= 0) { // k_score: S is slot `dyn_slot` of the dynamic shared memory
+        const RvlEpiResult r = rvl_cmi_epilogue_f_call<true>(dyn_slot, G, epsq, P.prune_theta, hy, am, lane);
+        cmi = r.cmi;
+        *nlive_out = r.ndirect;
+        *nfact_out = r.nfact;
+    } else cmi = rvl_cmi_epilogue_f<true>(S, G, epsq, P.prune_theta, hy, am, lane, nlive_out, nfact_out);
     return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * cmi));
 }
 
@@ -959,10 +1019,12 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
         }
         if (lane < G) {
             S.A[lane][0] = acc[0]; S.A[lane][1] = acc[1]; S.A[lane][2] = acc[2]; S.A[lane][3] = acc[3];
+            S.AT[0][lane] = acc[0]; S.AT[1][lane] = acc[1]; S.AT[2][lane] = acc[2]; S.AT[3][lane] = acc[3];
         }
         __syncwarp();
         int nlive, nfact;
-        double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, n1 > n - n1 ? 1 : 0, lane, &nlive, &nfact);
+        double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, n1 > n - n1 ? 1 : 0, lane, &nlive, &nfact,
+                                  RVL_EPI_CALL ? warp : -1);
         if (lane == 0) {
             out[f] = score;
             if (ctr) { // instrumentation: work actually executed (bench.py's roofline numerator)

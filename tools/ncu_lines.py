@@ -60,3 +60,38 @@ if len(sys.argv) > 3:  # bucket score.cu lines into regions: "name:lo-hi,name:lo
         print("%-14s samples %6d %5.1f%%  inst %11d  fp64 %11d" % (name, v[0], 100.0 * v[0] / tot_s, v[1], v[2]))
     for f, c in other.most_common():
         print("other %-28s samples %6d %5.1f%%" % (f, c, 100.0 * c / tot_s))
+if len(sys.argv) > 4 and sys.argv[4] == "stalls":  # per-region warp-stall reasons (SASS-level samples)
+    fname, hdr, cur = None, None, None
+    reg_of = {}
+    tot = collections.Counter()
+    per = collections.defaultdict(collections.Counter)
+    for r in rows:
+        if len(r) == 2 and r[0] == "File Path":
+            fname = os.path.basename(r[1]); continue
+        if r and r[0] == "Line No":
+            hdr = r
+            cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+            continue
+        if hdr is None or len(r) < len(hdr) - 2:
+            continue
+        if r[0] != "":
+            ln = num(r[0])
+            name = fname
+            if fname == "score.cu":
+                name = "score.cu:other"
+                for nm, lo, hi in regs:
+                    if lo <= ln <= hi:
+                        name = nm
+                        break
+            cur = name
+        elif cur is not None:
+            for i, h in cols:
+                v = num(r[i])
+                if v:
+                    per[cur][h] += v
+                    tot[h] += v
+    keys = [k for k, _ in tot.most_common(8)]
+    print("%-22s %8s " % ("region", "samples") + " ".join("%14s" % k[6:20] for k in keys))
+    for name, c in sorted(per.items(), key=lambda kv: -sum(kv[1].values())):
+        sm = sum(c.values())
+        print("%-22s %8d " % (name[:22], sm) + " ".join("%13.1f%%" % (100.0 * c[k] / max(sm, 1)) for k in keys))
