@@ -122,18 +122,41 @@ static bool blank_line(const char *p, const char *e)
     return true;
 }
 
-// Start offsets of the data lines (host scan with memchr; only needed for names / single rows).
+// Start offsets of the data lines (host scan with memchr, a few threads each on its own byte range cut at a
+// newline; only needed for names / single rows).
 static int gct_index(rvl_gct *g)
 {
     if (g->indexed) return 0;
-    const char *p = g->base + g->data_off, *end = g->base + g->size;
+    const char *beg = g->base + g->data_off, *end = g->base + g->size;
+    const size_t len = (size_t)(end - beg);
+    const int T = len > ((size_t)8 << 20) ? 4 : 1;
+    std::vector<const char *> cut(T + 1, end);
+    cut[0] = beg;
+    for (int i = 1; i < T; i++) { // segment i starts right after the first newline at or after its nominal start
+        const char *p = beg + len / T * i;
+        const char *e = (const char *)memchr(p, '\n', (size_t)(end - p));
+        cut[i] = e ? e + 1 : end;
+        if (cut[i] < cut[i - 1]) cut[i] = cut[i - 1];
+    }
+    std::vector<std::vector<size_t>> part(T);
+    auto scan = [&](int i) {
+        const char *p = cut[i], *stop = cut[i + 1];
+        part[i].reserve((size_t)g->nrow / T + 16);
+        while (p < stop) {
+            const char *e = line_end(p, end);
+            if (!blank_line(p, e)) part[i].push_back((size_t)(p - g->base));
+            p = e < end ? e + 1 : end;
+        }
+    };
+    if (T == 1) scan(0);
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < T; i++) th.emplace_back(scan, i);
+        for (auto &t : th) t.join();
+    }
     g->line_start.clear();
     g->line_start.reserve((size_t)g->nrow);
-    while (p < end) {
-        const char *e = line_end(p, end);
-        if (!blank_line(p, e)) g->line_start.push_back((size_t)(p - g->base));
-        p = e < end ? e + 1 : end;
-    }
+    for (int i = 0; i < T; i++) g->line_start.insert(g->line_start.end(), part[i].begin(), part[i].end());
     if ((int64_t)g->line_start.size() != g->nrow) {
         g->err = "file has " + std::to_string(g->line_start.size()) + " data lines, header says " + std::to_string(g->nrow);
         return -2;

@@ -57,3 +57,25 @@ def test_gct_open_errors(tmp_path):
     with rb.GctFile(p) as g:
         with pytest.raises(rb.RevealerError, match="data lines"):
             g.row_names
+
+
+def test_gct_index_of_a_large_file_uses_several_threads(tmp_path):
+    """> 8 MB of data lines: the line index is built by four threads on byte ranges cut at newlines; the
+    order of rows, blank-line skipping and single-row access must not depend on where the cuts fall."""
+    F, n = 30000, 200
+    m = (np.random.default_rng(0).random((F, n)) < 0.1).astype(np.uint8)
+    body = np.empty((F, 2 * n), dtype=np.uint8)
+    body[:, 0::2] = 9
+    body[:, 1::2] = m + 48
+    p = str(tmp_path / "big.gct")
+    with open(p, "wb") as fh:
+        fh.write(("#1.2\n%d\t%d\nName\tDescription\t%s\n" % (F, n, "\t".join("S%d" % j for j in range(n)))).encode())
+        for i in range(F):
+            fh.write(b"row_%d\tdesc %d" % (i, i) + body[i].tobytes() + b"\n")
+            if i % 1000 == 7:
+                fh.write(b"\n")
+    with rb.GctFile(p) as g:
+        assert g.row_names == ["row_%d" % i for i in range(F)]
+        assert g.descs[12345] == "desc 12345"
+        for i in (0, 7, 8, 14999, 15000, F - 1):
+            assert np.array_equal(g.row_values(i), m[i].astype(float))
