@@ -380,7 +380,8 @@ def main():
         # column, pass C G logs per direct column, G for the z marginal, 1 in the table lookup
         logs = evals * (2 * G * G + G + 1) + direct * (G + 1) + fact
         exps = ctr["dense_exps"] / k_n + evals * (2 * G + 1)
-        plain = evals * (G * G * 18 + G * G * 24 + 80) + direct * G * 10 + ctr["dense_exps"] / k_n * 6
+        two = ctr.get("two_term_columns", 0) / k_n    # direct columns whose cells take 2 FMAs instead of 4
+        plain = evals * (G * G * 18 + G * G * 24 + 80) + direct * G * 10 - two * G * 4 + ctr["dense_exps"] / k_n * 6
         flops = exps * FLOP_PER_EXP + logs * FLOP_PER_LOG + plain
         words = ((n + 63) // 64 + 1) & ~1
         bytes_alg = cnt * T * (words * 8 + 8)

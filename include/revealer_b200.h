@@ -241,6 +241,9 @@ int64_t rvl_unique_rows(const rvl_ctx *ctx);
 /* Work counters of the score kernel since the last reset: out4[0] evaluations that ran the KDE path,
  * out4[1] live (j,k) density columns (n_grid log() each), out4[2] dense-pass exp() evaluations. */
 int rvl_get_counters(rvl_ctx *ctx, uint64_t *out4, int reset);
+/* The same with more slots (n_out <= 8): out[3] (j,k) columns in the O(1) factorised form, out[4] direct columns
+ * evaluated with two of the four class terms (the other y-class cannot change fl(Q) anywhere in the column). */
+int rvl_get_counters_ex(rvl_ctx *ctx, uint64_t *out, int n_out, int reset);
 /* FP64 FMA peak of this device by a DFMA-chain micro-benchmark (TFLOP/s); the denominator of the
  * roofline bench.py reports, since the path is FP64-compute-bound. */
 int rvl_measure_fp64_peak(rvl_ctx *ctx, double *out_tflops);

@@ -88,6 +88,7 @@ SIGNATURES = {
     "rvl_set_dedup": (_i, [_vp, _i]),
     "rvl_unique_rows": (_i64, [_vp]),
     "rvl_get_counters": (_i, [_vp, _u64p, _i]),
+    "rvl_get_counters_ex": (_i, [_vp, _u64p, _i, _i]),
     "rvl_measure_fp64_peak": (_i, [_vp, _dp]),
 }
 

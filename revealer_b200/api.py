@@ -404,10 +404,10 @@ class RevealerContext:
         self._ck(self._lib.rvl_set_prune_theta(self._h, float(theta)))
 
     def counters(self, reset=False):
-        out = (C.c_uint64 * 4)()
-        self._ck(self._lib.rvl_get_counters(self._h, out, int(reset)))
+        out = (C.c_uint64 * 8)()
+        self._ck(self._lib.rvl_get_counters_ex(self._h, out, 8, int(reset)))
         return dict(kde_evaluations=int(out[0]), live_columns=int(out[1]), dense_exps=int(out[2]),
-                    factorised_columns=int(out[3]))
+                    factorised_columns=int(out[3]), two_term_columns=int(out[4]))
 
     def measure_fp64_peak(self):
         out = C.c_double()

@@ -172,7 +172,7 @@ struct rvl_ctx {
     bool side_pending = false;
 
     // instrumentation
-    unsigned long long *d_ctr = nullptr; // [0] KDE evaluations, [1] live (j,k) columns, [2] dense-pass exps
+    unsigned long long *d_ctr = nullptr; // [0] KDE evaluations, [1] direct (j,k) columns, [2] x-axis exps, [3] factorised, [4] two-term
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_events;
@@ -272,8 +272,8 @@ extern "C" int rvl_create(rvl_ctx **out, int device)
         cudaMalloc((void **)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_xerr, sizeof(int)) != cudaSuccess ||
         cudaMemset(ctx->d_xerr, 0, sizeof(int)) != cudaSuccess ||
-        cudaMalloc((void **)&ctx->d_ctr, 4 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(ctx->d_ctr, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->d_ctr, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_ctr, 0, 8 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
@@ -1339,17 +1339,19 @@ extern "C" int rvl_score_kernel_time(rvl_ctx *ctx, double *out_ms, int64_t *out_
     return RVL_OK;
 }
 
-extern "C" int rvl_get_counters(rvl_ctx *ctx, uint64_t *out4, int reset)
+extern "C" int rvl_get_counters_ex(rvl_ctx *ctx, uint64_t *out, int n_out, int reset)
 {
     GUARD();
-    if (!out4) return fail(ctx, RVL_ERR_ARG, "out is NULL");
+    if (!out || n_out < 1 || n_out > 8) return fail(ctx, RVL_ERR_ARG, "bad counter request");
     CK(cudaStreamSynchronize(ctx->stream));
-    unsigned long long h[4];
+    unsigned long long h[8];
     CK(cudaMemcpy(h, ctx->d_ctr, sizeof h, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 4; i++) out4[i] = (uint64_t)h[i];
+    for (int i = 0; i < n_out; i++) out[i] = (uint64_t)h[i];
     if (reset) CK(cudaMemset(ctx->d_ctr, 0, sizeof h));
     return RVL_OK;
 }
+
+extern "C" int rvl_get_counters(rvl_ctx *ctx, uint64_t *out4, int reset) { return rvl_get_counters_ex(ctx, out4, 4, reset); }
 
 extern "C" int rvl_measure_fp64_peak(rvl_ctx *ctx, double *out_tflops)
 {

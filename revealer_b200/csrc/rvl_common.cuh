@@ -141,10 +141,11 @@ __device__ __forceinline__ void rvl_log_pos4(const double q0, const double q1, c
     const int h0 = __double2hiint(q0), h1 = __double2hiint(q1), h2 = __double2hiint(q2), h3 = __double2hiint(q3);
     const int s0 = h0 + (0x3ff00000 - 0x3fe6a09e), s1 = h1 + (0x3ff00000 - 0x3fe6a09e),
               s2 = h2 + (0x3ff00000 - 0x3fe6a09e), s3 = h3 + (0x3ff00000 - 0x3fe6a09e);
-    const double2 e0 = *reinterpret_cast<const double2 *>(base + ((s0 >> 5) & 0x7f80));
-    const double2 e1 = *reinterpret_cast<const double2 *>(base + ((s1 >> 5) & 0x7f80));
-    const double2 e2 = *reinterpret_cast<const double2 *>(base + ((s2 >> 5) & 0x7f80));
-    const double2 e3 = *reinterpret_cast<const double2 *>(base + ((s3 >> 5) & 0x7f80));
+#define RVL_TABMASK 0x7f80
+    const double2 e0 = *reinterpret_cast<const double2 *>(base + ((s0 >> 5) & RVL_TABMASK));
+    const double2 e1 = *reinterpret_cast<const double2 *>(base + ((s1 >> 5) & RVL_TABMASK));
+    const double2 e2 = *reinterpret_cast<const double2 *>(base + ((s2 >> 5) & RVL_TABMASK));
+    const double2 e3 = *reinterpret_cast<const double2 *>(base + ((s3 >> 5) & RVL_TABMASK));
     const int k0 = (s0 >> 20) - 0x3ff, k1 = (s1 >> 20) - 0x3ff, k2 = (s2 >> 20) - 0x3ff, k3 = (s3 >> 20) - 0x3ff;
     const double m0 = __hiloint2double(h0 - (k0 << 20), __double2loint(q0));
     const double m1 = __hiloint2double(h1 - (k1 << 20), __double2loint(q1));

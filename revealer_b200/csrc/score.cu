@@ -39,9 +39,6 @@
 #ifndef RVL_UNROLL_B
 #define RVL_UNROLL_B 1 // unroll of pass B (column classification over the y grid)
 #endif
-#ifndef RVL_C_ILP
-#define RVL_C_ILP 4 // logs in flight per lane in pass C of the entropy epilogue (4 or 2)
-#endif
 #ifndef RVL_KSCORE_WARPS
 #define RVL_KSCORE_WARPS 8 // independent worker warps per block of k_score
 #endif
@@ -217,7 +214,7 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, double
 // roughly half of the logs.
 template <bool FAST>
 __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, double theta, double hy, int am, int lane,
-                                     int *ndirect_out, int *nfact_out)
+                                     int *ndirect_out, int *nfact_out, int *ntwo_out)
 {
     const unsigned FULL = 0xffffffffu;
     const int M0 = am * 2, M1 = am * 2 + 1, m0 = (1 - am) * 2, m1 = (1 - am) * 2 + 1;
@@ -261,53 +258,75 @@ RVL_UNROLL(RVL_UNROLL_A)
     if (!active) accxz = 0.0;
     const double sM = fma(sa[M0], gz0, sa[M1] * gz1), sm = fma(sa[m0], gz0, sa[m1] * gz1);
 
-    // ---- pass B: classify the G columns of this k, one j per round
+    // ---- pass B: classify the G columns of this k, one j per round.  Column codes are (j << 5) | k.
+    // (Taking the y-z marginal logs out of this loop -- live-column list, four logs per lane and trip
+    // afterwards -- was measured: 0.6 % slower.)
     double accF = 0.0, accyz = 0.0;
-    int ndirect = 0, nfact = 0, ndead = 0;
+    int n4 = 0, n2 = 0, nfact = 0, ndead = 0;
     const double inv = 1.0 / ((double)(G - 1) * hy);
+    const unsigned below = (1u << lane) - 1u;
 RVL_UNROLL(RVL_UNROLL_B)
+#ifdef RVL_ABLATE_PASS_B
+    for (int j = 0; j < 0; j++) {
+#else
     for (int j = 0; j < G; j++) {
+#endif
         const double g0 = S.gy[0][j], g1 = S.gy[1][j];
         const double gM = am ? g1 : g0, gm = am ? g0 : g1;
         const double dmax = fma(gM, maxV, gm * maxW);
         const bool dead = dmax < dead_thr;
-        if (!__any_sync(FULL, active && !dead)) { // the whole y-slice is below the threshold (typical mid-axis j)
+        const unsigned mL = __ballot_sync(FULL, active && !dead);
+        if (!mL) { // the whole y-slice is below the threshold (typical mid-axis j)
             ndead += G;
             continue;
         }
-        const bool fact = !dead && (gm * maxW <= 0x1p-54 * fma(gM, minV, epsq)) && (gM * minV >= 16.0 * epsq);
+        const int code = (j << 5) | lane;
         if (active && !dead) {
             const double qyz = fma(gM, sM, fma(gm, sm, gE));
             accyz = fma(qyz, rvl_logq<FAST>(qyz), accyz);
         }
+        const bool fact = !dead && (gm * maxW <= 0x1p-54 * fma(gM, minV, epsq)) && (gM * minV >= 16.0 * epsq);
         if (active && fact) {
             const double t = (double)(am ? (G - 1 - j) : j) * inv;
             const double lg = -0.5 * t * t; // log g_M[j]
             accF += fma(gM, fma(lg, SV, LV), epsq * (fma((double)G, lg, LLV) + (double)G));
         }
+        // direct columns: when one y-class cannot change fl(Q) anywhere in the column (its largest term is
+        // below half an ulp of the eps' floor every cell carries) the cell needs only the other class's two
+        // terms -- bit-identical to the four-term chain, half the FMAs and loads.  Four-term columns are
+        // listed from the front of S.live, two-term columns from the back (bit 15: the surviving class is
+        // the minority one).
         const bool direct = active && !dead && !fact;
-        const unsigned md = __ballot_sync(FULL, direct);
-        if (direct) S.live[ndirect + __popc(md & ((1u << lane) - 1u))] = (uint16_t)(j * G + lane);
-        ndirect += __popc(md);
+        const bool dropM = direct && (gM * maxV < 0x1p-54 * epsq);
+        const bool dropm = direct && !dropM && (gm * maxW < 0x1p-54 * epsq);
+        const bool four = direct && !dropM && !dropm;
+        const unsigned m4 = __ballot_sync(FULL, four), m2 = __ballot_sync(FULL, direct && !four);
+        if (four) S.live[n4 + __popc(m4 & below)] = (uint16_t)code;
+        if (direct && !four)
+            S.live[RVL_MAXG * RVL_MAXG - 1 - (n2 + __popc(m2 & below))] = (uint16_t)(code | (dropM ? 0x8000 : 0));
+        n4 += __popc(m4);
+        n2 += __popc(m2);
         nfact += __popc(__ballot_sync(FULL, active && fact));
-        ndead += __popc(__ballot_sync(FULL, active && dead));
+        ndead += G - __popc(mL);
     }
     __syncwarp();
-    *ndirect_out = ndirect;
+    *ndirect_out = n4 + n2;
     *nfact_out = nfact;
+    *ntwo_out = n2;
 
-    // ---- pass C: direct columns, lanes = columns
+    // ---- pass C: direct columns, lanes = columns; four grid points per trip, level by level: the four cells'
+    // FMA chains and the four logs advance side by side (class-major AT: two 16-byte loads fetch one class
+    // for all four points)
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-    for (int idx = lane; idx < ndirect; idx += 32) {
+#ifdef RVL_ABLATE_PASS_C // timing experiments only: results are wrong with these set
+    n4 = 0; n2 = 0;
+#endif
+    for (int idx = lane; idx < n4; idx += 32) {
         const int p = S.live[idx];
-        const int j = p / G, k = p - j * G;
+        const int j = p >> 5, k = p & 31;
         const double w00 = S.gy[0][j] * S.gz[0][k], w01 = S.gy[0][j] * S.gz[1][k];
         const double w10 = S.gy[1][j] * S.gz[0][k], w11 = S.gy[1][j] * S.gz[1][k];
-#define RVL_CELL(ii) fma(S.A[ii][0], w00, fma(S.A[ii][1], w01, fma(S.A[ii][2], w10, fma(S.A[ii][3], w11, epsq))))
         int i = 0;
-#if RVL_C_ILP == 4
-        // four grid points per trip, level by level: the four cells' FMA chains and the four logs advance
-        // side by side (class-major AT: two 16-byte loads fetch one class for all four points)
 #pragma unroll 1
         for (; i + 3 < G; i += 4) {
             double2 lo = *reinterpret_cast<const double2 *>(&S.AT[3][i]), hi = *reinterpret_cast<const double2 *>(&S.AT[3][i + 2]);
@@ -326,21 +345,39 @@ RVL_UNROLL(RVL_UNROLL_B)
             acc2 = fma(q2, l2, acc2);
             acc3 = fma(q3, l3, acc3);
         }
-#else
-#pragma unroll 1
-        for (; i + 1 < G; i += 2) {
-            double q0 = RVL_CELL(i), q1 = RVL_CELL(i + 1);
-            double l0 = rvl_logq<FAST>(q0), l1 = rvl_logq<FAST>(q1);
-            acc0 = fma(q0, l0, acc0);
-            acc1 = fma(q1, l1, acc1);
-        }
-#endif
 #pragma unroll 1
         for (; i < G; i++) {
-            double q0 = RVL_CELL(i);
+            const double q0 = fma(S.AT[0][i], w00, fma(S.AT[1][i], w01, fma(S.AT[2][i], w10, fma(S.AT[3][i], w11, epsq))));
             acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
         }
-#undef RVL_CELL
+    }
+    for (int idx = lane; idx < n2; idx += 32) { // two-term columns: classes (ra, ra + 1) of one y value
+        const int e = S.live[RVL_MAXG * RVL_MAXG - 1 - idx];
+        const int ra = (e >> 15) ? m0 : M0;
+        const int j = (e >> 5) & 31, k = e & 31;
+        const double g = S.gy[ra >> 1][j];
+        const double wa = g * S.gz[0][k], wb = g * S.gz[1][k];
+        const double *Aa = S.AT[ra], *Ab = S.AT[ra + 1];
+        int i = 0;
+#pragma unroll 1
+        for (; i + 3 < G; i += 4) {
+            double2 lo = *reinterpret_cast<const double2 *>(Ab + i), hi = *reinterpret_cast<const double2 *>(Ab + i + 2);
+            double q0 = fma(lo.x, wb, epsq), q1 = fma(lo.y, wb, epsq), q2 = fma(hi.x, wb, epsq), q3 = fma(hi.y, wb, epsq);
+            lo = *reinterpret_cast<const double2 *>(Aa + i); hi = *reinterpret_cast<const double2 *>(Aa + i + 2);
+            q0 = fma(lo.x, wa, q0); q1 = fma(lo.y, wa, q1); q2 = fma(hi.x, wa, q2); q3 = fma(hi.y, wa, q3);
+            double l0, l1, l2, l3;
+            if (FAST) rvl_log_pos4(q0, q1, q2, q3, l0, l1, l2, l3);
+            else { l0 = log(q0); l1 = log(q1); l2 = log(q2); l3 = log(q3); }
+            acc0 = fma(q0, l0, acc0);
+            acc1 = fma(q1, l1, acc1);
+            acc2 = fma(q2, l2, acc2);
+            acc3 = fma(q3, l3, acc3);
+        }
+#pragma unroll 1
+        for (; i < G; i++) {
+            const double q0 = fma(Aa[i], wa, fma(Ab[i], wb, epsq));
+            acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
+        }
     }
     const double L3 = rvl_warp_sum((acc0 + acc1) + (acc2 + acc3) + accF) + (double)ndead * (double)G * rvl_xlogx<FAST>(epsq);
     const double Lyz = rvl_warp_sum(accyz) + (double)ndead * rvl_xlogx<FAST>(gE);
@@ -360,7 +397,7 @@ RVL_UNROLL(RVL_UNROLL_B)
 // memory base so that its loads stay LDS (a reference parameter would make them generic).
 struct RvlEpiResult {
     double cmi;
-    int ndirect, nfact;
+    int ndirect, nfact, ntwo;
 };
 template <bool FAST>
 __device__ __noinline__ RvlEpiResult rvl_cmi_epilogue_f_call(int warp_slot, int G, double epsq, double theta, double hy, int am,
@@ -369,7 +406,7 @@ __device__ __noinline__ RvlEpiResult rvl_cmi_epilogue_f_call(int warp_slot, int 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RvlWarpScratch &S = reinterpret_cast<RvlWarpScratch *>(smem_raw)[warp_slot];
     RvlEpiResult r;
-    r.cmi = rvl_cmi_epilogue_f<FAST>(S, G, epsq, theta, hy, am, lane, &r.ndirect, &r.nfact);
+    r.cmi = rvl_cmi_epilogue_f<FAST>(S, G, epsq, theta, hy, am, lane, &r.ndirect, &r.nfact, &r.ntwo);
     return r;
 }
 
@@ -477,10 +514,12 @@ __global__ void k_rho_max(RvlParams P, const uint64_t *__restrict__ bits, const 
 // am: majority y-class (0 unless the row has more ones than zeros).  nlive_out: columns evaluated
 // cell by cell; nfact_out: columns handled by the O(1) factorised form.
 __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, double rho, double c, double hx,
-                             double bcv_y, double bcv_z, int am, int lane, int *nlive_out, int *nfact_out, int dyn_slot = -1)
+                             double bcv_y, double bcv_z, int am, int lane, int *nlive_out, int *nfact_out, int *ntwo_out,
+                             int dyn_slot = -1)
 {
     *nlive_out = 0;
     *nfact_out = 0;
+    *ntwo_out = 0;
     int G = P.G;
     double dn = (double)P.n;
     if (mode == RVL_MODE_IC) {
@@ -505,7 +544,8 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
         cmi = r.cmi;
         *nlive_out = r.ndirect;
         *nfact_out = r.nfact;
-    } else cmi = rvl_cmi_epilogue_f<true>(S, G, epsq, P.prune_theta, hy, am, lane, nlive_out, nfact_out);
+        *ntwo_out = r.ntwo;
+    } else cmi = rvl_cmi_epilogue_f<true>(S, G, epsq, P.prune_theta, hy, am, lane, nlive_out, nfact_out, ntwo_out);
     return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * cmi));
 }
 
@@ -1022,9 +1062,9 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
             S.AT[0][lane] = acc[0]; S.AT[1][lane] = acc[1]; S.AT[2][lane] = acc[2]; S.AT[3][lane] = acc[3];
         }
         __syncwarp();
-        int nlive, nfact;
+        int nlive, nfact, ntwo;
         double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, n1 > n - n1 ? 1 : 0, lane, &nlive, &nfact,
-                                  RVL_EPI_CALL ? warp : -1);
+                                  &ntwo, RVL_EPI_CALL ? warp : -1);
         if (lane == 0) {
             out[f] = score;
             if (ctr) { // instrumentation: work actually executed (bench.py's roofline numerator)
@@ -1032,6 +1072,7 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
                 atomicAdd(&ctr[1], (unsigned long long)nlive);     // (j,k) columns evaluated cell by cell
                 atomicAdd(&ctr[2], (unsigned long long)nexp * G);  // x-axis exp() evaluations
                 atomicAdd(&ctr[3], (unsigned long long)nfact);     // (j,k) columns in factorised form
+                atomicAdd(&ctr[4], (unsigned long long)ntwo);      // direct columns evaluated with two of the four terms
             }
         }
         if (rvl_ahead(score, f, best_v, best_i, P.negative)) { best_v = score; best_i = f; }
@@ -1094,8 +1135,8 @@ __device__ double rvl_assoc_block(const RvlParams &P, const RvlTarget &tg, const
             sh.S.A[lane][0] = b0; sh.S.A[lane][1] = 0.0; sh.S.A[lane][2] = b1; sh.S.A[lane][3] = 0.0;
         }
         __syncwarp();
-        int nlive, nfact;
-        score = rvl_finish(sh.S, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, 0, lane, &nlive, &nfact);
+        int nlive, nfact, ntwo;
+        score = rvl_finish(sh.S, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, 0, lane, &nlive, &nfact, &ntwo);
     }
     return score; // valid in warp 0
 }
