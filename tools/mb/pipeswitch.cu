@@ -2,6 +2,9 @@
 // chains per thread, 16 warps/SM; layout A interleaves them one by one, layout B issues 8 DFMA then 8 integer.
 #include <cstdio>
 #include <cuda_runtime.h>
+#ifndef INTOP
+#define INTOP "mad.lo.s32 %0, %0, %1, %0;"
+#endif
 template <int LAYOUT, int NI> __global__ void k(int iters, double *out, int *iout, double m, double c, int im)
 {
     double a[8];
@@ -12,13 +15,13 @@ template <int LAYOUT, int NI> __global__ void k(int iters, double *out, int *iou
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[i]) : "d"(m), "d"(c));
-                if (i < NI) asm volatile("mad.lo.s32 %0, %0, %1, %0;" : "+r"(v[i]) : "r"(im));
+                if (i < NI) asm volatile(INTOP : "+r"(v[i]) : "r"(im));
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 8; i++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[i]) : "d"(m), "d"(c));
 #pragma unroll
-            for (int i = 0; i < NI; i++) asm volatile("mad.lo.s32 %0, %0, %1, %0;" : "+r"(v[i]) : "r"(im));
+            for (int i = 0; i < NI; i++) asm volatile(INTOP : "+r"(v[i]) : "r"(im));
         }
     }
     double s = 0; int t = 0;
