@@ -87,7 +87,7 @@ struct RvlParams {
 // Table-driven and branch-free: the mantissa is folded to m in [sqrt(1/2), sqrt(2)); the top 8 bits of
 // the folded mantissa field select c_i (midpoint of the 256 sub-intervals) with rc_i = fl(1/c_i) and
 // lc_i = -log(rc_i) (rounded from an 80-bit evaluation on the host, rvl_upload_log_table); then
-//   r = fma(m, rc_i, -1), |r| <= 2^-9,   log q = k ln2 + lc_i + (r - r^2/2 + r^3/3 - r^4/4 + r^5/5)
+//   r = fma(m, rc_i, -1) = m rc_i - 1, |r| <= 2^-9,   log q = k ln2 + lc_i + (r - r^2/2 + r^3/3 - r^4/4 + r^5/5)
 // (truncation r^6/6 <= 9e-18).  Error: <= 2 ulp for |log q| > 0.5, <= 8e-17 absolute below (emulated in
 // tests/test_fastlog.py).  9 FP64-pipe instructions (was 18 with the division-based form), dependency
 // depth 5.  The table sits in shared memory, every entry replicated 8 times ([entry][lane & 7], 16 B
@@ -113,15 +113,18 @@ __device__ __forceinline__ void rvl_logtab_fill(const double2 *__restrict__ g)
     __syncthreads();
 }
 
+// The mantissa m = q 2^-k is never formed: the scaling is moved onto the table value, f = rc_i 2^-k (an integer
+// subtraction on rc_i's high word), and r = fma(q, f, -1) -- the same product m rc_i bit for bit (powers of two
+// scale exactly; q in [2^-1000, 2^1000] keeps f normal), one instruction and one FP64 <- integer operand word
+// fewer per log than assembling m from q's two words.
 __device__ __forceinline__ double rvl_log_pos(double q)
 {
-    const int hi = __double2hiint(q);
-    const int hs = hi + (0x3ff00000 - 0x3fe6a09e);
+    const int hs = __double2hiint(q) + (0x3ff00000 - 0x3fe6a09e);
     const int k = (hs >> 20) - 0x3ff;
-    const double m = __hiloint2double(hi - (k << 20), __double2loint(q)); // hi word in [0x3fe6a09e, 0x3ff6a09e)
     const char *base = reinterpret_cast<const char *>(rvl_logtab_smem()) + (threadIdx.x & (RVL_LOGTAB_COPIES - 1)) * 16;
     const double2 e = *reinterpret_cast<const double2 *>(base + ((hs >> 5) & 0x7f80)); // entry (hs >> 12) & 255, 128 B apart
-    const double r = fma(m, e.x, -1.0);
+    const double f = __hiloint2double(__double2hiint(e.x) - (k << 20), __double2loint(e.x));
+    const double r = fma(q, f, -1.0);
     const double r2 = r * r;
     const double pa = fma(r, RVL_LG[0], RVL_LG[1]);
     const double pb = fma(r, RVL_LG[2], RVL_LG[3]);
@@ -138,20 +141,18 @@ __device__ __forceinline__ void rvl_log_pos4(const double q0, const double q1, c
                                              double &l0, double &l1, double &l2, double &l3)
 {
     const char *base = reinterpret_cast<const char *>(rvl_logtab_smem()) + (threadIdx.x & (RVL_LOGTAB_COPIES - 1)) * 16;
-    const int h0 = __double2hiint(q0), h1 = __double2hiint(q1), h2 = __double2hiint(q2), h3 = __double2hiint(q3);
-    const int s0 = h0 + (0x3ff00000 - 0x3fe6a09e), s1 = h1 + (0x3ff00000 - 0x3fe6a09e),
-              s2 = h2 + (0x3ff00000 - 0x3fe6a09e), s3 = h3 + (0x3ff00000 - 0x3fe6a09e);
-#define RVL_TABMASK 0x7f80
-    const double2 e0 = *reinterpret_cast<const double2 *>(base + ((s0 >> 5) & RVL_TABMASK));
-    const double2 e1 = *reinterpret_cast<const double2 *>(base + ((s1 >> 5) & RVL_TABMASK));
-    const double2 e2 = *reinterpret_cast<const double2 *>(base + ((s2 >> 5) & RVL_TABMASK));
-    const double2 e3 = *reinterpret_cast<const double2 *>(base + ((s3 >> 5) & RVL_TABMASK));
+    const int s0 = __double2hiint(q0) + (0x3ff00000 - 0x3fe6a09e), s1 = __double2hiint(q1) + (0x3ff00000 - 0x3fe6a09e),
+              s2 = __double2hiint(q2) + (0x3ff00000 - 0x3fe6a09e), s3 = __double2hiint(q3) + (0x3ff00000 - 0x3fe6a09e);
+    const double2 e0 = *reinterpret_cast<const double2 *>(base + ((s0 >> 5) & 0x7f80));
+    const double2 e1 = *reinterpret_cast<const double2 *>(base + ((s1 >> 5) & 0x7f80));
+    const double2 e2 = *reinterpret_cast<const double2 *>(base + ((s2 >> 5) & 0x7f80));
+    const double2 e3 = *reinterpret_cast<const double2 *>(base + ((s3 >> 5) & 0x7f80));
     const int k0 = (s0 >> 20) - 0x3ff, k1 = (s1 >> 20) - 0x3ff, k2 = (s2 >> 20) - 0x3ff, k3 = (s3 >> 20) - 0x3ff;
-    const double m0 = __hiloint2double(h0 - (k0 << 20), __double2loint(q0));
-    const double m1 = __hiloint2double(h1 - (k1 << 20), __double2loint(q1));
-    const double m2 = __hiloint2double(h2 - (k2 << 20), __double2loint(q2));
-    const double m3 = __hiloint2double(h3 - (k3 << 20), __double2loint(q3));
-    const double r0 = fma(m0, e0.x, -1.0), r1 = fma(m1, e1.x, -1.0), r2 = fma(m2, e2.x, -1.0), r3 = fma(m3, e3.x, -1.0);
+    const double f0 = __hiloint2double(__double2hiint(e0.x) - (k0 << 20), __double2loint(e0.x));
+    const double f1 = __hiloint2double(__double2hiint(e1.x) - (k1 << 20), __double2loint(e1.x));
+    const double f2 = __hiloint2double(__double2hiint(e2.x) - (k2 << 20), __double2loint(e2.x));
+    const double f3 = __hiloint2double(__double2hiint(e3.x) - (k3 << 20), __double2loint(e3.x));
+    const double r0 = fma(q0, f0, -1.0), r1 = fma(q1, f1, -1.0), r2 = fma(q2, f2, -1.0), r3 = fma(q3, f3, -1.0);
     const double b0 = fma((double)k0, RVL_LG[4], e0.y), b1 = fma((double)k1, RVL_LG[4], e1.y),
                  b2 = fma((double)k2, RVL_LG[4], e2.y), b3 = fma((double)k3, RVL_LG[4], e3.y);
     const double z0 = r0 * r0, z1 = r1 * r1, z2 = r2 * r2, z3 = r3 * r3;
