@@ -387,7 +387,7 @@ def main():
         bytes_alg = cnt * T * (words * 8 + 8)
         traffic = None
         try:  # DRAM bytes per launch from the committed ncu capture of this workload (1 GPU)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_k_score_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_k_score_traffic.json")))
             if tj["workload"] == args.workload and world == 1 and not args.features:
                 traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
         except Exception:
