@@ -8,7 +8,15 @@ A *step* is one complete search over the resident matrix: `iters` x (score every
 the target given the current seed, rank, OR-merge the winner into the seed, assoc(target, seed)).
 metric value = feature-CMI evaluations / s = F_global * n_targets * iters / (device time per step),
 timed with CUDA events on the launching stream, max over ranks.  Feature rows are sharded across
-ranks (strong scaling on the named matrix); the only exchange is one tiny all-gather per iteration.
+ranks (strong scaling on the named matrix); the only exchange is one candidate record per rank and
+iteration (peer-memory stores over NVLink by default, `--exchange nccl` for the all-gather).
+
+Extra keys of the JSON line: `e2e` = the same search through the reference-facing calls with HOST buffers
+(R's column-major doubles in pinned memory: upload + bit-packing + targets + seed + search + D2H of the
+scores, wall clock, max over ranks; `phases_ms_rank0_last_step` splits it), `e2e_gct` = the same fed from a
+GCT v1.2 text file through the device tokeniser (single rank), `roofline` (FP64 work executed / measured DFMA
+peak, plus the HBM view), `cpu_baseline` (restated oracle on the host threads, rank 0, N=1).  Every rank is
+bound to the cores NVML reports as local to its GPU before the pinned buffers are allocated.
 
 `--impl reference` times the reference's own CPU algorithm for the same path.  R, MASS and misc3d do
 not exist in this image, so it runs the restated C oracle in *reference mode* (three bcv() bandwidth
