@@ -130,6 +130,11 @@ int rvl_load_matrix_gct(rvl_ctx *ctx, rvl_gct *gct, const int32_t *cols, int64_t
  * m.2 <- m.2[retain, ] of the count filter (LIB:1655-1671), of the seed rows (LIB:1704-1706) and of the
  * excluded features (LIB:1716-1720) without re-uploading.  rvl_get_row_counts supplies rowSums(m.2). */
 int rvl_select_rows(rvl_ctx *ctx, const int64_t *rows, int64_t k);
+/* consolidate.identical.features = "identical" (LIB:1727-1748) on the device: the rows are ordered like their
+ * 0/1 strings (paste(m.2[k,], collapse=""), stable as R's order()), every group of identical rows keeps its
+ * first row, and the matrix becomes those rows in that order.  out_rows[i] = original local index of kept row i,
+ * out_counts[i] = size of its group (the " (count)" suffix the reference appends); both hold F entries. */
+int rvl_consolidate_identical(rvl_ctx *ctx, int64_t *out_rows, int32_t *out_counts, int64_t *out_k);
 /* Rows rows[0..k) as one byte per sample, out[k][n] (the seed rows m.2[seed.names, ], LIB:1693-1700). */
 int rvl_get_rows_u8(rvl_ctx *ctx, const int64_t *rows, int64_t k, uint8_t *out);
 

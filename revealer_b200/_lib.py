@@ -56,6 +56,7 @@ SIGNATURES = {
     "rvl_gct_row_values": (_i, [_vp, _i64, _dp]),
     "rvl_load_matrix_gct": (_i, [_vp, _vp, _i32p, _i64, _i64, _i64]),
     "rvl_select_rows": (_i, [_vp, _i64p, _i64]),
+    "rvl_consolidate_identical": (_i, [_vp, _i64p, _i32p, _i64p]),
     "rvl_get_rows_u8": (_i, [_vp, _i64p, _i64, _u8p]),
     "rvl_set_targets": (_i, [_vp, _dp, _i64, _i64]),
     "rvl_set_targets_permuted": (_i, [_vp, _dp, _i64, _i64]),

@@ -242,6 +242,18 @@ class RevealerContext:
         self._ck(self._lib.rvl_select_rows(self._h, rows.ctypes.data_as(C.POINTER(C.c_int64)), len(rows)))
         self.F = len(rows)
 
+    def consolidate_identical(self):
+        """consolidate.identical.features = "identical" (LIB:1727-1748): returns (rows, counts) -- the original
+        index and the group size of every kept row, in the reference's (pattern-sorted) order; the resident
+        matrix becomes those rows."""
+        rows = np.empty(max(self.F, 1), dtype=np.int64)
+        counts = np.empty(max(self.F, 1), dtype=np.int32)
+        k = C.c_int64()
+        self._ck(self._lib.rvl_consolidate_identical(self._h, rows.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                     counts.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(k)))
+        self.F = int(k.value)
+        return rows[:self.F].copy(), counts[:self.F].copy()
+
     def get_rows(self, rows):
         """Rows of the loaded matrix as uint8[k][n]."""
         rows = np.ascontiguousarray(rows, dtype=np.int64)
@@ -610,8 +622,25 @@ def read_gct(path):
     return dict(ds=np.asarray(data, dtype=np.float64), row_names=rows, descs=descs, names=names)
 
 
+def consolidate_identical_host(m2, rows2):
+    """consolidate.identical.features = "identical", LIB:1727-1748, as the reference does it (numpy): order the
+    rows by their pasted 0/1 strings (stable), keep the first row of every run of equal strings, append
+    " (count)" to its name.  Returns (m2, rows2) in the reference's new row order."""
+    m2 = np.asarray(m2)
+    keys = [np.asarray(r != 0, dtype=np.uint8).tobytes() for r in m2]      # b"\x00\x01.." sorts like "01.."
+    ind = sorted(range(len(keys)), key=lambda i: keys[i])                  # stable, like R's order()
+    kept, counts = [], []
+    for i in ind:
+        if kept and keys[kept[-1]] == keys[i]:
+            counts[-1] += 1
+        else:
+            kept.append(i)
+            counts.append(1)
+    return m2[kept], ["%s (%d)" % (rows2[i], c) for i, c in zip(kept, counts)]
+
+
 def prepare_inputs(ds1, target_name, target_match="positive", ds2=None, seed_names=None, exclude_features=None,
-                   count_thres_low=None, count_thres_high=None):
+                   count_thres_low=None, count_thres_high=None, consolidate_identical_features=False):
     """REVEALER.v1's preprocessing, LIB:1575-1720 (host side, numpy): drop NA-target samples, intersect the
     samples of ds1 and ds2, sort samples by target (decreasing unless target.match == "negative"), drop the
     target row from the features, count filter (seed rows always kept), seed = column-wise max of the seed
@@ -674,12 +703,18 @@ def prepare_inputs(ds1, target_name, target_match="positive", ds2=None, seed_nam
         ex = {rows2.index(s) for s in exclude_features if s in rows2}
         m2 = np.delete(m2, sorted(ex), axis=0)
         rows2 = [r for i, r in enumerate(rows2) if i not in ex]
+    if consolidate_identical_features == "identical":       # LIB:1727-1748
+        m2, rows2 = consolidate_identical_host(m2, rows2)
+    elif consolidate_identical_features:
+        raise RevealerError(_lib.RVL_ERR_ARG, 'consolidate.identical.features: only F or "identical" (the "similar" '
+                            'branch calls e1071::hamming.distance, which the reference never loads)')
     return dict(target=target, m2=m2, seed=seed, seed_vectors=seed_vectors, seed_list=seed_list, feature_names=rows2,
                 sample_names=sample_names, negative=negative)
 
 
 def prepare_inputs_device(ctx, ds1, target_name, target_match="positive", ds2=None, seed_names=None,
-                          exclude_features=None, count_thres_low=None, count_thres_high=None):
+                          exclude_features=None, count_thres_low=None, count_thres_high=None,
+                          consolidate_identical_features=False):
     """prepare_inputs with ds2 read by the GCT ingest (GctFile + rvl_load_matrix_gct): the feature matrix goes
     from the file to the bit-packed device matrix of `ctx` without an F x n host array.  The sample
     intersection and the sort-by-target permutation become the column map of the device tokeniser; the
@@ -756,21 +791,29 @@ def prepare_inputs_device(ctx, ds1, target_name, target_match="positive", ds2=No
                 alive[i] = False
     idx = np.flatnonzero(alive)
     ctx.select_rows(idx)
+    names = [rows2[i] for i in idx]
+    if consolidate_identical_features == "identical":       # LIB:1727-1748, on the device
+        kept, counts = ctx.consolidate_identical()
+        names = ["%s (%d)" % (names[i], c) for i, c in zip(kept, counts)]
+    elif consolidate_identical_features:
+        raise RevealerError(_lib.RVL_ERR_ARG, 'consolidate.identical.features: only F or "identical"')
     return dict(target=target, m2=None, seed=seed, seed_vectors=seed_vectors, seed_list=seed_list,
-                feature_names=[rows2[i] for i in idx], sample_names=sample_names, negative=negative)
+                feature_names=names, sample_names=sample_names, negative=negative)
 
 
 def REVEALER_v1(ds1, target_name, target_match="positive", ds2=None, seed_names=None, exclude_features=None,
                 max_n_iter=5, pdf_output_file=None, count_thres_low=None, count_thres_high=None, n_markers=30,
                 locs_table_file=None, n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75, n_perm=0,
-                r_seed=34578, device=0, ingest=None):
+                r_seed=34578, device=0, ingest=None, consolidate_identical_features=False):
     """REVEALER.v1 with its 12 formals (LIB:1504-1516) plus the optional grid/bandwidth arguments.
     ds1 / ds2: GCT path or dict(ds, row_names, names) as MSIG.Gct2Frame returns.  Preprocessing
     mirrors LIB:1575-1707: drop NA-target samples, intersect samples, sort by target, drop the target
     row from the features, count filter (seeds always kept), build the seed as the column-wise max of
     the seed rows and remove those rows.  No plots/PDF (pdf_output_file and locs_table_file are accepted
     and ignored).  ingest: "device" reads ds2 with the device GCT tokeniser (default when ds2 is a path),
-    "host" builds the F x n host matrix first (default for in-memory ds2).  n_perm > 0 adds the permutation null with numpy's PCG64(r_seed) (R's sample() stream is
+    "host" builds the F x n host matrix first (default for in-memory ds2).  consolidate_identical_features: the
+    reference's internal switch (LIB:1532, default F); "identical" runs LIB:1727-1748 (on the device with
+    ingest="device").  n_perm > 0 adds the permutation null with numpy's PCG64(r_seed) (R's sample() stream is
     not reproduced)."""
     ctx = None
     if ingest is None:
@@ -780,13 +823,13 @@ def REVEALER_v1(ds1, target_name, target_match="positive", ds2=None, seed_names=
                               negative=(target_match == "negative"))
         try:
             p = prepare_inputs_device(ctx, ds1, target_name, target_match, ds2, seed_names, exclude_features,
-                                      count_thres_low, count_thres_high)
+                                      count_thres_low, count_thres_high, consolidate_identical_features)
         except Exception:
             ctx.close()
             raise
     else:
         p = prepare_inputs(ds1, target_name, target_match, ds2, seed_names, exclude_features, count_thres_low,
-                           count_thres_high)
+                           count_thres_high, consolidate_identical_features)
     target, m2, seed, seed_vectors, seed_list = p["target"], p["m2"], p["seed"], p["seed_vectors"], p["seed_list"]
     rows2, sample_names, negative = p["feature_names"], p["sample_names"], p["negative"]
     target_rand = None

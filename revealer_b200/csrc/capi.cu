@@ -720,6 +720,85 @@ extern "C" int rvl_select_rows(rvl_ctx *ctx, const int64_t *rows, int64_t k)
     return build_dedup(ctx);
 }
 
+// Lexicographic order of bit rows as R orders the strings paste(m.2[k,], collapse = "") (LIB:1728-1729):
+// sample 0 decides first.  Sample s sits at bit s%64 of word s/64, so within a word the lowest differing
+// bit decides: compare the bit-reversed words as unsigned numbers.
+struct rvl_row_lex_less {
+    const uint64_t *bits;
+    int words;
+    __device__ bool operator()(int64_t a, int64_t b) const
+    {
+        const uint64_t *ra = bits + (size_t)a * words, *rb = bits + (size_t)b * words;
+        for (int w = 0; w < words; w++) {
+            const uint64_t x = ra[w], y = rb[w];
+            if (x != y) return __brevll(x) < __brevll(y);
+        }
+        return false;
+    }
+};
+struct rvl_row_differs { // position p of the sorted order starts a new group
+    const uint64_t *bits;
+    const int64_t *order;
+    int words;
+    __device__ bool operator()(int64_t p) const
+    {
+        if (p == 0) return true;
+        const uint64_t *ra = bits + (size_t)order[p] * words, *rb = bits + (size_t)order[p - 1] * words;
+        for (int w = 0; w < words; w++)
+            if (ra[w] != rb[w]) return true;
+        return false;
+    }
+};
+
+// consolidate.identical.features = "identical" (LIB:1727-1748) on the device: rows are put in the order of their
+// 0/1 strings (stable, so the first row of a group of identical rows is the one with the lowest index, as with
+// R's order()), every group keeps its first row, and the matrix becomes those rows in that order.
+// out_rows[i] = original (local) index of kept row i, out_counts[i] = size of its group -- the " (count)" suffix
+// the reference appends to the row name.  out arrays hold F entries; *out_k rows are kept.
+extern "C" int rvl_consolidate_identical(rvl_ctx *ctx, int64_t *out_rows, int32_t *out_counts, int64_t *out_k)
+{
+    GUARD();
+    if (ctx->F < 0) return fail(ctx, RVL_ERR_STATE, "feature matrix not loaded");
+    if (!out_rows || !out_counts || !out_k) return fail(ctx, RVL_ERR_ARG, "output is NULL");
+    const int64_t F = ctx->F;
+    *out_k = 0;
+    if (F == 0) return RVL_OK;
+    quiesce_side(ctx);
+    int64_t *d_order = nullptr, *d_heads = nullptr;
+    CK(dalloc(&d_order, (size_t)F));
+    CK(dalloc(&d_heads, (size_t)F + 1));
+    int64_t k = 0;
+    int rc = RVL_OK;
+    std::vector<int64_t> heads, order;
+    try {
+        rvl_pool_alloc alloc{ctx};
+        auto pol = thrust::cuda::par(alloc).on(ctx->stream);
+        thrust::device_ptr<int64_t> ord(d_order), hd(d_heads);
+        thrust::copy(pol, thrust::counting_iterator<int64_t>(0), thrust::counting_iterator<int64_t>(F), ord);
+        thrust::stable_sort(pol, ord, ord + F, rvl_row_lex_less{ctx->d_bits, ctx->words});
+        auto end = thrust::copy_if(pol, thrust::counting_iterator<int64_t>(0), thrust::counting_iterator<int64_t>(F), hd,
+                                   rvl_row_differs{ctx->d_bits, d_order, ctx->words});
+        k = end - hd;
+        ctx->launches += 4;
+        heads.resize((size_t)k + 1);
+        order.resize((size_t)F);
+        CK(cudaMemcpyAsync(heads.data(), d_heads, sizeof(int64_t) * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(order.data(), d_order, sizeof(int64_t) * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        rc = fail(ctx, RVL_ERR_CUDA, "identical-row consolidation failed on the device");
+    }
+    cudaFree(d_order); cudaFree(d_heads);
+    if (rc) return rc;
+    heads[(size_t)k] = F;
+    for (int64_t i = 0; i < k; i++) {
+        out_rows[i] = order[(size_t)heads[(size_t)i]];
+        out_counts[i] = (int32_t)(heads[(size_t)i + 1] - heads[(size_t)i]);
+    }
+    *out_k = k;
+    return rvl_select_rows(ctx, out_rows, k);
+}
+
 // Rows `rows[0..k)` of the loaded matrix as one byte per sample, out[k][n] (the seed rows m.2[seed.names, ],
 // LIB:1693-1700).
 extern "C" int rvl_get_rows_u8(rvl_ctx *ctx, const int64_t *rows, int64_t k, uint8_t *out)

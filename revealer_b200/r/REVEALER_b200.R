@@ -36,12 +36,13 @@ REVEALER.v1.b200 <- function(
    max.n.iter = 5, pdf.output.file = NULL, count.thres.low = NULL, count.thres.high = NULL,
    n.markers = 30, locs.table.file = NULL,
    n.grid = 25, bandwidth.mult = 0.25, bandwidth.shrink = -0.75, n.perm = 10, r.seed = 34578, device = 0,
-   gct.ingest = TRUE)
+   gct.ingest = TRUE, consolidate.identical.features = FALSE)   # the reference's internal switch, LIB:1532
 {
    set.seed(r.seed)                                        # LIB:1557
    if (gct.ingest) return(REVEALER.v1.b200.gct(ds1, target.name, target.match, ds2, seed.names, exclude.features,
                                                max.n.iter, count.thres.low, count.thres.high, n.markers, n.grid,
-                                               bandwidth.mult, bandwidth.shrink, n.perm, device))
+                                               bandwidth.mult, bandwidth.shrink, n.perm, device,
+                                               consolidate.identical.features))
    read.gct <- function(f) {                               # same on-disk format as MSIG.Gct2Frame
       d <- read.delim(f, header = TRUE, sep = "\t", skip = 2, row.names = 1, blank.lines.skip = TRUE,
                       comment.char = "", as.is = TRUE, na.strings = "")
@@ -97,7 +98,7 @@ REVEALER.v1.b200 <- function(
 # (MSIG.Gct2Frame + data.matrix, LIB:2616-2626 / 1582).  R keeps only names, row counts and the seed rows.
 REVEALER.v1.b200.gct <- function(ds1, target.name, target.match, ds2, seed.names, exclude.features, max.n.iter,
                                  count.thres.low, count.thres.high, n.markers, n.grid, bandwidth.mult,
-                                 bandwidth.shrink, n.perm, device)
+                                 bandwidth.shrink, n.perm, device, consolidate.identical.features = FALSE)
 {
    ctx <- .Call("rvlR_create", as.integer(device))
    g1 <- .Call("rvlR_gct_open", ds1); i1 <- .Call("rvlR_gct_info", g1)
@@ -132,6 +133,11 @@ REVEALER.v1.b200.gct <- function(ds1, target.name, target.match, ds2, seed.names
    if (!is.null(exclude.features)) alive <- alive & !(rows %in% exclude.features)   # LIB:1716-1720
    idx <- which(alive)
    .Call("rvlR_select_rows", ctx, as.integer(idx))
+   feature.names <- rows[idx]
+   if (identical(consolidate.identical.features, "identical")) {             # LIB:1727-1748, on the device
+      g <- .Call("rvlR_consolidate_identical", ctx)
+      feature.names <- paste(feature.names[g$rows], " (", g$counts, ")", sep = "")
+   }
    target.rand <- NULL
    if (n.perm > 0) {
       target.rand <- matrix(target, nrow = n.perm, ncol = length(target), byrow = TRUE)
@@ -139,12 +145,11 @@ REVEALER.v1.b200.gct <- function(ds1, target.name, target.match, ds2, seed.names
    }
    res <- revealer.b200.search(as.double(target), NULL, seed, max.n.iter, target.match, target.rand, n.grid,
                                bandwidth.mult, bandwidth.shrink, device, ctx = ctx)
-   feature.names <- rows[idx]
    res$feature.names <- feature.names
    res$seed.names.iter <- feature.names[res$top]
    res$target <- target
    res$cmi.names <- apply(res$cmi, 2, function(v)
-      feature.names[order(v, decreasing = !identical(target.match, "negative"))][1:min(n.markers, length(idx))])
+      feature.names[order(v, decreasing = !identical(target.match, "negative"))][1:min(n.markers, length(feature.names))])
    if (n.perm > 0) {
       res$p.val <- sapply(1:max.n.iter, function(it)
          .Call("rvlR_pvalues", res$ctx, res$cmi[, it], as.double(res$cmi.rand[, , it])))

@@ -429,3 +429,30 @@ SEXP rvlR_select_rows(SEXP sctx, SEXP srows)
     if (rvl_select_rows(ctx, rows, (int64_t)k)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
     return R_NilValue;
 }
+
+/* .Call("rvlR_consolidate_identical", ctx) -> list(rows = int[k] (1-based rows of the resident matrix before the
+ * call), counts = int[k]): consolidate.identical.features = "identical" (LIB:1727-1748) on the device. */
+SEXP rvlR_consolidate_identical(SEXP sctx)
+{
+    rvl_ctx *ctx = get_ctx(sctx);
+    int64_t F = 0, n = 0, k = 0;
+    if (rvl_get_matrix_dims(ctx, &F, &n)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    int64_t *rows = (int64_t *)R_alloc((size_t)F + 1, sizeof(int64_t));
+    int32_t *counts = (int32_t *)R_alloc((size_t)F + 1, sizeof(int32_t));
+    if (rvl_consolidate_identical(ctx, rows, counts, &k)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP names = PROTECT(Rf_allocVector(STRSXP, 2));
+    SET_STRING_ELT(names, 0, Rf_mkChar("rows"));
+    SET_STRING_ELT(names, 1, Rf_mkChar("counts"));
+    Rf_setAttrib(out, R_NamesSymbol, names);
+    SEXP r = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)k));
+    SEXP c = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)k));
+    for (int64_t i = 0; i < k; i++) {
+        INTEGER(r)[i] = (int)rows[i] + 1;
+        INTEGER(c)[i] = (int)counts[i];
+    }
+    SET_VECTOR_ELT(out, 0, r);
+    SET_VECTOR_ELT(out, 1, c);
+    UNPROTECT(4);
+    return out;
+}

@@ -134,3 +134,37 @@ def test_revealer_v1_device_ingest_equals_host_ingest(tmp_path):
     assert list(a["top"]) == list(b["top"]) and np.array_equal(a["seed_iter"], b["seed_iter"])
     assert np.array_equal(a["cmi"], b["cmi"], equal_nan=True)          # same kernels on the same bits: identical
     assert a["cmi_orig_seed"] == b["cmi_orig_seed"]
+
+
+def test_identical_consolidation_matches_the_reference_procedure():
+    """consolidate.identical.features = "identical" (LIB:1727-1748) on the device against the reference's own
+    procedure restated in numpy (paste -> stable order -> first of each run, counts in the names)."""
+    from revealer_b200.api import consolidate_identical_host
+    rng = np.random.default_rng(12)
+    for F, n in [(1, 5), (50, 3), (400, 70), (3000, 130)]:
+        base = (rng.random((max(1, F // 3), n)) < 0.15).astype(np.uint8)
+        m = base[rng.integers(0, len(base), F)]                    # many exact duplicates, scattered
+        names = ["r%d" % i for i in range(F)]
+        want_m, want_names = consolidate_identical_host(m, names)
+        with rb.RevealerContext(0) as ctx:
+            ctx.load_matrix(m)
+            kept, counts = ctx.consolidate_identical()
+            got = matrix_of(ctx)
+            assert ctx.unique_rows() == ctx.F == len(kept)
+        assert ["%s (%d)" % (names[i], c) for i, c in zip(kept, counts)] == want_names
+        assert np.array_equal(got, want_m)
+        assert counts.sum() == F
+
+
+def test_revealer_v1_with_identical_consolidation_device_equals_host(tmp_path):
+    from revealer_b200 import synth
+    w = synth.make_workload(n=90, F=700)
+    names2 = ["P%03d" % i for i in range(90)]
+    f1, f2 = str(tmp_path / "ds1.gct"), str(tmp_path / "ds2.gct")
+    write_gct(f1, ["TGT"], ["y"], names2, [w["target"].tolist()])
+    fast_gct(f2, w["m2"].astype(np.uint8), names=names2, row_prefix="feat")
+    kw = dict(max_n_iter=2, consolidate_identical_features="identical", count_thres_low=3, count_thres_high=40)
+    a = rb.REVEALER_v1(f1, "TGT", "positive", f2, ingest="host", **kw)
+    b = rb.REVEALER_v1(f1, "TGT", "positive", f2, ingest="device", **kw)
+    assert a["feature_names"] == b["feature_names"] and any("(2)" in s or "(3)" in s for s in a["feature_names"])
+    assert list(a["top"]) == list(b["top"]) and np.array_equal(a["cmi"], b["cmi"], equal_nan=True)
