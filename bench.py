@@ -325,10 +325,15 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        h2d = cnt * n * 8 + targets.nbytes + seed_h.nbytes
+        pcie_bytes, host_words = ctx.upload_stats()      # of the last load: what actually crossed PCIe
+        host_in = cnt * n * 8 + targets.nbytes + seed_h.nbytes
+        h2d = pcie_bytes + targets.nbytes + seed_h.nbytes
         d2h = sum(v.nbytes for v in res.values() if v is not None)
         e2e = {"value": F * T * iters / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
+               "host_input_bytes_per_step": int(host_in),
+               "upload": "cooperative: %d of %d 64-sample words packed by host threads, the rest sent as doubles and "
+                         "packed on the device (rank 0, last step)" % (host_words, (n + 63) // 64),
                "phases_ms_rank0_last_step": {k: round(v, 3) for k, v in phases.items()},
                "call": "rvl_load_matrix_f64_colmajor + rvl_set_targets + rvl_set_seed + search + rvl_search_fetch"}
 

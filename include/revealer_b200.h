@@ -90,8 +90,17 @@ int rvl_set_shard(rvl_ctx *ctx, int rank, int world, int64_t row_offset, int64_t
 /* ---- inputs (replace the R objects m.2 / target / seed handed to the loop at LIB:1849) --- */
 
 /* m.2 as R holds it: F x n doubles, column-major (m2[k + ld*s]); every entry must be 0 or 1.
- * Bit-packed on the device into uint64[F][words], sample s -> bit s%64 of word s/64. */
+ * Becomes uint64[F][words] on the device, sample s -> bit s%64 of word s/64.  PCIe is the bottleneck of this
+ * call (8 bytes per bit kept), so the upload is cooperative: the DMA engine ships 64-sample words as doubles
+ * from the front (packed by k_pack_f64_colmajor) while host threads pack words from the back (1/64 of the
+ * bytes to send); the two sides meet wherever their speeds put them.  Same bits, same 0/1 validation. */
 int rvl_load_matrix_f64_colmajor(rvl_ctx *ctx, const double *m2, int64_t F, int64_t n, int64_t ld);
+/* Packer threads of the cooperative upload: n < 0 automatic (cores available to the process / world, at most
+ * 16; none for small matrices), 0 = off (DMA + device packing only), n > 0 = that many. */
+int rvl_set_host_threads(rvl_ctx *ctx, int n);
+/* Of the last rvl_load_matrix_f64_colmajor: bytes that actually crossed PCIe (doubles of the DMA-side words + the
+ * packed words of the host side) and how many 64-sample words the host threads packed. */
+int rvl_get_upload_stats(rvl_ctx *ctx, uint64_t *out_h2d_bytes, uint64_t *out_host_packed_words);
 /* Same matrix as one byte per entry, row-major (m2[k*n + s]). */
 int rvl_load_matrix_u8_rowmajor(rvl_ctx *ctx, const uint8_t *m2, int64_t F, int64_t n);
 /* Already bit-packed rows, `words` uint64 per row (words >= ceil(n/64)); padding bits must be 0. */

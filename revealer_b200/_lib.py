@@ -42,6 +42,8 @@ SIGNATURES = {
     "rvl_default_options": (_i, [C.POINTER(rvl_opts)]),
     "rvl_set_shard": (_i, [_vp, _i, _i, _i64, _i64]),
     "rvl_load_matrix_f64_colmajor": (_i, [_vp, _dp, _i64, _i64, _i64]),
+    "rvl_set_host_threads": (_i, [_vp, _i]),
+    "rvl_get_upload_stats": (_i, [_vp, _u64p, _u64p]),
     "rvl_load_matrix_u8_rowmajor": (_i, [_vp, _u8p, _i64, _i64]),
     "rvl_load_matrix_bits": (_i, [_vp, _u64p, _i64, _i64, _i64]),
     "rvl_load_matrix_bits_device": (_i, [_vp, _vp, _i64, _i64, _i64]),

@@ -208,6 +208,16 @@ class RevealerContext:
         self._ck(self._lib.rvl_set_shard(self._h, rank, world, row_offset, F_global))
         self.rank, self.world, self.row_offset = rank, world, row_offset
 
+    def set_host_threads(self, n):
+        """Packer threads of the cooperative upload of float64 matrices (-1 automatic, 0 off)."""
+        self._ck(self._lib.rvl_set_host_threads(self._h, int(n)))
+
+    def upload_stats(self):
+        """(bytes that crossed PCIe, 64-sample words packed by host threads) of the last float64 load_matrix."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.rvl_get_upload_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     # -- inputs
     def load_matrix(self, m2):
         """m2: F x n.  float64 -> the R layout path (column-major doubles, validated and packed on the

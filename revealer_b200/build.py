@@ -14,6 +14,7 @@ UNITS = [
     ("bandwidth.cu", ["-fmad=false"]),
     ("score.cu", []),
     ("gct.cu", []),
+    ("hostpack.cpp", ["-Xcompiler", "-O3"]),   # plain host C++ (g++ through nvcc): packer threads of the cooperative upload
     ("capi.cu", []),
 ]
 DEPS = ["rvl_common.cuh", os.path.join("..", "..", "include", "revealer_b200.h")]
@@ -43,7 +44,7 @@ def build(force=False, verbose=False):
     rebuilt = False
     for src, extra in UNITS:
         s = os.path.join(CSRC, src)
-        o = os.path.join(CSRC, src.replace(".cu", ".o"))
+        o = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         if force or _stale(o, [s] + deps):
             cmd = [nvcc] + ccbin + ARCH + COMMON + extra + ["-Xptxas", "-v", "-c", s, "-o", o]
             r = subprocess.run(cmd, env=env, capture_output=True, text=True)

@@ -11,7 +11,10 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <sched.h>
 
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
@@ -30,6 +33,11 @@
 // launchers (score.cu, bandwidth.cu)
 extern "C" {
 cudaError_t rvl_upload_log_table(void);
+// hostpack.cpp
+void *rvl_hostpack_begin(const double *m2, int64_t F, int64_t n, int64_t ld, uint64_t *packed, int nthreads);
+int64_t rvl_hostpack_claim_front(void *h);
+int rvl_hostpack_end(void *h, int64_t *first_host_word);
+void rvl_launch_scatter_words(const uint64_t *packed, int64_t F, int w0, int w1, int words, uint64_t *bits, cudaStream_t st);
 // gct.cu
 int64_t rvl_gct_row_names_impl(rvl_gct *g, int field, char *buf, size_t cap);
 int rvl_gct_open_impl(const char *path, rvl_gct **out, char *errbuf, size_t errcap);
@@ -111,6 +119,11 @@ struct rvl_ctx {
     struct pool_block { char *p; size_t bytes; bool used; };
     std::vector<pool_block> pool;
     void *gct_scratch = nullptr; // staging of the GCT ingest (gct.cu), kept across loads
+    // cooperative upload of R doubles: host packer threads (hostpack.cpp) + their pinned / device word buffers
+    int host_threads = -1;       // -1: automatic, 0: off (DMA + device packing only)
+    uint64_t *h_packed = nullptr, *d_packed = nullptr;
+    size_t packed_cap = 0;
+    uint64_t last_h2d_bytes = 0, last_host_packed_words = 0; // of the last rvl_load_matrix_f64_colmajor
     // exact-duplicate rows: rep[f] = first identical row; uniq = rows with rep[f] == f
     int64_t *d_rep = nullptr, *d_uniq = nullptr;
     int64_t U = 0;
@@ -301,6 +314,10 @@ static void free_matrix(rvl_ctx *c, bool release = false)
     c->pool.clear();
     if (c->gct_scratch) rvl_gct_scratch_free(c->gct_scratch);
     c->gct_scratch = nullptr;
+    if (c->h_packed) cudaFreeHost(c->h_packed);
+    c->h_packed = nullptr;
+    dfree(c->d_packed);
+    c->packed_cap = 0;
 }
 static void free_targets(rvl_ctx *c)
 {
@@ -368,6 +385,22 @@ extern "C" int rvl_set_options(rvl_ctx *ctx, const rvl_opts *o)
     if (ctx->T > 0 && o->n_grid != ctx->G_targets)
         return fail(ctx, RVL_ERR_STATE, "n_grid must be set before rvl_set_targets");
     ctx->opts = *o;
+    return RVL_OK;
+}
+
+extern "C" int rvl_get_upload_stats(rvl_ctx *ctx, uint64_t *out_h2d_bytes, uint64_t *out_host_packed_words)
+{
+    GUARD();
+    if (out_h2d_bytes) *out_h2d_bytes = ctx->last_h2d_bytes;
+    if (out_host_packed_words) *out_host_packed_words = ctx->last_host_packed_words;
+    return RVL_OK;
+}
+
+extern "C" int rvl_set_host_threads(rvl_ctx *ctx, int n)
+{
+    GUARD();
+    if (n > 256) return fail(ctx, RVL_ERR_ARG, "host threads must be <= 256 (negative: automatic, 0: off)");
+    ctx->host_threads = n < 0 ? -1 : n;
     return RVL_OK;
 }
 
@@ -543,28 +576,92 @@ extern "C" int rvl_load_matrix_f64_colmajor(rvl_ctx *ctx, const double *m2, int6
     CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     ctx->F = F;
     if (F == 0) return RVL_OK;
-    // column chunks of a multiple of 64 samples (whole bit words), ~64 MB each, through two staging
-    // halves: the copy stream fills one while the main stream packs the other, so the DMA engine
-    // never waits for a pack kernel and only the last chunk's pack is exposed
+    // Packer threads: PCIe carries 8 bytes for every bit the device keeps, so while the DMA engine ships the
+    // leading 64-sample words as doubles, host threads turn the trailing ones into bits (hostpack.cpp: the
+    // same packing and 0/1 validation as k_pack_f64_colmajor, 1/64 of the bytes to send).  The two sides
+    // claim words from opposite ends until they meet, so the split follows their actual speeds -- with
+    // pageable (unpinned) R memory the packers end up doing most of it.
+    const int64_t W = (n + 63) / 64;
+    int nthreads = ctx->host_threads;
+    if (nthreads < 0) {
+        int avail = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) avail = CPU_COUNT(&set);
+        nthreads = avail / (ctx->world > 0 ? ctx->world : 1);
+        if (nthreads > 16) nthreads = 16;
+        if ((double)F * (double)n < 4e6 || W < 2) nthreads = 0; // small matrices: not worth starting threads
+    }
+    void *plan = nullptr;
+    if (nthreads > 0) {
+        const size_t need = (size_t)W * (size_t)F;
+        if (need > ctx->packed_cap) {
+            if (ctx->h_packed) cudaFreeHost(ctx->h_packed);
+            ctx->h_packed = nullptr;
+            dfree(ctx->d_packed);
+            ctx->packed_cap = 0;
+            CK(cudaMallocHost((void **)&ctx->h_packed, sizeof(uint64_t) * need));
+            CK(dalloc(&ctx->d_packed, need));
+            ctx->packed_cap = need;
+        }
+        plan = rvl_hostpack_begin(m2, F, n, ld, ctx->h_packed, nthreads);
+    }
+    // the DMA side: column chunks of whole bit words (~64 MB each; exactly one word when packers run, so that the
+    // two sides meet on a word boundary) through two staging halves -- the copy stream fills one while the main
+    // stream packs the other, so the DMA engine never waits for a pack kernel
     int64_t cols = (64ll << 20) / (8 * ld);
     cols = (cols / 64) * 64;
-    if (cols < 64) cols = 64;
+    if (cols < 64 || plan) cols = 64;
     int64_t stage_cols = cols < n ? cols : n;
     rc = reserve_stage(ctx, sizeof(double) * (size_t)ld * stage_cols);
-    if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev_packed[0], ctx->stream)); // staging halves are free once earlier work is done
-    CK(cudaEventRecord(ctx->ev_packed[1], ctx->stream));
+    cudaError_t ce = cudaSuccess;
+    if (!rc) ce = cudaEventRecord(ctx->ev_packed[0], ctx->stream); // staging halves are free once earlier work is done
+    if (!rc && ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_packed[1], ctx->stream);
     int half = 0;
-    for (int64_t s0 = 0; s0 < n; s0 += cols, half ^= 1) {
-        int64_t nc = (n - s0 < cols) ? (n - s0) : cols;
+    int64_t s0 = 0;
+    ctx->last_h2d_bytes = 0;
+    ctx->last_host_packed_words = 0;
+    while (!rc && ce == cudaSuccess) {
+        if (plan) {
+            const int64_t w = rvl_hostpack_claim_front(plan);
+            if (w < 0) break;
+            s0 = w * 64;
+        } else if (s0 >= n) break;
+        const int64_t nc = (n - s0 < cols) ? (n - s0) : cols;
         double *stage = reinterpret_cast<double *>(ctx->d_stage[half]);
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[half], 0));
-        CK(cudaMemcpyAsync(stage, m2 + ld * s0, sizeof(double) * (size_t)ld * nc, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CK(cudaEventRecord(ctx->ev_copied[half], ctx->copy_stream));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[half], 0));
+        ce = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[half], 0);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(stage, m2 + ld * s0, sizeof(double) * (size_t)ld * nc, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_copied[half], ctx->copy_stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[half], 0);
+        if (ce != cudaSuccess) break;
+        ctx->last_h2d_bytes += sizeof(double) * (uint64_t)ld * (uint64_t)nc;
         rvl_launch_pack_f64_colmajor(stage, F, ld, (int)s0, (int)nc, ctx->words, ctx->d_bits, ctx->d_flag, ctx->stream);
-        CK(cudaEventRecord(ctx->ev_packed[half], ctx->stream));
+        ce = cudaEventRecord(ctx->ev_packed[half], ctx->stream);
         ctx->launches++;
+        half ^= 1;
+        if (!plan) s0 += cols;
+        else if (ce == cudaSuccess) ce = cudaEventSynchronize(ctx->ev_copied[half ^ 1]); // claim the next word only when this copy is done
+    }
+    int host_bad = 0;
+    if (plan) { // always join the packers, also on an error above
+        int64_t first = W;
+        host_bad = rvl_hostpack_end(plan, &first);
+        if (!rc && ce == cudaSuccess && first < W) {
+            ce = cudaMemcpyAsync(ctx->d_packed, ctx->h_packed + (size_t)first * F, sizeof(uint64_t) * (size_t)(W - first) * F,
+                                 cudaMemcpyHostToDevice, ctx->stream);
+            if (ce == cudaSuccess) {
+                rvl_launch_scatter_words(ctx->d_packed, F, (int)first, (int)W, ctx->words, ctx->d_bits, ctx->stream);
+                ctx->launches++;
+                ctx->last_h2d_bytes += sizeof(uint64_t) * (uint64_t)(W - first) * (uint64_t)F;
+                ctx->last_host_packed_words = (uint64_t)(W - first);
+            }
+        }
+    }
+    if (rc) { free_matrix(ctx); return rc; }
+    if (ce != cudaSuccess) { free_matrix(ctx); return fail(ctx, RVL_ERR_CUDA, "upload: %s", cudaGetErrorString(ce)); }
+    if (host_bad) {
+        cudaStreamSynchronize(ctx->stream);
+        free_matrix(ctx);
+        return fail(ctx, RVL_ERR_NOT_BINARY, "feature matrix has an entry that is not 0 or 1 (binary features only; no fallback)");
     }
     rc = check_flag(ctx, "feature matrix has an entry that is not 0 or 1 (binary features only; no fallback)");
     if (rc) { free_matrix(ctx); return rc; }

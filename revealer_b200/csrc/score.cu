@@ -1192,6 +1192,16 @@ __global__ void k_pack_f64_colmajor(const double *__restrict__ chunk, int64_t F,
     if (bad) atomicOr(flag, 1);
 }
 
+// Words packed on the host (hostpack.cpp): packed[(w - w0) * F + k] -> bits[k][w] for w in [w0, w1).
+__global__ void k_scatter_words(const uint64_t *__restrict__ packed, int64_t F, int w0, int w1, int words,
+                                uint64_t *__restrict__ bits)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = w0 + blockIdx.y;
+    if (k >= F || w >= w1) return;
+    bits[(size_t)k * words + w] = packed[(size_t)(w - w0) * F + k];
+}
+
 // Row-major bytes -> bit rows.  One warp per (row, 32 words) tile; lane = word.
 __global__ void k_pack_u8_rowmajor(const uint8_t *__restrict__ m, int64_t F, int n, int words,
                                    uint64_t *__restrict__ bits, int *__restrict__ flag)
@@ -1453,6 +1463,14 @@ extern "C" void rvl_launch_unpack_rows(const uint64_t *src, const int64_t *rows,
     int blocks = (int)((tot + 255) / 256 < 148 * 16 ? (tot + 255) / 256 : 148 * 16);
     if (blocks < 1) blocks = 1;
     k_unpack_rows<<<blocks, 256, 0, st>>>(src, rows, k, n, words, dst);
+}
+
+extern "C" void rvl_launch_scatter_words(const uint64_t *packed, int64_t F, int w0, int w1, int words, uint64_t *bits,
+                                         cudaStream_t st)
+{
+    if (w1 <= w0 || F <= 0) return;
+    dim3 grid((unsigned)((F + 255) / 256), (unsigned)(w1 - w0));
+    k_scatter_words<<<grid, 256, 0, st>>>(packed, F, w0, w1, words, bits);
 }
 
 extern "C" void rvl_launch_check_padding(const uint64_t *bits, int64_t F, int n, int words, int *flag,

@@ -168,3 +168,32 @@ def test_revealer_v1_with_identical_consolidation_device_equals_host(tmp_path):
     b = rb.REVEALER_v1(f1, "TGT", "positive", f2, ingest="device", **kw)
     assert a["feature_names"] == b["feature_names"] and any("(2)" in s or "(3)" in s for s in a["feature_names"])
     assert list(a["top"]) == list(b["top"]) and np.array_equal(a["cmi"], b["cmi"], equal_nan=True)
+
+
+@pytest.mark.parametrize("F,n,threads", [(3000, 130, 1), (5000, 1000, 3), (20000, 257, 8)])
+def test_cooperative_upload_equals_device_only_upload(F, n, threads):
+    """rvl_load_matrix_f64_colmajor with host packer threads (words claimed from the back while the DMA engine
+    ships words from the front) leaves exactly the bits the device-only path leaves, and rejects the same input."""
+    rng = np.random.default_rng(F + n)
+    m = np.asfortranarray((rng.random((F, n)) < 0.07).astype(np.float64))
+    with rb.RevealerContext(0) as ctx:
+        ctx.set_host_threads(0)
+        ctx.load_matrix(m)
+        want = matrix_of(ctx)
+        assert np.array_equal(want, m.astype(np.uint8))
+        ctx.set_host_threads(threads)
+        for _ in range(3):                                   # the meeting point of the two sides varies run to run
+            ctx.load_matrix(m)
+            assert np.array_equal(matrix_of(ctx), want)
+        for s in (0, n // 2, n - 1):                         # a bad entry in a DMA-side word, in the middle, in a packer-side word
+            bad = m.copy(order="F")
+            bad[F // 3, s] = 0.5
+            with pytest.raises(rb.RevealerError) as e:
+                ctx.load_matrix(bad)
+            assert e.value.code == _lib.RVL_ERR_NOT_BINARY
+        bad = m.copy(order="F")
+        bad[5, n - 1] = np.nan
+        with pytest.raises(rb.RevealerError):
+            ctx.load_matrix(bad)
+        ctx.load_matrix(m)                                   # and the context is still usable
+        assert np.array_equal(ctx.row_counts(), want.sum(axis=1))
