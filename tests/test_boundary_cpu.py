@@ -203,3 +203,41 @@ def test_synthetic_workload_is_deterministic_and_shardable():
     assert 0.1 < dup < 0.3
     cnt = a["m2"].sum(axis=1)
     assert (cnt == 0).any() and (cnt == 120).any()
+
+
+def test_host_packer_threads_produce_the_device_bit_layout(built_lib):
+    """hostpack.cpp (the host side of the cooperative upload) needs no GPU: with no DMA side claiming words the
+    packer threads take every 64-sample word, and what they leave must be the bit layout pack_bits() defines
+    (sample s -> bit s % 64 of word s / 64); entries that are not 0/1 must be reported."""
+    from revealer_b200.api import pack_bits
+    lib = ctypes.CDLL(built_lib)
+    lib.rvl_hostpack_begin.restype = ctypes.c_void_p
+    lib.rvl_hostpack_begin.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]
+    lib.rvl_hostpack_claim_front.restype = ctypes.c_int64
+    lib.rvl_hostpack_claim_front.argtypes = [ctypes.c_void_p]
+    lib.rvl_hostpack_end.restype = ctypes.c_int
+    lib.rvl_hostpack_end.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+    rng = np.random.default_rng(21)
+    for F, n, ld_extra, threads in [(1, 2, 0, 1), (37, 64, 0, 2), (5000, 130, 3, 4), (9000, 257, 0, 3)]:
+        ld = F + ld_extra
+        m = np.zeros((n, ld), dtype=np.float64)                  # C-order n x ld == column-major ld x n
+        m[:, :F] = (rng.random((n, F)) < 0.2)
+        W = (n + 63) // 64
+        packed = np.zeros((W, F), dtype=np.uint64)
+        h = lib.rvl_hostpack_begin(m.ctypes.data, F, n, ld, packed.ctypes.data, threads)
+        first = ctypes.c_int64(-1)
+        bad = lib.rvl_hostpack_end(h, ctypes.byref(first))
+        assert bad == 0 and first.value == 0                     # nobody claimed from the front: the packers did all words
+        want, words = pack_bits(m[:, :F].T)
+        assert np.array_equal(packed.T, want[:, :W])
+        # the DMA side takes the first words: the packers must stop where it stands
+        h = lib.rvl_hostpack_begin(m.ctypes.data, F, n, ld, packed.ctypes.data, 0)   # no threads: only claims
+        got = [lib.rvl_hostpack_claim_front(h) for _ in range(W + 1)]
+        assert got == list(range(W)) + [-1]
+        assert lib.rvl_hostpack_end(h, ctypes.byref(first)) == 0 and first.value == W
+        m[n - 1, F // 2] = 2.0
+        h = lib.rvl_hostpack_begin(m.ctypes.data, F, n, ld, packed.ctypes.data, threads)
+        assert lib.rvl_hostpack_end(h, ctypes.byref(first)) != 0
+        m[n - 1, F // 2] = np.nan
+        h = lib.rvl_hostpack_begin(m.ctypes.data, F, n, ld, packed.ctypes.data, threads)
+        assert lib.rvl_hostpack_end(h, ctypes.byref(first)) != 0
