@@ -79,7 +79,10 @@ void *rvl_hostpack_begin(const double *m2, int64_t F, int64_t n, int64_t ld, uin
     p->tiles_per_word = (F + p->tile_rows - 1) / p->tile_rows;
     p->back = p->W;
     p->cur_tile = p->tiles_per_word;
-    for (int i = 0; i < nthreads; i++) p->threads.emplace_back(worker, p);
+    try { // fewer threads than asked for (or none) is fine: the DMA side takes whatever the packers do not claim
+        for (int i = 0; i < nthreads; i++) p->threads.emplace_back(worker, p);
+    } catch (...) {
+    }
     return p;
 }
 
