@@ -742,11 +742,17 @@ extern "C" int rvl_load_matrix_bits_device(rvl_ctx *ctx, const void *dev_bits, i
 
 static thread_local std::string g_gct_err;
 
+// (the host side of the GCT handle allocates strings and vectors: nothing may be thrown across the ABI)
 extern "C" int rvl_gct_open(const char *path, rvl_gct **out)
 {
     char buf[512] = {0};
-    int rc = rvl_gct_open_impl(path, out, buf, sizeof buf);
-    g_gct_err = buf;
+    int rc = -2;
+    try {
+        rc = rvl_gct_open_impl(path, out, buf, sizeof buf);
+        g_gct_err = buf;
+    } catch (...) {
+        if (out) *out = nullptr;
+    }
     return rc ? RVL_ERR_ARG : RVL_OK;
 }
 extern "C" void rvl_gct_close(rvl_gct *g) { rvl_gct_close_impl(g); }
@@ -757,10 +763,22 @@ extern "C" const char *rvl_gct_last_error(const rvl_gct *g)
 }
 extern "C" int rvl_gct_dims(const rvl_gct *g, int64_t *nrow, int64_t *ncol) { return rvl_gct_dims_impl(g, nrow, ncol) ? RVL_ERR_ARG : RVL_OK; }
 extern "C" int rvl_gct_sample_name(const rvl_gct *g, int64_t j, char *buf, size_t cap) { return rvl_gct_sample_name_impl(g, j, buf, cap); }
-extern "C" int rvl_gct_row_name(rvl_gct *g, int64_t i, char *buf, size_t cap) { return rvl_gct_row_field_impl(g, i, 0, buf, cap); }
-extern "C" int rvl_gct_row_description(rvl_gct *g, int64_t i, char *buf, size_t cap) { return rvl_gct_row_field_impl(g, i, 1, buf, cap); }
-extern "C" int64_t rvl_gct_row_names(rvl_gct *g, int field, char *buf, size_t cap) { return rvl_gct_row_names_impl(g, field, buf, cap); }
-extern "C" int rvl_gct_row_values(rvl_gct *g, int64_t i, double *out) { return rvl_gct_row_values_impl(g, i, out) ? RVL_ERR_ARG : RVL_OK; }
+extern "C" int rvl_gct_row_name(rvl_gct *g, int64_t i, char *buf, size_t cap)
+{
+    try { return rvl_gct_row_field_impl(g, i, 0, buf, cap); } catch (...) { return RVL_ERR_ARG; }
+}
+extern "C" int rvl_gct_row_description(rvl_gct *g, int64_t i, char *buf, size_t cap)
+{
+    try { return rvl_gct_row_field_impl(g, i, 1, buf, cap); } catch (...) { return RVL_ERR_ARG; }
+}
+extern "C" int64_t rvl_gct_row_names(rvl_gct *g, int field, char *buf, size_t cap)
+{
+    try { return rvl_gct_row_names_impl(g, field, buf, cap); } catch (...) { return RVL_ERR_ARG; }
+}
+extern "C" int rvl_gct_row_values(rvl_gct *g, int64_t i, double *out)
+{
+    try { return rvl_gct_row_values_impl(g, i, out) ? RVL_ERR_ARG : RVL_OK; } catch (...) { return RVL_ERR_ARG; }
+}
 
 extern "C" int rvl_load_matrix_gct(rvl_ctx *ctx, rvl_gct *g, const int32_t *cols, int64_t n, int64_t first_row, int64_t n_rows)
 {
