@@ -241,3 +241,26 @@ def test_host_packer_threads_produce_the_device_bit_layout(built_lib):
         m[n - 1, F // 2] = np.nan
         h = lib.rvl_hostpack_begin(m.ctypes.data, F, n, ld, packed.ctypes.data, threads)
         assert lib.rvl_hostpack_end(h, ctypes.byref(first)) != 0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the same metric /
+    unit / config keys, impl = reference, a cpu_baseline describing the run and an e2e with zero transfer bytes;
+    under torchrun only rank 0 prints."""
+    import json
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--cpu-sample-rows", "48"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "feature-CMI evaluations/sec" and line["unit"] == "evaluations/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["config"]["workload"] == "C3_1kx100k" and line["config"]["features"] == 100000
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    env["RANK"] = "1"
+    env["WORLD_SIZE"] = "2"
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
