@@ -231,6 +231,10 @@ int rvl_get_matrix_dims(rvl_ctx *ctx, int64_t *out_rows, int64_t *out_samples);
 int rvl_get_row_counts(rvl_ctx *ctx, int32_t *out_counts);
 /* Kernel launches issued by this ctx since creation (bench.py's gpu_launches claim). */
 int64_t rvl_launch_count(const rvl_ctx *ctx);
+/* Instrumentation switch (default off): on != 0 makes every k_score launch count its work (rvl_get_counters*) and
+ * brackets it with a CUDA-event pair (rvl_score_kernel_time).  Off, the product path carries neither the per-evaluation
+ * atomics nor the event records. */
+int rvl_set_profiling(rvl_ctx *ctx, int on);
 /* Device time of the dominant score kernel, summed over launches since the last reset (ms),
  * measured with CUDA events on the ctx stream; and the number of launches it covers. */
 int rvl_score_kernel_time(rvl_ctx *ctx, double *out_ms, int64_t *out_launches, int reset);
@@ -256,7 +260,8 @@ int64_t rvl_unique_rows(const rvl_ctx *ctx);
  * out4[1] live (j,k) density columns (n_grid log() each), out4[2] dense-pass exp() evaluations. */
 int rvl_get_counters(rvl_ctx *ctx, uint64_t *out4, int reset);
 /* The same with more slots (n_out <= 8): out[3] (j,k) columns in the O(1) factorised form, out[4] direct columns
- * evaluated with two of the four class terms (the other y-class cannot change fl(Q) anywhere in the column). */
+ * evaluated with two of the four class terms (the other y-class cannot change fl(Q) anywhere in the column),
+ * out[5] log() evaluations, out[6] FP64 flops outside exp() and log() (an FMA counts 2).  Needs rvl_set_profiling. */
 int rvl_get_counters_ex(rvl_ctx *ctx, uint64_t *out, int n_out, int reset);
 /* FP64 FMA peak of this device by a DFMA-chain micro-benchmark (TFLOP/s); the denominator of the
  * roofline bench.py reports, since the path is FP64-compute-bound. */

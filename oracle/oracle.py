@@ -22,10 +22,10 @@ class CMI(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("CMI", "MI", "SCMI", "SMI", "HXY", "HXYZ", "IC", "CIC")]
 
 
-def build(force=False):
-    so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "revealer_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+def build(force=False, name="liboracle.so"):
+    so = os.path.join(_HERE, name)
+    srcs = [os.path.join(_HERE, f) for f in ("revealer_oracle.c", "oracle_hp.c", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
 
@@ -61,8 +61,26 @@ def lib():
         L.orc_pvals.restype = None
         L.orc_pvals.argtypes = [dp, C.c_int64, dp, C.c_int64, dp]
         L.orc_max_threads.restype = C.c_int
+        L.orc_score_rows_info.restype = None
+        L.orc_score_rows_info.argtypes = [dp, dp, C.c_int64, C.c_int, dp, C.c_int, C.c_int, dp, dp]
         _LIB = L
     return _LIB
+
+
+_HP = {}
+
+
+def hp_lib(quad=False):
+    """The extended-precision evaluation of the same estimators (oracle_hp.c): long double, or
+    __float128 with quad=True.  Noise-band measurements only."""
+    if quad not in _HP:
+        L = C.CDLL(build(name="liboracle_q.so" if quad else "liboracle_hp.so"))
+        dp = C.POINTER(C.c_double)
+        L.orchp_bits.restype = C.c_int
+        L.orchp_score_rows.restype = None
+        L.orchp_score_rows.argtypes = [dp, dp, C.c_int64, C.c_int, dp, C.c_int, C.c_int, dp, dp]
+        _HP[quad] = L
+    return _HP[quad]
 
 
 def _d(a):
@@ -132,6 +150,30 @@ def score_rows(target, m2_rows, seed, n_grid=25, hoist=True, nthreads=0):
     lib().orc_score_rows(pt, pm, F, n, ps, n_grid, int(hoist), nthreads,
                          out.ctypes.data_as(C.POINTER(C.c_double)))
     return out
+
+
+def score_rows_info(target, m2_rows, seed, n_grid=25, nthreads=0):
+    """(scores, info): info[k] = the MI / CMI score k was formed from (double-precision oracle, hoisted bcv)."""
+    t, pt = _d(target)
+    m, pm = _d(m2_rows)
+    s, ps = _d(seed)
+    F, n = m.shape
+    out, info = np.empty(F), np.empty(F)
+    dp = C.POINTER(C.c_double)
+    lib().orc_score_rows_info(pt, pm, F, n, ps, n_grid, nthreads, out.ctypes.data_as(dp), info.ctypes.data_as(dp))
+    return out, info
+
+
+def score_rows_hp(target, m2_rows, seed, n_grid=25, nthreads=0, quad=False):
+    """(scores, info) from the extended-precision evaluation (same inputs, same bcv bandwidths)."""
+    t, pt = _d(target)
+    m, pm = _d(m2_rows)
+    s, ps = _d(seed)
+    F, n = m.shape
+    out, info = np.empty(F), np.empty(F)
+    dp = C.POINTER(C.c_double)
+    hp_lib(quad).orchp_score_rows(pt, pm, F, n, ps, n_grid, nthreads, out.ctypes.data_as(dp), info.ctypes.data_as(dp))
+    return out, info
 
 
 def top1(v, negative=False):

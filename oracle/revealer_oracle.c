@@ -46,6 +46,15 @@
 #define ORC_NGRID_MAX 64
 typedef long double LDOUBLE;
 
+/* The two KDE contractions are compiled twice (AVX2 and baseline x86-64, picked at load time): vector
+ * lanes hold different grid points i, each with its own accumulator, so the result is bit-identical
+ * to the scalar loop (-ffp-contract=off: no FMA in either clone). */
+#if defined(__GNUC__) && defined(__x86_64__) && !defined(__clang__)
+#define ORC_HOT __attribute__((target_clones("avx2", "default")))
+#else
+#define ORC_HOT
+#endif
+
 #define ORC_M_1_SQRT_2PI 0.398942280401432677939946059934
 #define ORC_M_PI 3.141592653589793238462643383280
 
@@ -179,13 +188,14 @@ static void orc_den_bin(int n, int nb, double *d, const double *x, int *cnt)
     double rang = (xmax - xmin) * 1.01;
     double dd = rang / nb;
     *d = dd;
+    /* the original recomputes jj = (int)(x[j]/dd) inside the pair loop; the values are the same */
+    int *bin = (int *)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < n; i++) bin[i] = (int)(x[i] / dd);
     for (int i = 1; i < n; i++) {
-        int ii = (int)(x[i] / dd);
-        for (int j = 0; j < i; j++) {
-            int jj = (int)(x[j] / dd);
-            cnt[abs(ii - jj)]++;
-        }
+        int ii = bin[i];
+        for (int j = 0; j < i; j++) cnt[abs(ii - bin[j])]++;
     }
+    free(bin);
 }
 
 typedef struct { int n, nb; double d; const int *cnt; } orc_bcv_info;
@@ -253,7 +263,7 @@ static double orc_dnorm(double x, double mu, double sd)
 /* ------------------------------------------------------------------ MASS::kde2d */
 
 /* z is ng x ng, column-major like R: z[i + ng*j]. h is kde2d's `h` argument (divided by 4 inside). */
-static void orc_kde2d(const double *x, const double *y, int n, const double h[2], int ng,
+ORC_HOT static void orc_kde2d(const double *x, const double *y, int n, const double h[2], int ng,
                       double *gx, double *gy, double *z)
 {
     double xlo, xhi, ylo, yhi;
@@ -270,19 +280,26 @@ static void orc_kde2d(const double *x, const double *y, int n, const double h[2]
             mx[i + (size_t)ng * s] = ORC_M_1_SQRT_2PI * exp(-0.5 * ax * ax);
             my[i + (size_t)ng * s] = ORC_M_1_SQRT_2PI * exp(-0.5 * ay * ay);
         }
-    for (int j = 0; j < ng; j++)
-        for (int i = 0; i < ng; i++) {
-            double acc = 0.0;
-            for (int s = 0; s < n; s++) acc += mx[i + (size_t)ng * s] * my[j + (size_t)ng * s];
-            z[i + ng * j] = acc / (n * hx * hy);
+    /* z = tcrossprod(mx, my)/(n hx hy): every cell is the sum over s = 0..n-1, in that order, of
+     * mx[i,s]*my[j,s].  The loops run s-outer / i-inner over ng independent accumulators (one per
+     * i) so that the compiler can keep them in vector registers; no cell's summation order changes. */
+    for (int j = 0; j < ng; j++) {
+        double acc[ORC_NGRID_MAX];
+        for (int i = 0; i < ng; i++) acc[i] = 0.0;
+        for (int s = 0; s < n; s++) {
+            const double w = my[j + (size_t)ng * s];
+            const double *col = mx + (size_t)ng * s;
+            for (int i = 0; i < ng; i++) acc[i] += col[i] * w;
         }
+        for (int i = 0; i < ng; i++) z[i + ng * j] = acc[i] / (n * hx * hy);
+    }
     free(mx);
 }
 
 /* ------------------------------------------------------------------ misc3d::kde3d */
 
 /* d is ng^3, column-major: d[i + ng*(j + ng*k)].  h used directly as the sd of each axis. */
-static void orc_kde3d(const double *x, const double *y, const double *zz, int n, const double h[3],
+ORC_HOT static void orc_kde3d(const double *x, const double *y, const double *zz, int n, const double h[3],
                       int ng, double *gx, double *gy, double *gz, double *d)
 {
     double lo, hi;
@@ -298,16 +315,23 @@ static void orc_kde3d(const double *x, const double *y, const double *zz, int n,
             mz[i + (size_t)ng * s] = orc_dnorm(gz[i], zz[s], h[2]);
         }
     for (int k = 0; k < ng; k++) {
-        /* tmy.nz.zk = t(my)/nx * mz[k,]  (n x ng), then v[,,k] = mx %*% tmy.nz.zk */
+        /* tmy.nz.zk = t(my)/nx * mz[k,]  (n x ng), then v[,,k] = mx %*% tmy.nz.zk: every cell is the
+         * sum over s = 0..n-1, in that order, of mx[i,s]*t[s,j].  As in orc_kde2d the loops run
+         * s-outer / i-inner over ng independent accumulators; no cell's summation order changes. */
         for (int j = 0; j < ng; j++)
             for (int s = 0; s < n; s++)
                 t[s + (size_t)n * j] = my[j + (size_t)ng * s] / n * mz[k + (size_t)ng * s];
-        for (int j = 0; j < ng; j++)
-            for (int i = 0; i < ng; i++) {
-                double acc = 0.0;
-                for (int s = 0; s < n; s++) acc += mx[i + (size_t)ng * s] * t[s + (size_t)n * j];
-                d[i + ng * (j + ng * k)] = acc;
+        for (int j = 0; j < ng; j++) {
+            double acc[ORC_NGRID_MAX];
+            const double *tj = t + (size_t)n * j;
+            for (int i = 0; i < ng; i++) acc[i] = 0.0;
+            for (int s = 0; s < n; s++) {
+                const double w = tj[s];
+                const double *col = mx + (size_t)ng * s;
+                for (int i = 0; i < ng; i++) acc[i] += col[i] * w;
             }
+            for (int i = 0; i < ng; i++) d[i + ng * (j + ng * k)] = acc[i];
+        }
     }
     free(mx);
 }
@@ -534,6 +558,40 @@ void orc_score_rows(const double *target, const double *m2, int64_t F, int n, co
             out[k] = orc_cond_assoc_bw(target, y, seed, n, ng, bw);
         } else {
             out[k] = orc_cond_assoc(target, y, seed, n, ng);
+        }
+    }
+}
+
+/* As orc_score_rows(hoist = 1), additionally returning the MI / CMI each score was formed from
+ * (out_info): the quantity whose absolute rounding noise tests/test_noise_band.py measures. */
+void orc_score_rows_info(const double *target, const double *m2, int64_t F, int n, const double *seed,
+                         int ng, int nthreads, double *out, double *out_info)
+{
+    const double bwx = orc_bcv(target, n);
+    const int zconst = orc_is_constant(seed, n), xconst = orc_is_constant(target, n);
+    const double bwz = zconst ? 0.0 : orc_bcv(seed, n);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t k = 0; k < F; k++) {
+        const double *y = m2 + (size_t)k * n;
+        out[k] = 0.0;
+        out_info[k] = 0.0;
+        if (xconst || orc_is_constant(y, n)) continue;
+        const double bwy = orc_bcv(y, n);
+        if (zconst) {
+            orc_mi_t r;
+            double d2[2] = { bwx, bwy };
+            orc_mutual_inf_v2(target, y, n, ng, d2, &r);
+            out[k] = r.IC;
+            out_info[k] = r.MI;
+        } else {
+            orc_cmi_t r;
+            double d3[3] = { 0.25 * bwx, 0.25 * bwy, 0.25 * bwz };
+            orc_cond_mutual_inf(target, y, seed, n, ng, d3, &r);
+            out[k] = r.CIC;
+            out_info[k] = r.CMI;
         }
     }
 }

@@ -85,6 +85,7 @@ SIGNATURES = {
     "rvl_get_matrix_dims": (_i, [_vp, _i64p, _i64p]),
     "rvl_get_row_counts": (_i, [_vp, _i32p]),
     "rvl_launch_count": (_i64, [_vp]),
+    "rvl_set_profiling": (_i, [_vp, _i]),
     "rvl_score_kernel_time": (_i, [_vp, _dp, _i64p, _i]),
     "rvl_set_dense_x": (_i, [_vp, _i]),
     "rvl_set_prune_theta": (_i, [_vp, C.c_double]),

@@ -236,6 +236,19 @@ class RevealerContext:
             raise RevealerError(_lib.RVL_ERR_ARG, "feature matrix dtype must be float64, uint8 or bool")
         self.F, self.n = F, n
 
+    def load_matrix_block(self, m2_fortran, row_lo, n_rows):
+        """Rows [row_lo, row_lo + n_rows) of a column-major float64 F_total x n matrix, read in place
+        (ld = F_total): what a shard of an R matrix looks like (rvlR_search_multi)."""
+        a = m2_fortran
+        if a.dtype != np.float64 or a.ndim != 2 or not a.flags.f_contiguous:
+            raise RevealerError(_lib.RVL_ERR_ARG, "load_matrix_block needs a Fortran-contiguous float64 matrix")
+        Ft, n = a.shape
+        if row_lo < 0 or n_rows < 0 or row_lo + n_rows > Ft:
+            raise RevealerError(_lib.RVL_ERR_ARG, "row block out of range")
+        ptr = C.cast(C.c_void_p(a.ctypes.data + 8 * int(row_lo)), C.POINTER(C.c_double))
+        self._ck(self._lib.rvl_load_matrix_f64_colmajor(self._h, ptr, int(n_rows), n, max(Ft, 1)))
+        self.F, self.n = int(n_rows), n
+
     def load_gct(self, gct, cols=None, first_row=0, n_rows=None):
         """Rows [first_row, first_row + n_rows) of a GctFile, tokenised on the device; output sample s is file
         column cols[s] (default: all columns in file order)."""
@@ -425,11 +438,16 @@ class RevealerContext:
         """Density-column pruning threshold of the 3-D epilogue (see rvl_set_prune_theta); 0 = exact rule only."""
         self._ck(self._lib.rvl_set_prune_theta(self._h, float(theta)))
 
+    def set_profiling(self, on):
+        """Work counters + per-launch timing of the score kernel (off by default; see rvl_set_profiling)."""
+        self._ck(self._lib.rvl_set_profiling(self._h, int(bool(on))))
+
     def counters(self, reset=False):
         out = (C.c_uint64 * 8)()
         self._ck(self._lib.rvl_get_counters_ex(self._h, out, 8, int(reset)))
         return dict(kde_evaluations=int(out[0]), live_columns=int(out[1]), dense_exps=int(out[2]),
-                    factorised_columns=int(out[3]), two_term_columns=int(out[4]))
+                    factorised_columns=int(out[3]), two_term_columns=int(out[4]), logs=int(out[5]),
+                    plain_flops=int(out[6]))
 
     def measure_fp64_peak(self):
         out = C.c_double()

@@ -184,7 +184,8 @@ struct rvl_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool side_pending = false;
 
-    // instrumentation
+    // instrumentation (rvl_set_profiling): work counters of k_score and a CUDA-event pair around each of its launches
+    int profiling = 0;
     unsigned long long *d_ctr = nullptr; // [0] KDE evaluations, [1] direct (j,k) columns, [2] x-axis exps, [3] factorised, [4] two-term
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -608,11 +609,14 @@ extern "C" int rvl_load_matrix_f64_colmajor(rvl_ctx *ctx, const double *m2, int6
     // the DMA side: column chunks of whole bit words (~64 MB each; exactly one word when packers run, so that the
     // two sides meet on a word boundary) through two staging halves -- the copy stream fills one while the main
     // stream packs the other, so the DMA engine never waits for a pack kernel
-    int64_t cols = (64ll << 20) / (8 * ld);
+    int64_t cols = (64ll << 20) / (8 * F);
     cols = (cols / 64) * 64;
     if (cols < 64 || plan) cols = 64;
     int64_t stage_cols = cols < n ? cols : n;
-    rc = reserve_stage(ctx, sizeof(double) * (size_t)ld * stage_cols);
+    // the staging halves hold the F rows of each column densely (pitch F), whatever the caller's ld: a row block of a
+    // larger R matrix (ld > F) is gathered by a pitched copy, so neither PCIe nor the pack kernel ever sees the
+    // other shards' rows and nothing beyond m2 + ld*(n-1) + F is read
+    rc = reserve_stage(ctx, sizeof(double) * (size_t)F * stage_cols);
     cudaError_t ce = cudaSuccess;
     if (!rc) ce = cudaEventRecord(ctx->ev_packed[0], ctx->stream); // staging halves are free once earlier work is done
     if (!rc && ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_packed[1], ctx->stream);
@@ -629,12 +633,18 @@ extern "C" int rvl_load_matrix_f64_colmajor(rvl_ctx *ctx, const double *m2, int6
         const int64_t nc = (n - s0 < cols) ? (n - s0) : cols;
         double *stage = reinterpret_cast<double *>(ctx->d_stage[half]);
         ce = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[half], 0);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(stage, m2 + ld * s0, sizeof(double) * (size_t)ld * nc, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (ce == cudaSuccess) {
+            if (ld == F)
+                ce = cudaMemcpyAsync(stage, m2 + ld * s0, sizeof(double) * (size_t)F * nc, cudaMemcpyHostToDevice, ctx->copy_stream);
+            else
+                ce = cudaMemcpy2DAsync(stage, sizeof(double) * (size_t)F, m2 + ld * s0, sizeof(double) * (size_t)ld,
+                                       sizeof(double) * (size_t)F, (size_t)nc, cudaMemcpyHostToDevice, ctx->copy_stream);
+        }
         if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_copied[half], ctx->copy_stream);
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[half], 0);
         if (ce != cudaSuccess) break;
-        ctx->last_h2d_bytes += sizeof(double) * (uint64_t)ld * (uint64_t)nc;
-        rvl_launch_pack_f64_colmajor(stage, F, ld, (int)s0, (int)nc, ctx->words, ctx->d_bits, ctx->d_flag, ctx->stream);
+        ctx->last_h2d_bytes += sizeof(double) * (uint64_t)F * (uint64_t)nc;
+        rvl_launch_pack_f64_colmajor(stage, F, F, (int)s0, (int)nc, ctx->words, ctx->d_bits, ctx->d_flag, ctx->stream);
         ce = cudaEventRecord(ctx->ev_packed[half], ctx->stream);
         ctx->launches++;
         half ^= 1;
@@ -1174,21 +1184,21 @@ static int launch_score(rvl_ctx *ctx, double *base)
 {
     RvlParams P = make_params(ctx);
     if (ctx->F == 0) return RVL_OK; // k_seed_prep already left every best slot at "none"
-    if (ctx->score_events_used == ctx->score_events.size()) {
+    const bool prof = ctx->profiling != 0;
+    if (prof && ctx->score_events_used == ctx->score_events.size()) {
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));
         CK(cudaEventCreate(&b));
         ctx->score_events.push_back({a, b});
     }
-    auto &ev = ctx->score_events[ctx->score_events_used++];
     if (ctx->work_dirty) CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned long long), ctx->stream));
     ctx->work_dirty = true; // k_seed_prep re-arms the counter; a repeated launch without it must do so here
-    CK(cudaEventRecord(ev.first, ctx->stream));
+    if (prof) CK(cudaEventRecord(ctx->score_events[ctx->score_events_used].first, ctx->stream));
     rvl_launch_score(&P, ctx->score_grid_x, ctx->score_smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed,
-                     ctx->d_bcvtab, ctx->d_tt, base, ctx->d_part, ctx->d_work, ctx->d_ctr,
+                     ctx->d_bcvtab, ctx->d_tt, base, ctx->d_part, ctx->d_work, prof ? ctx->d_ctr : nullptr,
                      ctx->dedup ? ctx->d_uniq : nullptr, ctx->U, ctx->stream);
     ctx->fill_pending = ctx->dedup && ctx->U < ctx->F;
-    CK(cudaEventRecord(ev.second, ctx->stream));
+    if (prof) CK(cudaEventRecord(ctx->score_events[ctx->score_events_used++].second, ctx->stream));
     ctx->launches++;
     CK(cudaGetLastError());
     return RVL_OK;
@@ -1570,6 +1580,15 @@ extern "C" int rvl_measure_fp64_peak(rvl_ctx *ctx, double *out_tflops)
     }
     cudaFree(d);
     *out_tflops = best;
+    return RVL_OK;
+}
+
+extern "C" int rvl_set_profiling(rvl_ctx *ctx, int on)
+{
+    GUARD();
+    CK(cudaStreamSynchronize(ctx->stream));
+    drain_score_events(ctx);
+    ctx->profiling = on ? 1 : 0;
     return RVL_OK;
 }
 

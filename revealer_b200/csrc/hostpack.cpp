@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -71,7 +72,12 @@ extern "C" {
 // Start `nthreads` packers on the words at the back of the matrix.  `packed` holds W * F uint64.
 void *rvl_hostpack_begin(const double *m2, int64_t F, int64_t n, int64_t ld, uint64_t *packed, int nthreads)
 {
-    RvlHostPackPlan *p = new RvlHostPackPlan();
+    RvlHostPackPlan *p = nullptr;
+    try { // nothing may be thrown across the C ABI: no plan == the DMA side does the whole upload
+        p = new RvlHostPackPlan();
+    } catch (...) {
+        return nullptr;
+    }
     p->m2 = m2; p->F = F; p->n = n; p->ld = ld;
     p->W = (n + 63) / 64;
     p->packed = packed;

@@ -1073,6 +1073,12 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
                 atomicAdd(&ctr[2], (unsigned long long)nexp * G);  // x-axis exp() evaluations
                 atomicAdd(&ctr[3], (unsigned long long)nfact);     // (j,k) columns in factorised form
                 atomicAdd(&ctr[4], (unsigned long long)ntwo);      // direct columns evaluated with two of the four terms
+                // log() calls and plain FP64 flops (outside exp / log) of this evaluation, for the roofline numerator:
+                // pass A 2 G^2 logs, one per non-dead column in pass B, G per direct column in pass C, G for the z
+                // marginal, 1 in the table lookup; FMAs of passes A/B, 10 flop per direct cell (6 for a two-term one)
+                atomicAdd(&ctr[5], (unsigned long long)(2 * G * G + G + 1) + (unsigned long long)nlive * (G + 1) + nfact);
+                atomicAdd(&ctr[6], (unsigned long long)(G * G * 42 + 80) + (unsigned long long)nlive * G * 10 -
+                                       (unsigned long long)ntwo * G * 4 + (unsigned long long)nexp * G * 6);
             }
         }
         if (rvl_ahead(score, f, best_v, best_i, P.negative)) { best_v = score; best_i = f; }
