@@ -28,17 +28,6 @@
 #include <cstring>
 
 #define RVL_SCORE_WARPS 8 // warps per block of k_advance / k_assoc (fixes their summation order)
-#ifndef RVL_EPI_CALL
-#define RVL_EPI_CALL 0 // 1: the production entropy epilogue is a real call with its own register budget
-#endif
-#define RVL_STR(x) #x
-#define RVL_UNROLL(n) _Pragma(RVL_STR(unroll n))
-#ifndef RVL_UNROLL_A
-#define RVL_UNROLL_A 1 // unroll of the entropy epilogue's pass A (per-k tables over the x grid)
-#endif
-#ifndef RVL_UNROLL_B
-#define RVL_UNROLL_B 1 // unroll of pass B (column classification over the y grid)
-#endif
 #ifndef RVL_KSCORE_WARPS
 #define RVL_KSCORE_WARPS 8 // independent worker warps per block of k_score
 #endif
@@ -48,15 +37,21 @@
 __device__ double2 rvl_logtab_g[RVL_LOGTAB_ENTRIES];
 
 // ---- per-warp scratch in shared memory ----------------------------------------------------
+#define RVL_LIST_MAX 512    // minority-class samples listed per row (longer rows walk their bit words instead)
+#define RVL_ITEMS_CAP 1024  // direct (j,k) columns: four-term ones from the front, two-term ones from the back
 struct __align__(16) RvlWarpScratch {
-    double A[RVL_MAXG][4];     // A[i][a*2+b]
+    double A[RVL_MAXG][4];     // A[i][a*2+b]: x-axis kernel sums of the four (y,z) classes
     double AT[4][RVL_MAXG];    // the same numbers class-major (pass C loads four consecutive grid points per class)
     double gy[2][RVL_MAXG];    // gy[a][j]
     double gz[2][RVL_MAXG];    // gz[b][k]
-    uint16_t live[RVL_MAXG * RVL_MAXG];
-    uint32_t list[512];        // minority-class samples of the row being scored (RVL_LIST_MAX)
+    // y-axis tables of the entropy epilogue, indexed by the distance d from a y-class's own end of the axis:
+    // prefix sums PG = sum g, PGL = sum g log g, PL = sum log g (d' <= d); suffix sums SG1..3 = sum g^1..3 (d' >= d)
+    double tab[6][RVL_MAXG + 1];
+    union {
+        uint32_t list[RVL_LIST_MAX];   // minority-class samples of the row being scored (before the epilogue)
+        uint16_t items[RVL_ITEMS_CAP]; // (j << 5 | k) codes of the density columns evaluated cell by cell (epilogue)
+    };
 };
-#define RVL_LIST_MAX 512
 
 // FAST: rvl_log_pos (normal positive arguments only); otherwise the library log.
 template <bool FAST> __device__ __forceinline__ double rvl_logq(double q) { return FAST ? rvl_log_pos(q) : log(q); }
@@ -142,7 +137,7 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, double
             live = dmax >= dead_thr;
         }
         unsigned m = __ballot_sync(FULL, live);
-        if (live) S.live[nlive + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
+        if (live) S.items[nlive + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
         nlive += __popc(m);
     }
     __syncwarp();
@@ -153,7 +148,7 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, double
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0, accyz = 0.0;
     const double gE = (double)G * epsq;
     for (int idx = lane; idx < nlive; idx += 32) {
-        int p = S.live[idx];
+        int p = S.items[idx];
         int j = p / G, k = p - j * G;
         double w00 = S.gy[0][j] * S.gz[0][k], w01 = S.gy[0][j] * S.gz[1][k];
         double w10 = S.gy[1][j] * S.gz[0][k], w11 = S.gy[1][j] * S.gz[1][k];
@@ -198,38 +193,156 @@ __device__ double rvl_cmi_epilogue(RvlWarpScratch &S, int G, double epsq, double
     return (L3 - Lxz - Lyz + Lz) / Stot;
 }
 
+// ---- closed forms along the y axis ---------------------------------------------------------------
+// The densities above one (x,z) cell -- and the entries of the y-z marginal above one z grid point -- have the form
+//   Q_j = g[d_M] XM + g[d_m] Xm + E,   g[d] = exp(-kappa d^2) the y-axis kernel at distance d from a y-class's own end
+// of the axis, d_M + d_m = G-1.  g falls off so fast that along j a class term t = g[d] X / E is, from its own end outwards,
+//   big    t >= 16:      Q log Q = D log D + E (log D + 1) + O(E^2/D),  log D = log g[d] + log X    -- no log needed
+//   mid    16 > t > 1/2: evaluated directly
+//   small  t <= 1/2:     Q log Q = E log E + D (log E + 1) + D^2/(2E) - D^3/(6E^2) + O(E t^4/12)
+// wherever the other class's term is invisible to fl(Q).  Summed over the j of a regime these are O(1) from six tables
+// over d: prefix sums of g, g log g, log g (`big`), suffix sums of g, g^2, g^3 (`small`).  The neglected terms sum to
+// < 1e-17 on CMI (tools/proto/epilogue_c.py checks the closed forms against the literal cube in extended precision;
+// tests: production == literal cube).  Regime boundaries come from an approximate float sqrt: a term one step off its
+// regime is still well inside the expansions' range, and direct evaluation is exact everywhere.
+struct RvlRegime {          // per evaluation and per floor E
+    double E, lE1;          // floor, log E + 1
+    double h2, h3;          // 1/(2E), 1/(6E^2)
+    double Lhi;             // log(16 E)
+    float inv_kappa;        // 1/kappa = 2 ((G-1) hy)^2
+    float x_lo, x_dead;     // log(16 / 0.5) / kappa, log(16 * 2^54) / kappa
+};
+
+__device__ __forceinline__ RvlRegime rvl_regime_make(double E, double lE, double inv_kappa)
+{
+    RvlRegime R;
+    R.E = E; R.lE1 = lE + 1.0;
+    R.h2 = 0.5 / E;
+    R.h3 = (1.0 / 6.0) / (E * E);
+    R.Lhi = lE + 2.772588722239781;                       // log 16
+    R.inv_kappa = (float)inv_kappa;
+    R.x_lo = (float)(3.4657359027997265 * inv_kappa);     // log 32
+    R.x_dead = (float)(40.20253647247683 * inv_kappa);    // log(16 * 2^54)
+    return R;
+}
+
+// floor(sqrt(x)) clamped to [-1, hi] (x < 0: -1) from the approximate square root: one MUFU instead of the IEEE sequence.
+__device__ __forceinline__ int rvl_sqrt_bound(float x, int hi)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(x, 0.f)));
+    return x < 0.f ? -1 : min(hi, (int)r);
+}
+
+// One cell: class values XM / Xm (>= 0) with logs lM / lm.  Adds the closed-form parts to accX (terms carrying X) and
+// accE (coefficient of E), the number of j whose E log E is still owed to cntE, and returns the mask (bit = j' = d_M)
+// of the entries that must be evaluated directly.  `valid` = 0 turns the lane into a no-op.
+__device__ __forceinline__ unsigned rvl_cell_regimes(const RvlWarpScratch &S, const RvlRegime &R, int G, bool valid, double XM,
+                                                     double Xm, double lM, double lm, double &accX, double &accE, int &cntE)
+{
+    const int G1 = G - 1;
+    // last d with t >= 16 (a1), t > 1/2 (a2), t >= 2^-54 (a3); -1: none
+    const float xM = (float)(lM - R.Lhi) * R.inv_kappa, xm = (float)(lm - R.Lhi) * R.inv_kappa;
+    const int a1M = rvl_sqrt_bound(xM, G1), a2M = rvl_sqrt_bound(xM + R.x_lo, G1), a3M = rvl_sqrt_bound(xM + R.x_dead, G1);
+    const int a1m = rvl_sqrt_bound(xm, G1), a2m = rvl_sqrt_bound(xm + R.x_lo, G1), a3m = rvl_sqrt_bound(xm + R.x_dead, G1);
+    // a class's closed forms stop where the other class becomes visible
+    const int limM = G - 2 - a3m, limm = G - 2 - a3M;
+    const int bM = min(a1M, limM), bm = min(a1m, limm);
+    const int s1M = a2M + 1, s1m = a2m + 1;
+    unsigned closedM = 0u, closedm = 0u; // in each class's own d coordinates
+    if (valid) {
+        if (bM >= 0) { // big, d_M in [0, bM]
+            accX = fma(XM, fma(lM, S.tab[0][bM], S.tab[1][bM]), accX);
+            accE += fma((double)(bM + 1), lM + 1.0, S.tab[2][bM]);
+            closedM = (2u << bM) - 1u;
+        }
+        if (bm >= 0) {
+            accX = fma(Xm, fma(lm, S.tab[0][bm], S.tab[1][bm]), accX);
+            accE += fma((double)(bm + 1), lm + 1.0, S.tab[2][bm]);
+            closedm = (2u << bm) - 1u;
+        }
+        if (s1M <= limM) { // small, d_M in [s1M, limM] (through the gap where both classes are dead)
+            const double g1 = S.tab[3][s1M] - S.tab[3][limM + 1], g2 = S.tab[4][s1M] - S.tab[4][limM + 1],
+                         g3 = S.tab[5][s1M] - S.tab[5][limM + 1];
+            accX = fma(XM, fma(XM, fma(-XM * R.h3, g3, g2 * R.h2), g1 * R.lE1), accX);
+            closedM |= ((2u << limM) - 1u) & ~((1u << s1M) - 1u);
+        }
+        if (s1m <= limm) {
+            const double g1 = S.tab[3][s1m] - S.tab[3][limm + 1], g2 = S.tab[4][s1m] - S.tab[4][limm + 1],
+                         g3 = S.tab[5][s1m] - S.tab[5][limm + 1];
+            accX = fma(Xm, fma(Xm, fma(-Xm * R.h3, g3, g2 * R.h2), g1 * R.lE1), accX);
+            closedm |= ((2u << limm) - 1u) & ~((1u << s1m) - 1u);
+        }
+    }
+    const unsigned all = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
+    const unsigned direct = valid ? (all & ~closedM & ~(__brev(closedm) >> (32 - G))) : 0u;
+    cntE += valid ? (G - (bM >= 0 ? bM + 1 : 0) - (bm >= 0 ? bm + 1 : 0) - __popc(direct)) : 0;
+    return direct;
+}
+
+// bits lo..hi (inclusive) of a 32-bit mask; empty when lo > hi or hi < 0
+__device__ __forceinline__ unsigned rvl_bits(int lo, int hi)
+{
+    lo = max(lo, 0);
+    return (lo <= hi) ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+}
+
 // 3-D epilogue, production form.  Same quantity as rvl_cmi_epilogue, organised around the majority
 // y-class `am` (the class holding most samples; a = 0 for the usual sparse alteration row):
 //   Q_ijk = g_M[j] * V_k[i] + g_m[j] * W_k[i] + eps',   V_k[i] = A_{am,0}[i] gz_0[k] + A_{am,1}[i] gz_1[k]
 // (W likewise for the minority class).  Pass A (lanes = k) builds V, W once per (i,k) and takes the
-// x-z marginal log there.  Pass B (lanes = k, loop over j) sorts every (j,k) column into
+// x-z marginal log there.  Pass B (lanes = k) sorts the G density columns above every k into
 //   dead        largest possible density below the pruning threshold  -> constant G eps' log eps'
-//   factorised  minority term cannot change fl(Q) (g_m maxW <= 2^-54 (g_M minV + eps')) and
-//               eps' <= g_M minV / 16: then sum_i Q log Q = g (log g * SV + LV) + eps' (G log g + LLV + G)
+//   factorised  minority term cannot change fl(Q) (g_m maxW < 2^-54 eps') and eps' <= g_M minV / 16: then
+//               sum_i Q log Q = g (log g * SV + LV) + eps' (G log g + LLV + G)
 //               with SV = sum V, LV = sum V log V, LLV = sum log V from pass A and log g known in closed
 //               form.  This is (a + e) log(a + e) expanded to first order in e = eps'; the neglected
 //               part is < eps'/32 per cell, i.e. < G^3 eps' / (32 S) ~ 1e-16 on CMI -- O(1) per column
 //   direct      everything else: G cells, one log each (pass C, lanes = columns, 4 logs in flight)
-// For a sparse row every column on the majority side of the y axis is factorised, which removes
+// The y-axis kernel g[d] = exp(-kappa d^2) is monotone in the distance d from a class's end of the axis, so all
+// three sets are INTERVALS of j whose ends follow in closed form from log maxV, log minV, log maxW (five sqrt bounds
+// per lane) -- no loop over j: the factorised interval is summed with the prefix tables of the y-axis kernel, the
+// direct columns are written to the lists at offsets from a warp scan, and the y-z marginal comes from the cell
+// closed forms above (cells = k).  (Round 1 classified column by column in 25 serial trips of ballots: 23 % of the
+// kernel's time.)  For a sparse row every column on the majority side of the y axis is factorised, which removes
 // roughly half of the logs.
 template <bool FAST>
 __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, double theta, double hy, int am, int lane,
-                                     int *ndirect_out, int *nfact_out, int *ntwo_out)
+                                     int *ndirect_out, int *nfact_out, int *ntwo_out, int *nyz_out)
 {
     const unsigned FULL = 0xffffffffu;
     const int M0 = am * 2, M1 = am * 2 + 1, m0 = (1 - am) * 2, m1 = (1 - am) * 2 + 1;
     double sa[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) sa[c] = rvl_warp_sum((lane < G) ? S.A[lane][c] : 0.0);
-    const double Gy = rvl_warp_sum((lane < G) ? S.gy[0][lane] : 0.0);
-    const double Gz = rvl_warp_sum((lane < G) ? S.gz[0][lane] : 0.0);
-    const int GG = G * G;
+    const bool active = lane < G;
+    const double g = active ? S.gy[0][lane] : 0.0;
+    const double Gy = rvl_warp_sum(g);
+    const double Gz = rvl_warp_sum(active ? S.gz[0][lane] : 0.0);
+    const int GG = G * G, G1 = G - 1;
     const double gE = (double)G * epsq;
     const double Stot = (sa[0] + sa[1] + sa[2] + sa[3]) * Gy * Gz + (double)GG * (double)G * epsq;
     const double dead_thr = fmax(epsq * 0x1p-55, theta * Stot / ((double)GG * (double)G));
-    const bool active = lane < G;
     const int kk = active ? lane : 0;
     const double gz0 = S.gz[0][kk], gz1 = S.gz[1][kk];
+
+    // ---- y-axis tables over d = lane (the argument of exp in rvl_fill_axis is log g)
+    const double inv = 1.0 / ((double)G1 * hy);
+    {
+        const double t = (double)lane * inv;
+        const double lg = active ? -0.5 * t * t : 0.0;
+        double p0 = g, p1 = g * lg, p2 = lg, s1 = g, s2 = g * g, s3 = g * g * g;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double u0 = __shfl_up_sync(FULL, p0, o), u1 = __shfl_up_sync(FULL, p1, o), u2 = __shfl_up_sync(FULL, p2, o);
+            const double d1 = __shfl_down_sync(FULL, s1, o), d2 = __shfl_down_sync(FULL, s2, o), d3 = __shfl_down_sync(FULL, s3, o);
+            if (lane >= o) { p0 += u0; p1 += u1; p2 += u2; }
+            if (lane + o < 32) { s1 += d1; s2 += d2; s3 += d3; }
+        }
+        S.tab[0][lane] = p0; S.tab[1][lane] = p1; S.tab[2][lane] = p2;
+        S.tab[3][lane] = s1; S.tab[4][lane] = s2; S.tab[5][lane] = s3;
+        if (lane == 0) { S.tab[3][32] = 0.0; S.tab[4][32] = 0.0; S.tab[5][32] = 0.0; }
+    }
 
     // ---- pass A: per-k tables over i, and the x-z marginal
     // min / max of V and max of W are only used in the (conservative) column tests of pass B, so they are
@@ -237,7 +350,7 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
     // instead of a NaN-aware FP64 compare-select) and widened outwards afterwards.
     double SV = 0.0, LV = 0.0, LLV = 0.0, accxz = 0.0;
     int minVh = 0x7ff00000, maxVh = 0, maxWh = 0;
-RVL_UNROLL(RVL_UNROLL_A)
+#pragma unroll 1
     for (int i = 0; i < G; i++) {
         const double V = fma(S.A[i][M0], gz0, S.A[i][M1] * gz1);
         const double W = fma(S.A[i][m0], gz0, S.A[i][m1] * gz1);
@@ -256,73 +369,90 @@ RVL_UNROLL(RVL_UNROLL_A)
     const double maxV = __hiloint2double(maxVh, (int)0xffffffff);   // >= the true maxima
     const double maxW = __hiloint2double(maxWh, (int)0xffffffff);
     if (!active) accxz = 0.0;
-    const double sM = fma(sa[M0], gz0, sa[M1] * gz1), sm = fma(sa[m0], gz0, sa[m1] * gz1);
-
-    // ---- pass B: classify the G columns of this k, one j per round.  Column codes are (j << 5) | k.
-    // (Taking the y-z marginal logs out of this loop -- live-column list, four logs per lane and trip
-    // afterwards -- was measured: 0.6 % slower.)
-    double accF = 0.0, accyz = 0.0;
-    int n4 = 0, n2 = 0, nfact = 0, ndead = 0;
-    const double inv = 1.0 / ((double)(G - 1) * hy);
-    const unsigned below = (1u << lane) - 1u;
-RVL_UNROLL(RVL_UNROLL_B)
-#ifdef RVL_ABLATE_PASS_B
-    for (int j = 0; j < 0; j++) {
-#else
-    for (int j = 0; j < G; j++) {
-#endif
-        const double g0 = S.gy[0][j], g1 = S.gy[1][j];
-        const double gM = am ? g1 : g0, gm = am ? g0 : g1;
-        const double dmax = fma(gM, maxV, gm * maxW);
-        const bool dead = dmax < dead_thr;
-        const unsigned mL = __ballot_sync(FULL, active && !dead);
-        if (!mL) { // the whole y-slice is below the threshold (typical mid-axis j)
-            ndead += G;
-            continue;
-        }
-        const int code = (j << 5) | lane;
-        if (active && !dead) {
-            const double qyz = fma(gM, sM, fma(gm, sm, gE));
-            accyz = fma(qyz, rvl_logq<FAST>(qyz), accyz);
-        }
-        const bool fact = !dead && (gm * maxW <= 0x1p-54 * fma(gM, minV, epsq)) && (gM * minV >= 16.0 * epsq);
-        if (active && fact) {
-            const double t = (double)(am ? (G - 1 - j) : j) * inv;
-            const double lg = -0.5 * t * t; // log g_M[j]
-            accF += fma(gM, fma(lg, SV, LV), epsq * (fma((double)G, lg, LLV) + (double)G));
-        }
-        // direct columns: when one y-class cannot change fl(Q) anywhere in the column (its largest term is
-        // below half an ulp of the eps' floor every cell carries) the cell needs only the other class's two
-        // terms -- bit-identical to the four-term chain, half the FMAs and loads.  Four-term columns are
-        // listed from the front of S.live, two-term columns from the back (bit 15: the surviving class is
-        // the minority one).
-        const bool direct = active && !dead && !fact;
-        const bool dropM = direct && (gM * maxV < 0x1p-54 * epsq);
-        const bool dropm = direct && !dropM && (gm * maxW < 0x1p-54 * epsq);
-        const bool four = direct && !dropM && !dropm;
-        const unsigned m4 = __ballot_sync(FULL, four), m2 = __ballot_sync(FULL, direct && !four);
-        if (four) S.live[n4 + __popc(m4 & below)] = (uint16_t)code;
-        if (direct && !four)
-            S.live[RVL_MAXG * RVL_MAXG - 1 - (n2 + __popc(m2 & below))] = (uint16_t)(code | (dropM ? 0x8000 : 0));
-        n4 += __popc(m4);
-        n2 += __popc(m2);
-        nfact += __popc(__ballot_sync(FULL, active && fact));
-        ndead += G - __popc(mL);
-    }
+    const double sM = am ? fma(sa[2], gz0, sa[3] * gz1) : fma(sa[0], gz0, sa[1] * gz1);
+    const double sm = am ? fma(sa[0], gz0, sa[1] * gz1) : fma(sa[2], gz0, sa[3] * gz1);
     __syncwarp();
+
+    // ---- pass B: the column intervals of this k, in d_M coordinates (j' = distance from the majority class's end)
+    const double inv_kappa = 2.0 * ((double)G1 * hy) * ((double)G1 * hy);
+    const float ik = (float)inv_kappa;
+    const double lEps = rvl_logq<FAST>(epsq);
+    const double lmaxV = rvl_logq<FAST>(fmax(maxV, 1e-290)), lminV = rvl_logq<FAST>(fmax(minV, 1e-290)),
+                 lmaxW = rvl_logq<FAST>(fmax(maxW, 1e-290));
+    const double Ld = rvl_logq<FAST>(fmax(0.5 * dead_thr, 1e-300)); // each class term below half the threshold
+    const double L54 = lEps - 37.429947750237048;                  // log(2^-54 eps'): below it a term cannot change fl(Q)
+    const int vM = rvl_sqrt_bound((float)(lmaxV - Ld) * ik, G1);   // last j' where the majority term can reach the threshold
+    const int vm = rvl_sqrt_bound((float)(lmaxW - Ld) * ik, G1);   // last d_m where the minority term can
+    const int fM = rvl_sqrt_bound((float)(lminV - (lEps + 2.772588722239781)) * ik, G1); // last j' with g_M minV >= 16 eps'
+    const int iM = rvl_sqrt_bound((float)(lmaxV - L54) * ik, G1);  // last j' where the majority term is visible at all
+    const int im = rvl_sqrt_bound((float)(lmaxW - L54) * ik, G1);  // last d_m where the minority term is visible at all
+    const int bF = active ? min(fM, G - 2 - im) : -1;              // factorised: j' in [0, bF]
+    const unsigned mFact = rvl_bits(0, bF);
+    const unsigned mAlive = active ? (rvl_bits(0, vM) | rvl_bits(G1 - vm, G1) | mFact) : 0u;
+    const unsigned mDirect = mAlive & ~mFact;
+    const unsigned m4 = mDirect & rvl_bits(G1 - im, iM);            // both classes visible
+    const unsigned m2m = mDirect & ~rvl_bits(0, iM);                // majority invisible: the minority class's two terms
+    const unsigned m2M = mDirect & ~m4 & ~m2m;                      // minority invisible: the majority class's two terms
+    const int c4 = __popc(m4), c2 = __popc(m2m | m2M);
+    const int ndead = active ? G - __popc(mAlive) : 0;
+    double accF = 0.0;
+    if (bF >= 0) // sum over the factorised interval: g (log g SV + LV) + eps' (G log g + LLV + G)
+        accF = fma(SV, S.tab[1][bF], LV * S.tab[0][bF]) + epsq * fma((double)G, S.tab[2][bF], (double)(bF + 1) * (LLV + (double)G));
+    // list offsets: four-term columns from the front of S.items, two-term columns from the back (bit 15: the
+    // surviving class is the minority one)
+    int o4 = c4, o2 = c2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u4 = __shfl_up_sync(FULL, o4, o), u2 = __shfl_up_sync(FULL, o2, o);
+        if (lane >= o) { o4 += u4; o2 += u2; }
+    }
+    const int n4 = __shfl_sync(FULL, o4, 31), n2 = __shfl_sync(FULL, o2, 31);
+    o4 -= c4;
+    o2 -= c2;
+    for (unsigned m = m4; m; m &= m - 1u) {
+        const int jp = __ffs((int)m) - 1, j = am ? G1 - jp : jp;
+        S.items[o4++] = (uint16_t)((j << 5) | lane);
+    }
+    for (unsigned m = m2M; m; m &= m - 1u) {
+        const int jp = __ffs((int)m) - 1, j = am ? G1 - jp : jp;
+        S.items[RVL_MAXG * RVL_MAXG - 1 - (o2++)] = (uint16_t)((j << 5) | lane);
+    }
+    for (unsigned m = m2m; m; m &= m - 1u) {
+        const int jp = __ffs((int)m) - 1, j = am ? G1 - jp : jp;
+        S.items[RVL_MAXG * RVL_MAXG - 1 - (o2++)] = (uint16_t)((j << 5) | lane | 0x8000);
+    }
     *ndirect_out = n4 + n2;
-    *nfact_out = nfact;
+    *nfact_out = rvl_warp_sum_i(bF + 1);
     *ntwo_out = n2;
+
+    // ---- y-z marginal: Q_jk = g[d_M] sM_k + g[d_m] sm_k + G eps', cells = k
+    double accyz = 0.0;
+    int nyz;
+    {
+        const double lgE = rvl_logq<FAST>(gE);
+        const RvlRegime Ryz = rvl_regime_make(gE, lgE, inv_kappa);
+        const double lM = rvl_logq<FAST>(fmax(sM, 1e-290)), lm = rvl_logq<FAST>(fmax(sm, 1e-290));
+        double aX = 0.0, aE = 0.0;
+        int cE = 0;
+        unsigned mask = rvl_cell_regimes(S, Ryz, G, active, sM, sm, lM, lm, aX, aE, cE);
+        nyz = __popc(mask);
+        while (mask) { // a handful per lane
+            const int jp = __ffs((int)mask) - 1;
+            mask &= mask - 1u;
+            const double q = fma(S.gy[0][jp], sM, fma(S.gy[0][G1 - jp], sm, gE));
+            accyz = fma(q, rvl_logq<FAST>(q), accyz);
+        }
+        accyz += aX + gE * aE + (double)cE * (gE * lgE);
+    }
+    *nyz_out = rvl_warp_sum_i(nyz);
+    __syncwarp();
 
     // ---- pass C: direct columns, lanes = columns; four grid points per trip, level by level: the four cells'
     // FMA chains and the four logs advance side by side (class-major AT: two 16-byte loads fetch one class
     // for all four points)
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#ifdef RVL_ABLATE_PASS_C // timing experiments only: results are wrong with these set
-    n4 = 0; n2 = 0;
-#endif
     for (int idx = lane; idx < n4; idx += 32) {
-        const int p = S.live[idx];
+        const int p = S.items[idx];
         const int j = p >> 5, k = p & 31;
         const double w00 = S.gy[0][j] * S.gz[0][k], w01 = S.gy[0][j] * S.gz[1][k];
         const double w10 = S.gy[1][j] * S.gz[0][k], w11 = S.gy[1][j] * S.gz[1][k];
@@ -352,11 +482,11 @@ RVL_UNROLL(RVL_UNROLL_B)
         }
     }
     for (int idx = lane; idx < n2; idx += 32) { // two-term columns: classes (ra, ra + 1) of one y value
-        const int e = S.live[RVL_MAXG * RVL_MAXG - 1 - idx];
+        const int e = S.items[RVL_MAXG * RVL_MAXG - 1 - idx];
         const int ra = (e >> 15) ? m0 : M0;
         const int j = (e >> 5) & 31, k = e & 31;
-        const double g = S.gy[ra >> 1][j];
-        const double wa = g * S.gz[0][k], wb = g * S.gz[1][k];
+        const double gg = S.gy[ra >> 1][j];
+        const double wa = gg * S.gz[0][k], wb = gg * S.gz[1][k];
         const double *Aa = S.AT[ra], *Ab = S.AT[ra + 1];
         int i = 0;
 #pragma unroll 1
@@ -379,8 +509,9 @@ RVL_UNROLL(RVL_UNROLL_B)
             acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
         }
     }
-    const double L3 = rvl_warp_sum((acc0 + acc1) + (acc2 + acc3) + accF) + (double)ndead * (double)G * rvl_xlogx<FAST>(epsq);
-    const double Lyz = rvl_warp_sum(accyz) + (double)ndead * rvl_xlogx<FAST>(gE);
+    const double L3 = rvl_warp_sum((acc0 + acc1) + (acc2 + acc3) + accF) +
+                      (double)rvl_warp_sum_i(ndead) * ((double)G * (epsq * lEps));
+    const double Lyz = rvl_warp_sum(accyz);
     const double Lxz = rvl_warp_sum(accxz);
     double accz = 0.0;
     if (active) {
@@ -389,25 +520,6 @@ RVL_UNROLL(RVL_UNROLL_B)
     }
     const double Lz = rvl_warp_sum(accz);
     return (L3 - Lxz - Lyz + Lz) / Stot;
-}
-
-// The production epilogue as a real call (one per evaluation): the callee gets a register budget of its own
-// instead of sharing 128 registers with everything k_score keeps live across an evaluation, which is what
-// lets pass C hold four cells and four logs in flight.  The scratch is re-derived from the dynamic shared
-// memory base so that its loads stay LDS (a reference parameter would make them generic).
-struct RvlEpiResult {
-    double cmi;
-    int ndirect, nfact, ntwo;
-};
-template <bool FAST>
-__device__ __noinline__ RvlEpiResult rvl_cmi_epilogue_f_call(int warp_slot, int G, double epsq, double theta, double hy, int am,
-                                                             int lane)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RvlWarpScratch &S = reinterpret_cast<RvlWarpScratch *>(smem_raw)[warp_slot];
-    RvlEpiResult r;
-    r.cmi = rvl_cmi_epilogue_f<FAST>(S, G, epsq, theta, hy, am, lane, &r.ndirect, &r.nfact, &r.ntwo);
-    return r;
 }
 
 // 2-D epilogue (mutual.inf.v2, LIB:2536-2550): MI from B_a[i] = A[i][a*2] and gy.  Whole warp.
@@ -511,13 +623,15 @@ __global__ void k_rho_max(RvlParams P, const uint64_t *__restrict__ bits, const 
 // Finish one evaluation once A (dense sums) is in scratch.  Returns IC or CIC.
 // mode: RVL_MODE_IC (2-D) or RVL_MODE_CIC (3-D).  c is the bandwidth shrink factor already applied
 // to hx (beta); here it is applied to hy / hz.
-// am: majority y-class (0 unless the row has more ones than zeros).  nlive_out: columns evaluated
-// cell by cell; nfact_out: columns handled by the O(1) factorised form.
+// am: majority y-class (0 unless the row has more ones than zeros).  nitems_out: cube cells evaluated with a log of
+// their own; nyz_out: the same for the y-z marginal; nfact_out: columns in factorised form; ntwo_out: direct columns
+// evaluated with two of the four class terms.
 __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, double rho, double c, double hx,
-                             double bcv_y, double bcv_z, int am, int lane, int *nlive_out, int *nfact_out, int *ntwo_out,
-                             int dyn_slot = -1)
+                             double bcv_y, double bcv_z, int am, int lane, int *nitems_out, int *nyz_out, int *nfact_out,
+                             int *ntwo_out)
 {
-    *nlive_out = 0;
+    *nitems_out = 0;
+    *nyz_out = 0;
     *nfact_out = 0;
     *ntwo_out = 0;
     int G = P.G;
@@ -537,15 +651,21 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
     double epsq = RVL_DBL_EPS * (dn * RVL_TWO_PI * sqrt(RVL_TWO_PI) * hx * hy * hz);
     // every Q lies in [eps', 4 n G^3]: normal doubles unless eps' itself is tiny (degenerate bandwidths)
     double cmi;
-    if (epsq < 1e-290) cmi = rvl_cmi_epilogue<false>(S, G, epsq, P.prune_theta, lane, nlive_out);
-    else if (P.literal) cmi = rvl_cmi_epilogue<true>(S, G, epsq, P.prune_theta, lane, nlive_out); // literal mode
-    else if (dyn_slot >= 0) { // k_score: S is slot `dyn_slot` of the dynamic shared memory
-        const RvlEpiResult r = rvl_cmi_epilogue_f_call<true>(dyn_slot, G, epsq, P.prune_theta, hy, am, lane);
-        cmi = r.cmi;
-        *nlive_out = r.ndirect;
-        *nfact_out = r.nfact;
-        *ntwo_out = r.ntwo;
-    } else cmi = rvl_cmi_epilogue_f<true>(S, G, epsq, P.prune_theta, hy, am, lane, nlive_out, nfact_out, ntwo_out);
+    if (epsq < 1e-290) {
+        int nl;
+        cmi = rvl_cmi_epilogue<false>(S, G, epsq, P.prune_theta, lane, &nl);
+        *nitems_out = nl * G;
+    } else if (P.literal) { // validation mode: the cube cell by cell
+        int nl;
+        cmi = rvl_cmi_epilogue<true>(S, G, epsq, P.prune_theta, lane, &nl);
+        *nitems_out = nl * G;
+    } else {
+        int nd, nf, n2;
+        cmi = rvl_cmi_epilogue_f<true>(S, G, epsq, P.prune_theta, hy, am, lane, &nd, &nf, &n2, nyz_out);
+        *nitems_out = nd * G;
+        *nfact_out = nf;
+        *ntwo_out = n2;
+    }
     return rvl_sign(rho) * sqrt(1.0 - exp(-2.0 * cmi));
 }
 
@@ -1062,23 +1182,27 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
             S.AT[0][lane] = acc[0]; S.AT[1][lane] = acc[1]; S.AT[2][lane] = acc[2]; S.AT[3][lane] = acc[3];
         }
         __syncwarp();
-        int nlive, nfact, ntwo;
-        double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, n1 > n - n1 ? 1 : 0, lane, &nlive, &nfact,
-                                  &ntwo, RVL_EPI_CALL ? warp : -1);
+        int nitems, nyz, nfact, ntwo;
+        double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, n1 > n - n1 ? 1 : 0, lane, &nitems, &nyz, &nfact,
+                                  &ntwo);
         if (lane == 0) {
             out[f] = score;
-            if (ctr) { // instrumentation: work actually executed (bench.py's roofline numerator)
+            if (ctr) { // instrumentation (rvl_set_profiling): work actually executed, bench.py's roofline numerator
                 atomicAdd(&ctr[0], 1ull);                          // evaluations that ran the KDE path
-                atomicAdd(&ctr[1], (unsigned long long)nlive);     // (j,k) columns evaluated cell by cell
+                atomicAdd(&ctr[1], (unsigned long long)(nitems / G)); // (j,k) density columns evaluated cell by cell
                 atomicAdd(&ctr[2], (unsigned long long)nexp * G);  // x-axis exp() evaluations
                 atomicAdd(&ctr[3], (unsigned long long)nfact);     // (j,k) columns in factorised form
                 atomicAdd(&ctr[4], (unsigned long long)ntwo);      // direct columns evaluated with two of the four terms
-                // log() calls and plain FP64 flops (outside exp / log) of this evaluation, for the roofline numerator:
-                // pass A 2 G^2 logs, one per non-dead column in pass B, G per direct column in pass C, G for the z
-                // marginal, 1 in the table lookup; FMAs of passes A/B, 10 flop per direct cell (6 for a two-term one)
-                atomicAdd(&ctr[5], (unsigned long long)(2 * G * G + G + 1) + (unsigned long long)nlive * (G + 1) + nfact);
-                atomicAdd(&ctr[6], (unsigned long long)(G * G * 42 + 80) + (unsigned long long)nlive * G * 10 -
-                                       (unsigned long long)ntwo * G * 4 + (unsigned long long)nexp * G * 6);
+                // log() calls and plain FP64 flops (outside exp / log) of this evaluation.  CIC: pass A 2 logs per (i,k),
+                // one per cell of a direct column, 7 per lane in pass B and the y-z marginal + its direct entries, G for
+                // the z marginal, 1 in the table lookup; FMAs of pass A (~26 flop per cell), 10 flop per direct cell (6 when
+                // two-term).  IC / literal: one log per cell.
+                const unsigned long long GG = (unsigned long long)G * G;
+                const bool cols = (mode == RVL_MODE_CIC) && !P.literal;
+                atomicAdd(&ctr[5], cols ? 2ull * GG + nitems + 8ull * G + nyz + 1ull
+                                        : (mode == RVL_MODE_CIC ? (unsigned long long)nitems + 2ull * GG + G : GG + 2ull * G) + 1ull);
+                atomicAdd(&ctr[6], (cols ? 26ull * GG + 10ull * nitems - 4ull * (unsigned long long)ntwo * G + 60ull * G
+                                         : 10ull * (unsigned long long)nitems + 6ull * GG) + (unsigned long long)nexp * G * 6ull);
             }
         }
         if (rvl_ahead(score, f, best_v, best_i, P.negative)) { best_v = score; best_i = f; }
@@ -1141,8 +1265,8 @@ __device__ double rvl_assoc_block(const RvlParams &P, const RvlTarget &tg, const
             sh.S.A[lane][0] = b0; sh.S.A[lane][1] = 0.0; sh.S.A[lane][2] = b1; sh.S.A[lane][3] = 0.0;
         }
         __syncwarp();
-        int nlive, nfact, ntwo;
-        score = rvl_finish(sh.S, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, 0, lane, &nlive, &nfact, &ntwo);
+        int nitems, nyz, nfact, ntwo;
+        score = rvl_finish(sh.S, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, 0, lane, &nitems, &nyz, &nfact, &ntwo);
     }
     return score; // valid in warp 0
 }

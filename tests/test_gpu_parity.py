@@ -414,31 +414,41 @@ def test_duplicate_row_grouping_is_exact():
         assert np.array_equal(ra[k], rb_[k]), k
 
 
-def test_column_pruning_stays_within_its_bound(oracle):
-    """Default pruning (theta = 1e-14) against the exact rule (theta = 0): CMI may move by at most
-    theta*(|log eps'|+1) ~ 4e-13, i.e. IC = sqrt(1-exp(-2 CMI)) by <= 4e-13/IC."""
-    w = _workload(400, 1500)
-    with _ctx() as ctx:
-        ctx.set_profiling(True)
-        ctx.load_matrix(w["m2"])
-        ctx.set_targets(w["target"])
-        ctx.set_seed(w["seed"])
-        a = ctx.score_once()[0]
-        ca = ctx.counters(reset=True)
-        ctx.set_prune_theta(0.0)
-        b = ctx.score_once()[0]
-        cb = ctx.counters(reset=True)
-        with pytest.raises(Exception):
-            ctx.set_prune_theta(1e-3)
-    assert ca["live_columns"] < cb["live_columns"]
-    cmi_a = -0.5 * np.log1p(-a * a)
-    cmi_b = -0.5 * np.log1p(-b * b)
-    assert np.max(np.abs(cmi_a - cmi_b)) <= 1e-12
-    assert np.array_equal(np.sign(a), np.sign(b))
-    rows = np.arange(0, 1500, 10)
-    o = oracle.score_rows(w["target"], w["m2"][rows].astype(float), w["seed"].astype(float))
-    ok, err = score_close(a[rows], o)
-    assert ok, err
+def test_production_epilogue_equals_literal_cube(oracle):
+    """The production entropy epilogue (cell regimes: closed forms for the big / small densities, a log only
+    for the few in between) against the literal cell-by-cell cube of the validation mode, on the same x-axis
+    sums: CMI may differ by rounding only.  The literal mode's mass-based column pruning (rvl_set_prune_theta)
+    is checked against its bound theta*(|log eps'|+1) as well."""
+    for n, F in ((400, 1500), (82, 600), (1000, 800)):
+        w = _workload(n, F)
+        rng = np.random.default_rng(n)
+        m2 = w["m2"].copy()
+        for r, p in zip(range(5, 5 + 6), (0.1, 0.25, 0.5, 0.75, 0.9, 0.97)):     # dense rows: both y-classes visible
+            m2[r] = rng.random(n) < p
+        with _ctx() as ctx:
+            ctx.set_profiling(True)
+            ctx.load_matrix(m2)
+            ctx.set_targets(w["target"])
+            ctx.set_seed(w["seed"])
+            a = ctx.score_once()[0]
+            ca = ctx.counters(reset=True)
+            ctx.set_dense_x(True)
+            ctx.set_prune_theta(0.0)
+            b = ctx.score_once()[0]
+            cb = ctx.counters(reset=True)
+            ctx.set_prune_theta(1e-14)
+            c = ctx.score_once()[0]
+            with pytest.raises(Exception):
+                ctx.set_prune_theta(1e-3)
+        assert ca["logs"] < cb["logs"]
+        cmi_a, cmi_b, cmi_c = (-0.5 * np.log1p(-v * v) for v in (a, b, c))
+        assert np.max(np.abs(cmi_a - cmi_b)) <= 2e-14, (n, np.max(np.abs(cmi_a - cmi_b)))
+        assert np.max(np.abs(cmi_c - cmi_b)) <= 1e-12
+        assert np.array_equal(np.sign(a), np.sign(b))
+        rows = np.arange(0, F, 10)
+        o = oracle.score_rows(w["target"], m2[rows].astype(float), w["seed"].astype(float))
+        ok, err = score_close(a[rows], o)
+        assert ok, err
 
 
 # ------------------------------------------------------------------ target batches and the permutation null
