@@ -355,11 +355,13 @@ class Bench:
             use_p2p, use_nccl, send, recv = self.connect(ctx)
 
         def one_search():
+            if not use_nccl:       # one persistent launch per search (k_search); ranks meet through peer memory inside it
+                ctx.search_run(iters)
+                return
             ctx.search_begin(iters)
             for it in range(iters):
                 ctx.iter_score(it)
-                if use_nccl:
-                    dist.all_gather_into_tensor(recv, send)
+                dist.all_gather_into_tensor(recv, send)
                 ctx.iter_merge(it)
 
         for _ in range(warmup):

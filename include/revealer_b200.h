@@ -202,6 +202,14 @@ int rvl_p2p_disable(rvl_ctx *ctx);
  * seed ICs identical on every context). */
 int rvl_group_connect(rvl_ctx **ctxs, int n);
 int rvl_group_search(rvl_ctx **ctxs, int n, int iters);
+/* The whole search of this shard enqueued without waiting (rvl_search_fetch / rvl_synchronize wait): ONE persistent
+ * cooperative launch (k_search: score, rank, peer exchange over NVLink, merge and table update of every iteration
+ * inside the kernel) when the device allows it, the split-phase launches otherwise.  world > 1 needs the peer exchange
+ * (rvl_p2p_import or rvl_group_connect) and every rank must call it.  Results are bit-identical either way. */
+int rvl_search_run(rvl_ctx *ctx, int iters);
+/* on = 0 keeps rvl_search / rvl_search_run / rvl_group_search on the split-phase launches (validation, profiling of
+ * the individual kernels).  Default 1. */
+int rvl_set_fused(rvl_ctx *ctx, int on);
 int rvl_search_begin(rvl_ctx *ctx, int iters);
 size_t rvl_candidate_bytes(const rvl_ctx *ctx);
 int rvl_set_exchange_buffers(rvl_ctx *ctx, void *dev_send, void *dev_recv);
@@ -215,9 +223,13 @@ int rvl_synchronize(rvl_ctx *ctx);
 int rvl_assoc(rvl_ctx *ctx, int64_t target_index, const uint8_t *y, int64_t n, double *out_ic);
 
 /* Permutation p-values, LIB:1868-1869: pval[i] = #(cmi_rand > cmi[i]) / n_rand, on the device
- * (sort + binary search instead of the O(F^2 n.perm) scan). */
+ * (sort + binary search instead of the O(F^2 n.perm) scan).  A NaN score gives a NaN p-value (R: NA). */
 int rvl_pvalues(rvl_ctx *ctx, const double *cmi, int64_t F, const double *cmi_rand, int64_t n_rand,
                 double *out_pval);
+/* The same for iteration `iter` (0-based) of the last search, from the scores still resident in HBM: target 0's
+ * scores against the scores of the permutation-null targets (rvl_set_null_targets) -- no score crosses PCIe, only
+ * the F p-values come back.  A NaN score gives a NaN p-value (R: NA).  Single shard only. */
+int rvl_pvalues_iter(rvl_ctx *ctx, int iter, double *out_pval);
 
 /* ---- introspection (parity tests, INTEGRATION checks) ----------------------------------- */
 
@@ -263,6 +275,10 @@ int rvl_get_counters(rvl_ctx *ctx, uint64_t *out4, int reset);
  * evaluated with two of the four class terms (the other y-class cannot change fl(Q) anywhere in the column),
  * out[5] log() evaluations, out[6] FP64 flops outside exp() and log() (an FMA counts 2).  Needs rvl_set_profiling. */
 int rvl_get_counters_ex(rvl_ctx *ctx, uint64_t *out, int n_out, int reset);
+/* Development aid: nanosecond (globaltimer) stamps of the phases of the last rvl_search_run's k_search launch, out[iters][8]:
+ * [0] block 0 starts scoring, [1] block 0 done, [2] every block done, [3] candidate records + stamps published,
+ * [4] block 0's merge tasks done, [5] grid barrier passed.  Call once with out == NULL to arm the recording. */
+int rvl_debug_phase_times(rvl_ctx *ctx, unsigned long long *out, int iters);
 /* FP64 FMA peak of this device by a DFMA-chain micro-benchmark (TFLOP/s); the denominator of the
  * roofline bench.py reports, since the path is FP64-compute-bound. */
 int rvl_measure_fp64_peak(rvl_ctx *ctx, double *out_tflops);

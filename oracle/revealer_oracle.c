@@ -659,10 +659,14 @@ void orc_search(const double *target, const double *m2, int64_t F, int n, double
     }
 }
 
-/* p.val[i] = sum(cmi.rand > cmi[i]) / (F*n.perm)   LIB:1868-1869 (O(F^2 n.perm) in R). */
+/* p.val[i] = sum(cmi.rand > cmi[i]) / (F*n.perm)   LIB:1868-1869 (O(F^2 n.perm) in R).  A NaN score makes every
+ * comparison NA in R and sum() of NAs is NA: NaN here.  NaN null scores are NA comparisons as well -- R's sum would be
+ * NA for EVERY row then; the reference never removes them (no na.rm), so neither case is reachable on valid input;
+ * the null-side NaNs are simply not counted. */
 void orc_pvals(const double *cmi, int64_t F, const double *cmi_rand, int64_t nrand, double *pval)
 {
     for (int64_t i = 0; i < F; i++) {
+        if (isnan(cmi[i])) { pval[i] = NAN; continue; }
         int64_t c = 0;
         for (int64_t r = 0; r < nrand; r++) c += (cmi_rand[r] > cmi[i]);
         pval[i] = (double)c / (double)nrand;

@@ -71,6 +71,8 @@ SIGNATURES = {
     "rvl_p2p_disable": (_i, [_vp]),
     "rvl_group_connect": (_i, [C.POINTER(_vp), _i]),
     "rvl_group_search": (_i, [C.POINTER(_vp), _i, _i]),
+    "rvl_search_run": (_i, [_vp, _i]),
+    "rvl_set_fused": (_i, [_vp, _i]),
     "rvl_search_begin": (_i, [_vp, _i]),
     "rvl_candidate_bytes": (C.c_size_t, [_vp]),
     "rvl_set_exchange_buffers": (_i, [_vp, _vp, _vp]),
@@ -80,6 +82,7 @@ SIGNATURES = {
     "rvl_synchronize": (_i, [_vp]),
     "rvl_assoc": (_i, [_vp, _i64, _u8p, _i64, _dp]),
     "rvl_pvalues": (_i, [_vp, _dp, _i64, _dp, _i64, _dp]),
+    "rvl_pvalues_iter": (_i, [_vp, _i, _dp]),
     "rvl_get_target_bandwidth": (_i, [_vp, _i64, _dp]),
     "rvl_get_binary_bandwidth_table": (_i, [_vp, _dp]),
     "rvl_get_matrix_dims": (_i, [_vp, _i64p, _i64p]),
@@ -94,6 +97,7 @@ SIGNATURES = {
     "rvl_get_counters": (_i, [_vp, _u64p, _i]),
     "rvl_get_counters_ex": (_i, [_vp, _u64p, _i, _i]),
     "rvl_measure_fp64_peak": (_i, [_vp, _dp]),
+    "rvl_debug_phase_times": (_i, [_vp, _u64p, _i]),
 }
 
 _LIB = None

@@ -349,6 +349,14 @@ class RevealerContext:
         self._ck(self._lib.rvl_search(self._h, int(iters), C.byref(r)))
         return res
 
+    def search_run(self, iters):
+        """Enqueue the whole search of this shard (one persistent launch when possible); search_fetch waits."""
+        self._ck(self._lib.rvl_search_run(self._h, int(iters)))
+
+    def set_fused(self, on):
+        """on=False keeps the search on the split-phase launches (k_score / k_argmax / k_advance per iteration)."""
+        self._ck(self._lib.rvl_set_fused(self._h, int(bool(on))))
+
     # split-phase (sharded) form
     def search_begin(self, iters):
         self._ck(self._lib.rvl_search_begin(self._h, int(iters)))
@@ -402,6 +410,12 @@ class RevealerContext:
         r = np.ascontiguousarray(np.ravel(cmi_rand), dtype=np.float64)
         out = np.empty(len(c), dtype=np.float64)
         self._ck(self._lib.rvl_pvalues(self._h, _dp(c), len(c), _dp(r), len(r), _dp(out)))
+        return out
+
+    def pvalues_iter(self, it):
+        """p-values of iteration `it` of the last search from the resident scores (rvl_pvalues_iter)."""
+        out = np.empty(self.F, dtype=np.float64)
+        self._ck(self._lib.rvl_pvalues_iter(self._h, int(it), _dp(out)))
         return out
 
     # -- introspection
@@ -533,7 +547,8 @@ def revealer_search(target, m2, seed=None, max_n_iter=5, target_match="positive"
         out["top_markers"] = out["order"][:, :n_markers]
         if target_rand is not None:
             out["cmi_rand"] = np.transpose(res["cmi"][1:], (1, 2, 0)).copy()  # iters x F x n.perm
-            out["p_val"] = np.stack([ctx.pvalues(cmi[:, it], out["cmi_rand"][it]) for it in range(max_n_iter)])
+            # p-values on the scores still resident in HBM (LIB:1868-1869); NaN score -> NaN p-value (R: NA)
+            out["p_val"] = np.stack([ctx.pvalues_iter(it) for it in range(max_n_iter)])
             # FDR as REVEALER.v1 reports it (LIB:1870-1878): BH on p and on 1-p; rows with a negative score
             # take the lower-tail pair.  Display-side bookkeeping on F numbers: host numpy, like R's p.adjust.
             fdr = np.stack([p_adjust_fdr(p) for p in out["p_val"]])

@@ -67,11 +67,13 @@ void rvl_launch_advance(const RvlParams *P, RvlTarget *tg, const double *u_all, 
                         uint64_t *seeds_out, const double *bcvtab, double *tt, RvlCandHead *slots, int nslots,
                         unsigned long long *work, const unsigned char *recv, size_t rec_bytes, int iter, int iters,
                         int first_null, int64_t *top, double *top_score, uint64_t *seed_iter, int allow_incr,
-                        const RvlPeerXchg *X, const uint64_t *bits, int fuse_rank, cudaStream_t st);
+                        const RvlPeerXchg *X, cudaStream_t st);
 void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaStream_t st);
 void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of, const double *u_all,
                       const double *xc_all, const uint64_t *y_all, const double *bcvtab, double *out,
-                      size_t y_stride, size_t out_stride, cudaStream_t st);
+                      size_t y_stride, size_t out_stride, int t_div, cudaStream_t st);
+cudaError_t rvl_search_configure(size_t smem, int device, int *grid_out);
+cudaError_t rvl_launch_search(const RvlSearchArgs *a, int grid_x, size_t smem, cudaStream_t st);
 void rvl_launch_argmax(const RvlParams *P, const RvlCandHead *part, int nparts, const uint64_t *bits,
                        unsigned char *send, size_t rec_bytes, const RvlPeerXchg *X, cudaStream_t st);
 void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols, int words,
@@ -172,6 +174,23 @@ struct rvl_ctx {
     bool p2p = false;
     int *d_xerr = nullptr;
     unsigned int epoch = 0;
+
+    // fused search (k_search): one persistent cooperative launch per search
+    int fused = 1;                  // rvl_set_fused
+    int search_grid_x = -1;         // -1: not configured; 0: cooperative launch unavailable
+    size_t search_smem = 0;
+    unsigned long long *d_swork = nullptr; // [sctr_cap] per-iteration item counters
+    unsigned int *d_sdone = nullptr;       // [sctr_cap] per-iteration block tickets, then the barrier counter
+    int sctr_cap = 0;
+    unsigned char *d_self_xchg = nullptr;  // world == 1: the "exchange" buffer the last block publishes into
+    unsigned char **d_self_peers = nullptr;
+    size_t self_xchg_bytes = 0, self_stamps_off = 0;
+    int self_T = 0, self_words = 0;
+    int xseq = 0, seq0 = 0;         // exchanges issued so far / before the current search: the parity slot runs on across searches
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> search_events; // profiling: one pair per k_search launch
+    size_t search_events_used = 0;
+    int last_search_iters = 0;
+    unsigned long long *d_phase_dbg = nullptr; // rvl_debug_phase_times: [64][8] globaltimer stamps of the last k_search
 
     // per-CTA bests of the last k_score launch [T][score_grid_x]; side stream for the seed IC
     RvlCandHead *d_part = nullptr;
@@ -357,6 +376,8 @@ extern "C" void rvl_destroy(rvl_ctx *ctx)
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     dfree(ctx->d_part);
     dfree(ctx->d_work);
+    dfree(ctx->d_swork); dfree(ctx->d_sdone); dfree(ctx->d_self_xchg); dfree(ctx->d_self_peers); dfree(ctx->d_phase_dbg);
+    for (auto &p : ctx->search_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1097,7 +1118,7 @@ static int prep_iteration(rvl_ctx *ctx)
     RvlPeerXchg Xnone;
     memset(&Xnone, 0, sizeof Xnone);
     rvl_launch_advance(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_seed_alt, ctx->d_bcvtab, ctx->d_tt, ctx->d_part, nslots,
-                       ctx->d_work, nullptr, 0, 0, 1, ctx->first_null, nullptr, nullptr, nullptr, 0, &Xnone, ctx->d_bits, 0, ctx->stream);
+                       ctx->d_work, nullptr, 0, 0, 1, ctx->first_null, nullptr, nullptr, nullptr, 0, &Xnone, ctx->stream);
     ctx->work_dirty = false;
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1139,7 +1160,7 @@ static RvlPeerXchg make_xchg(const rvl_ctx *c, int iter)
     X.local = c->d_xchg;
     X.stamps_off = c->xchg_stamps_off;
     X.stamp = (c->epoch << 16) | (unsigned int)(iter + 1);
-    X.parity = iter & 1;
+    X.parity = (c->seq0 + iter) & 1; // the slot alternates across searches too: reuse is ordered by the stamp chain
     X.err = c->d_xerr;
     return X;
 }
@@ -1217,7 +1238,6 @@ static int join_side(rvl_ctx *ctx)
 // A peer-exchange stamp that never arrived (k_advance's bounded wait) is an error, not a silent result.
 static int check_xerr(rvl_ctx *ctx)
 {
-    if (!ctx->p2p) return RVL_OK;
     int h = 0;
     CK(cudaMemcpy(&h, ctx->d_xerr, sizeof(int), cudaMemcpyDeviceToHost));
     if (h) {
@@ -1229,6 +1249,12 @@ static int check_xerr(rvl_ctx *ctx)
 
 static int drain_score_events(rvl_ctx *ctx)
 {
+    for (size_t i = 0; i < ctx->search_events_used; i++) { // a k_search launch counts as one launch of the dominant kernel
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, ctx->search_events[i].first, ctx->search_events[i].second);
+        if (e == cudaSuccess) { ctx->score_ms += ms; ctx->score_launches++; }
+    }
+    ctx->search_events_used = 0;
     for (size_t i = 0; i < ctx->score_events_used; i++) {
         float ms = 0.f;
         cudaError_t e = cudaEventElapsedTime(&ms, ctx->score_events[i].first, ctx->score_events[i].second);
@@ -1262,7 +1288,9 @@ extern "C" int rvl_search_begin(rvl_ctx *ctx, int iters)
         return fail(ctx, RVL_ERR_STATE, "peer exchange was set up for another shape: call rvl_p2p_export/import again");
     if (!ctx->p2p && (!ctx->d_send || !ctx->d_recv))
         return fail(ctx, RVL_ERR_STATE, "world > 1 needs rvl_set_exchange_buffers or rvl_p2p_import");
-    if (ctx->p2p) ctx->epoch = (ctx->epoch + 1) & 0x7fff;
+    ctx->epoch = (ctx->epoch + 1) & 0x7fff;
+    ctx->seq0 = ctx->xseq;
+    ctx->xseq = (ctx->xseq + iters) & 0x3fffffff;
     RvlParams P = make_params(ctx);
     CK(cudaMemcpyAsync(ctx->d_seed, ctx->d_seed0, sizeof(uint64_t) * (size_t)ctx->T * ctx->words, cudaMemcpyDeviceToDevice, ctx->stream));
     rc = prep_iteration(ctx);
@@ -1272,7 +1300,7 @@ extern "C" int rvl_search_begin(rvl_ctx *ctx, int iters)
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
     rvl_launch_assoc(&P, ctx->T, ctx->d_tg, nullptr, ctx->d_u, ctx->d_xc, ctx->d_seed0, ctx->d_bcvtab, ctx->d_ic0,
-                     (size_t)ctx->words, 1, ctx->side);
+                     (size_t)ctx->words, 1, 0, ctx->side);
     ctx->side_pending = true;
     ctx->launches += 1;
     CK(cudaGetLastError());
@@ -1306,7 +1334,7 @@ extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
     rvl_launch_advance(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_seed_alt, ctx->d_bcvtab, ctx->d_tt, ctx->d_part,
                        ctx->score_grid_x * rvl_score_warps(), ctx->d_work, ctx->p2p ? ctx->d_xchg : ctx->d_recv,
                        sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, iter, ctx->iters, ctx->first_null,
-                       ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, 1, &X, ctx->d_bits, 0, ctx->stream);
+                       ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, 1, &X, ctx->stream);
     { uint64_t *tmp = ctx->d_seed; ctx->d_seed = ctx->d_seed_alt; ctx->d_seed_alt = tmp; }
     ctx->work_dirty = false;
     ctx->launches += 1;
@@ -1317,7 +1345,7 @@ extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
     rvl_launch_assoc(&P, nreal, ctx->d_tg, nullptr, ctx->d_u, ctx->d_xc, ctx->d_seed_iter + (size_t)iter * ctx->words,
-                     ctx->d_bcvtab, ctx->d_cmi_seed + iter, (size_t)ctx->iters * ctx->words, (size_t)ctx->iters,
+                     ctx->d_bcvtab, ctx->d_cmi_seed + iter, (size_t)ctx->iters * ctx->words, (size_t)ctx->iters, 0,
                      ctx->side);
     ctx->launches += 1;
     ctx->side_pending = true;
@@ -1376,11 +1404,118 @@ extern "C" int rvl_search_fetch(rvl_ctx *ctx, rvl_result *out)
     return RVL_OK;
 }
 
-extern "C" int rvl_search(rvl_ctx *ctx, int iters, rvl_result *out)
+// world == 1: the last block of k_search publishes into a local buffer laid out like a peer exchange buffer of one rank.
+static int ensure_self_xchg(rvl_ctx *ctx)
+{
+    if (ctx->d_self_xchg && ctx->self_T == ctx->T && ctx->self_words == ctx->words) return RVL_OK;
+    dfree(ctx->d_self_xchg);
+    dfree(ctx->d_self_peers);
+    size_t rec = sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words;
+    size_t recs = 2 * (size_t)ctx->T * rec;
+    ctx->self_stamps_off = (recs + 255) & ~(size_t)255;
+    ctx->self_xchg_bytes = ctx->self_stamps_off + 2 * (size_t)ctx->T * sizeof(unsigned int);
+    CK(cudaMalloc((void **)&ctx->d_self_xchg, ctx->self_xchg_bytes));
+    CK(cudaMemset(ctx->d_self_xchg, 0, ctx->self_xchg_bytes));
+    CK(dalloc(&ctx->d_self_peers, 1));
+    CK(cudaMemcpy(ctx->d_self_peers, &ctx->d_self_xchg, sizeof(unsigned char *), cudaMemcpyHostToDevice));
+    ctx->self_T = ctx->T; ctx->self_words = ctx->words;
+    return RVL_OK;
+}
+
+// Can this context run the search as one k_search launch?  (cooperative launch available; with world > 1 the candidate
+// exchange must be the peer-memory one -- an NCCL all-gather cannot be called from inside a kernel.)
+static bool fused_possible(rvl_ctx *ctx)
+{
+    if (!ctx->fused || ctx->F < 0 || ctx->T <= 0) return false;
+    if (ctx->world > 1 && !ctx->p2p) return false;
+    size_t smem = rvl_score_smem_bytes(ctx->n, ctx->words);
+    if (ctx->search_grid_x < 0 || smem != ctx->search_smem) {
+        int grid = 0;
+        if (rvl_search_configure(smem, ctx->device, &grid) != cudaSuccess) { cudaGetLastError(); grid = 0; }
+        ctx->search_grid_x = grid;
+        ctx->search_smem = smem;
+    }
+    return ctx->search_grid_x > 0;
+}
+
+// The whole search enqueued as ONE launch (k_search) + one batched launch of the seed ICs.  Asynchronous.
+static int search_enqueue_fused(rvl_ctx *ctx, int iters)
+{
+    int rc = rvl_search_begin(ctx, iters); // seeds, initial seed state + table, assoc(target, initial seed), epoch / slot parity
+    if (rc) return rc;
+    if (ctx->world == 1 && !ctx->p2p) {
+        rc = ensure_self_xchg(ctx);
+        if (rc) return rc;
+    }
+    if (ctx->d_phase_dbg && iters > 64) return fail(ctx, RVL_ERR_ARG, "phase timing is armed: iters <= 64");
+    if (iters > ctx->sctr_cap) {
+        dfree(ctx->d_swork); dfree(ctx->d_sdone);
+        ctx->sctr_cap = 0;
+        CK(dalloc(&ctx->d_swork, (size_t)iters));
+        CK(dalloc(&ctx->d_sdone, 2 * (size_t)iters + 1));
+        ctx->sctr_cap = iters;
+    }
+    CK(cudaMemsetAsync(ctx->d_swork, 0, sizeof(unsigned long long) * (size_t)iters, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_sdone, 0, sizeof(unsigned int) * (2 * (size_t)iters + 1), ctx->stream));
+    // the k_search grid equals the k_score grid the best slots were sized for (same block shape and shared memory)
+    if ((size_t)ctx->T * (size_t)ctx->search_grid_x * rvl_score_warps() > ctx->part_cap)
+        return fail(ctx, RVL_ERR_STATE, "internal: k_search grid exceeds the best-slot buffer");
+    RvlSearchArgs a;
+    memset(&a, 0, sizeof a);
+    a.P = make_params(ctx);
+    a.bits = ctx->d_bits; a.u_all = ctx->d_u; a.xc_all = ctx->d_xc; a.tg_all = ctx->d_tg;
+    a.seed_a = ctx->d_seed; a.seed_b = ctx->d_seed_alt;
+    a.bcvtab = ctx->d_bcvtab; a.tt = ctx->d_tt; a.scores = ctx->d_scores; a.part = ctx->d_part;
+    a.work = ctx->d_swork; a.done = ctx->d_sdone; a.bar = ctx->d_sdone + iters; a.need = ctx->d_sdone + iters + 1;
+    a.ctr = ctx->profiling ? ctx->d_ctr : nullptr;
+    a.uniq = ctx->dedup ? ctx->d_uniq : nullptr; a.U = ctx->U;
+    a.rec_bytes = sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words;
+    a.iters = iters; a.first_null = ctx->first_null; a.nreal = ctx->first_null > 0 ? ctx->first_null : ctx->T;
+    a.top = ctx->d_top; a.top_score = ctx->d_top_score; a.seed_iter = ctx->d_seed_iter;
+    if (ctx->p2p) a.X = make_xchg(ctx, 0);
+    else {
+        a.X.peers = ctx->d_self_peers; a.X.local = ctx->d_self_xchg; a.X.stamps_off = ctx->self_stamps_off;
+        a.X.err = ctx->d_xerr; a.X.stamp = 0; a.X.parity = 0;
+    }
+    a.epoch = ctx->epoch; a.seq0 = ctx->seq0;
+    a.dbg = ctx->d_phase_dbg;
+    const bool prof = ctx->profiling != 0;
+    if (prof && ctx->search_events_used == ctx->search_events.size()) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        ctx->search_events.push_back({e0, e1});
+    }
+    if (prof) CK(cudaEventRecord(ctx->search_events[ctx->search_events_used].first, ctx->stream));
+    if (ctx->F > 0 || ctx->world > 1) CK(rvl_launch_search(&a, ctx->search_grid_x, ctx->search_smem, ctx->stream));
+    if (prof) CK(cudaEventRecord(ctx->search_events[ctx->search_events_used++].second, ctx->stream));
+    ctx->launches++;
+    if (iters & 1) { uint64_t *tmp = ctx->d_seed; ctx->d_seed = ctx->d_seed_alt; ctx->d_seed_alt = tmp; }
+    ctx->work_dirty = true;
+    ctx->fill_pending = ctx->dedup && ctx->U < ctx->F;
+    // cmi.seed[iter] <- assoc(target, seed) (LIB:2170) for every iteration at once, from the seed.iter rows k_search wrote
+    RvlParams P = a.P;
+    rvl_launch_assoc(&P, a.nreal * iters, ctx->d_tg, nullptr, ctx->d_u, ctx->d_xc, ctx->d_seed_iter, ctx->d_bcvtab, ctx->d_cmi_seed,
+                     (size_t)ctx->words, 1, iters, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return RVL_OK;
+}
+
+// The whole search of this shard, enqueued without waiting: one persistent launch (k_search) when possible, the
+// split-phase launches otherwise.  With world > 1 this needs the peer exchange (rvl_p2p_import / rvl_group_connect)
+// and every rank must call it; rvl_search_fetch / rvl_synchronize wait for the result.
+extern "C" int rvl_search_run(rvl_ctx *ctx, int iters)
 {
     GUARD();
-    if (ctx->world != 1) return fail(ctx, RVL_ERR_STATE, "rvl_search is the single-shard driver; use the split-phase calls when world > 1");
-    int rc = rvl_search_begin(ctx, iters);
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (iters < 1) return fail(ctx, RVL_ERR_ARG, "iters < 1");
+    if (ctx->world > 1 && !ctx->p2p)
+        return fail(ctx, RVL_ERR_STATE, "rvl_search_run with world > 1 needs the peer exchange (rvl_p2p_import / rvl_group_connect); "
+                                        "use rvl_iter_score / rvl_iter_merge around your own all-gather otherwise");
+    if (fused_possible(ctx) && (ctx->F > 0 || ctx->world > 1)) return search_enqueue_fused(ctx, iters);
+    rc = rvl_search_begin(ctx, iters);
     if (rc) return rc;
     for (int it = 0; it < iters; it++) { // enqueued back to back: no host round-trip inside the loop
         rc = rvl_iter_score(ctx, it);
@@ -1388,6 +1523,39 @@ extern "C" int rvl_search(rvl_ctx *ctx, int iters, rvl_result *out)
         rc = rvl_iter_merge(ctx, it);
         if (rc) return rc;
     }
+    return RVL_OK;
+}
+
+// Development aid (tools/time_phases.py): out[iters][8] nanosecond stamps of the last fused search's phases -- [0] block 0
+// starts scoring, [1] block 0 done scoring, [2] every block done, [3] records + stamps published, [4] block 0's merge
+// tasks done, [5] grid barrier passed.  First call (out == NULL) arms the recording for the following searches.
+extern "C" int rvl_debug_phase_times(rvl_ctx *ctx, unsigned long long *out, int iters)
+{
+    GUARD();
+    if (!ctx->d_phase_dbg) {
+        CK(dalloc(&ctx->d_phase_dbg, (size_t)64 * 8));
+        CK(cudaMemset(ctx->d_phase_dbg, 0, sizeof(unsigned long long) * 64 * 8));
+    }
+    if (!out) return RVL_OK;
+    if (iters < 1 || iters > 64) return fail(ctx, RVL_ERR_ARG, "iters must be in [1, 64]");
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, ctx->d_phase_dbg, sizeof(unsigned long long) * 8 * (size_t)iters, cudaMemcpyDeviceToHost));
+    return RVL_OK;
+}
+
+extern "C" int rvl_set_fused(rvl_ctx *ctx, int on)
+{
+    GUARD();
+    ctx->fused = on ? 1 : 0;
+    return RVL_OK;
+}
+
+extern "C" int rvl_search(rvl_ctx *ctx, int iters, rvl_result *out)
+{
+    GUARD();
+    if (ctx->world != 1) return fail(ctx, RVL_ERR_STATE, "rvl_search is the single-shard driver; use rvl_search_run or the split-phase calls when world > 1");
+    int rc = rvl_search_run(ctx, iters);
+    if (rc) return rc;
     if (out) return rvl_search_fetch(ctx, out);
     return rvl_synchronize(ctx);
 }
@@ -1437,7 +1605,7 @@ extern "C" int rvl_assoc(rvl_ctx *ctx, int64_t target_index, const uint8_t *y, i
     RvlParams P = make_params(ctx);
     cudaMemcpyAsync(d_y, packed.data(), sizeof(uint64_t) * ctx->words, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_t, &ti, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-    rvl_launch_assoc(&P, 1, ctx->d_tg, d_t, ctx->d_u, ctx->d_xc, d_y, ctx->d_bcvtab, d_o, (size_t)ctx->words, 1, ctx->stream);
+    rvl_launch_assoc(&P, 1, ctx->d_tg, d_t, ctx->d_u, ctx->d_xc, d_y, ctx->d_bcvtab, d_o, (size_t)ctx->words, 1, 0, ctx->stream);
     ctx->launches++;
     cudaMemcpyAsync(out_ic, d_o, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -1477,6 +1645,54 @@ extern "C" int rvl_pvalues(rvl_ctx *ctx, const double *cmi, int64_t F, const dou
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_c); cudaFree(d_r); cudaFree(d_p);
     if (e != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "rvl_pvalues: %s", cudaGetErrorString(e));
+    return RVL_OK;
+}
+
+// p-values of one iteration of the last search from the scores ALREADY in HBM (LIB:1868-1869): target 0's scores are
+// cmi[, iter], the permutation-null targets' scores are cmi.rand -- contiguous in the [iters][T][F] score buffer, so
+// nothing is downloaded or uploaded except the F p-values.  The null scores are sorted in a scratch copy.
+extern "C" int rvl_pvalues_iter(rvl_ctx *ctx, int iter, double *out_pval)
+{
+    GUARD();
+    if (!out_pval) return fail(ctx, RVL_ERR_ARG, "out_pval is NULL");
+    if (ctx->iters < 1 || iter < 0 || iter >= ctx->iters) return fail(ctx, RVL_ERR_STATE, "no search result for iteration %d", iter);
+    if (ctx->first_null != 1 || ctx->T < 2) return fail(ctx, RVL_ERR_STATE, "the last search had no permutation-null targets (rvl_set_null_targets)");
+    if (ctx->world != 1) return fail(ctx, RVL_ERR_STATE, "rvl_pvalues_iter needs the null scores of every row: single shard only (gather and use rvl_pvalues)");
+    const int64_t F = ctx->F, n_rand = (int64_t)(ctx->T - 1) * F;
+    if (F < 1) return RVL_OK;
+    int jrc = join_side(ctx);
+    if (jrc) return jrc;
+    if (ctx->fill_pending) { // duplicate rows get their group's score first (they count in the null distribution too)
+        rvl_launch_fill_duplicates(ctx->d_scores, F, (int64_t)ctx->iters * ctx->T, ctx->d_rep, ctx->stream);
+        ctx->launches++;
+        ctx->fill_pending = false;
+    }
+    const double *base = ctx->d_scores + (size_t)iter * ctx->T * F;
+    double *d_r = nullptr, *d_p = nullptr;
+    CK(dalloc(&d_r, (size_t)n_rand));
+    CK(dalloc(&d_p, (size_t)F));
+    int64_t n_valid = 0;
+    cudaError_t e = cudaMemcpyAsync(d_r, base + F, sizeof(double) * (size_t)n_rand, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        try {
+            rvl_pool_alloc alloc{ctx};
+            auto pol = thrust::cuda::par(alloc).on(ctx->stream);
+            thrust::device_ptr<double> r(d_r);
+            auto mid = thrust::partition(pol, r, r + n_rand, rvl_not_nan());
+            n_valid = mid - r;
+            thrust::sort(pol, r, r + n_valid);
+        } catch (...) {
+            cudaFree(d_r); cudaFree(d_p);
+            return fail(ctx, RVL_ERR_CUDA, "device sort failed");
+        }
+        rvl_launch_pvalues(base, F, d_r, n_valid, n_rand, d_p, ctx->stream);
+        ctx->launches += 3;
+        e = cudaMemcpyAsync(out_pval, d_p, sizeof(double) * (size_t)F, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_r); cudaFree(d_p);
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return fail(ctx, RVL_ERR_CUDA, "rvl_pvalues_iter: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
     return RVL_OK;
 }
 
@@ -1731,19 +1947,31 @@ extern "C" int rvl_group_connect(rvl_ctx **ctxs, int n)
 extern "C" int rvl_group_search(rvl_ctx **ctxs, int n, int iters)
 {
     if (!ctxs || n < 1) return RVL_ERR_ARG;
+    bool fused = true;
     for (int i = 0; i < n; i++) {
         if (n > 1 && !ctxs[i]->p2p) return fail(ctxs[i], RVL_ERR_STATE, "rvl_group_search: call rvl_group_connect first");
-        int rc = rvl_search_begin(ctxs[i], iters);
-        if (rc) return rc;
+        cudaSetDevice(ctxs[i]->device);
+        fused = fused && fused_possible(ctxs[i]);
     }
-    for (int it = 0; it < iters; it++) {
+    if (fused) { // one persistent launch per device; they meet through the stamped peer exchange inside k_search
         for (int i = 0; i < n; i++) {
-            int rc = rvl_iter_score(ctxs[i], it);
+            int rc = rvl_search_run(ctxs[i], iters);
             if (rc) return rc;
         }
+    } else {
         for (int i = 0; i < n; i++) {
-            int rc = rvl_iter_merge(ctxs[i], it);
+            int rc = rvl_search_begin(ctxs[i], iters);
             if (rc) return rc;
+        }
+        for (int it = 0; it < iters; it++) {
+            for (int i = 0; i < n; i++) {
+                int rc = rvl_iter_score(ctxs[i], it);
+                if (rc) return rc;
+            }
+            for (int i = 0; i < n; i++) {
+                int rc = rvl_iter_merge(ctxs[i], it);
+                if (rc) return rc;
+            }
         }
     }
     for (int i = 0; i < n; i++) {

@@ -76,6 +76,35 @@ struct RvlParams {
     double prune_theta; // density columns holding < theta/G^3 of the mass are replaced by the eps floor
 };
 
+// Arguments of k_search (score.cu): the whole search in one persistent cooperative launch.
+struct RvlSearchArgs {
+    RvlParams P;
+    const uint64_t *bits;
+    const double *u_all, *xc_all;
+    RvlTarget *tg_all;
+    uint64_t *seed_a, *seed_b;     // iteration `it` reads (it & 1 ? b : a) and writes the other
+    const double *bcvtab;
+    double *tt;
+    double *scores;                // [iters][T][F]
+    RvlCandHead *part;
+    unsigned long long *work;      // [iters] item counters, zeroed before the launch
+    unsigned int *done;            // [iters] block tickets, zeroed before the launch
+    unsigned int *bar;             // grid barrier counter, zeroed before the launch
+    unsigned int *need;            // [iters] set when an iteration's merge needs a table rebuild, zeroed before the launch
+    unsigned long long *ctr;
+    const int64_t *uniq;
+    int64_t U;
+    size_t rec_bytes;
+    int iters, first_null, nreal;  // nreal: targets that own a seed (the others are permutation nulls)
+    int64_t *top;
+    double *top_score;
+    uint64_t *seed_iter;
+    RvlPeerXchg X;                 // peers / local / stamps_off / err; stamp and parity are set per iteration here
+    unsigned int epoch;
+    int seq0;                      // exchanges issued before this search (parity continues across searches)
+    unsigned long long *dbg;       // NULL, or [iters][8] globaltimer stamps of the phases (tools/time_phases.py)
+};
+
 #define RVL_TT_STENCIL 8   // Lagrange points
 #define RVL_TT_PAD 4       // nodes beyond each end of [0, tau_max]
 #define RVL_TT_INV_DT 128  // nodes per unit of tau = -2 ln c

@@ -73,16 +73,37 @@ __device__ __forceinline__ bool rvl_ahead(double va, int64_t ia, double vb, int6
     return ia < ib;
 }
 
+// Loads of data that ANOTHER block of the same launch may have written (k_search: the x-axis table, the seeds, the
+// per-iteration seed state, the candidate records): COH = true goes to L2 (ld.global.cg) instead of a possibly stale
+// L1 line; COH = false is the plain load of the split-phase kernels, whose inputs are constant during a launch.
+template <bool COH> __device__ __forceinline__ double rvl_ld(const double *p) { return COH ? __ldcg(p) : *p; }
+template <bool COH> __device__ __forceinline__ uint64_t rvl_ld(const uint64_t *p)
+{
+    return COH ? (uint64_t)__ldcg(reinterpret_cast<const unsigned long long *>(p)) : *p;
+}
+template <bool COH> __device__ __forceinline__ RvlTarget rvl_ld_target(const RvlTarget *p)
+{
+    if (!COH) return *p;
+    static_assert(sizeof(RvlTarget) % 8 == 0, "RvlTarget is copied in 8-byte words");
+    RvlTarget t;
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(p);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(&t);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(RvlTarget) / 8); i++) dst[i] = __ldcg(src + i);
+    return t;
+}
+
 // Accumulate the class-masked Gaussian sums for grid point `lane` over samples [s_begin, s_end)
 // with stride s_step.  yrow / zrow are bit rows (zrow may be NULL: single z class).
+template <bool COH>
 __device__ __forceinline__ void rvl_accumulate_dense(const double *__restrict__ u, const uint64_t *__restrict__ yrow,
-                                                     const uint64_t *__restrict__ zrow, int s_begin, int s_end,
+                                                     const uint64_t *zrow, int s_begin, int s_end,
                                                      int s_step, double gi, double beta, double acc[4])
 {
 #define RVL_DENSE_ADD(ss, ee)                                                          \
     {                                                                                  \
         const int yb = (int)((yrow[(ss) >> 6] >> ((ss) & 63)) & 1ull);                 \
-        const int zb = zrow ? (int)((zrow[(ss) >> 6] >> ((ss) & 63)) & 1ull) : 0;      \
+        const int zb = zrow ? (int)((rvl_ld<COH>(zrow + ((ss) >> 6)) >> ((ss) & 63)) & 1ull) : 0; \
         if (yb) { if (zb) acc[3] += (ee); else acc[2] += (ee); }                       \
         else    { if (zb) acc[1] += (ee); else acc[0] += (ee); }                       \
     }
@@ -685,17 +706,32 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
 // record [score][global row][bit row].  With a peer exchange (X.peers) the record goes straight into
 // every rank's buffer over NVLink and is followed by a stamp; otherwise into `send` for the caller's
 // all-gather.  Called by a whole block (any size that is a multiple of 32).
-__device__ void rvl_publish_best(const RvlParams &P, const RvlCandHead *__restrict__ v, int nparts,
+template <bool COH>
+__device__ void rvl_publish_best(const RvlParams &P, const RvlCandHead *v, int nparts,
                                  const uint64_t *__restrict__ bits, unsigned char *__restrict__ send, size_t rec_bytes,
                                  const RvlPeerXchg &X, int t)
 {
     __shared__ double shv[32];
     __shared__ long long shi[32];
+    __syncthreads(); // k_search calls this once per target: shv / shi are reused
     double bv = 0.0;
     int64_t bi = -1;
-    for (int k = threadIdx.x; k < nparts; k += blockDim.x) {
-        RvlCandHead h = v[k];
-        if (rvl_ahead(h.score, h.row, bv, bi, P.negative)) { bv = h.score; bi = h.row; }
+    for (int k0 = threadIdx.x; k0 < nparts; k0 += 8 * blockDim.x) { // eight loads in flight per thread, then the compares
+        double hs[8];
+        int64_t hr[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int k = k0 + q * blockDim.x;
+            hr[q] = -1;
+            hs[q] = 0.0;
+            if (k < nparts) {
+                hs[q] = rvl_ld<COH>(&v[k].score);
+                hr[q] = (int64_t)rvl_ld<COH>(reinterpret_cast<const uint64_t *>(&v[k].row));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (rvl_ahead(hs[q], hr[q], bv, bi, P.negative)) { bv = hs[q]; bi = hr[q]; }
     }
     for (int o = 16; o > 0; o >>= 1) {
         double ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -728,7 +764,8 @@ __device__ void rvl_publish_best(const RvlParams &P, const RvlCandHead *__restri
         for (int i = threadIdx.x; i < P.words; i += blockDim.x) rb[i] = (bi < 0) ? 0ull : bits[(size_t)bi * P.words + i];
     }
     if (X.peers) {
-        __threadfence_system(); // records visible to every GPU before any stamp
+        if (P.world > 1) __threadfence_system(); // records visible to every GPU before any stamp
+        else __threadfence();
         __syncthreads();
         if (threadIdx.x < P.world) {
             volatile unsigned int *st =
@@ -750,30 +787,191 @@ __device__ void rvl_publish_best(const RvlParams &P, const RvlCandHead *__restri
 //   * x-axis table: rebuilt from all samples (first iteration, or when the dispatch mode changed), or
 //     updated in place from the samples the winner just moved from z-class 0 to z-class 1
 //     (T_1 += d, T_0 -= d with d summed over those few samples): O(n1) instead of O(n) per node.
-__global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
-k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, const uint64_t *__restrict__ seeds_in,
-          uint64_t *__restrict__ seeds_out, const double *__restrict__ bcvtab, double *__restrict__ tt,
-          RvlCandHead *__restrict__ slots, int nslots, unsigned long long *__restrict__ work,
-          const unsigned char *__restrict__ recv, size_t rec_bytes, int iter, int iters, int first_null,
-          int64_t *__restrict__ top, double *__restrict__ top_score, uint64_t *__restrict__ seed_iter, int allow_incr,
-          RvlPeerXchg X, const uint64_t *__restrict__ bits, int fuse_rank)
+// In-place update of one table node by ONE warp: the samples the winner moved from z-class 0 to z-class 1 (the new
+// bits of the seed) leave T_0 and enter T_1.  Lanes own grid points; the new samples are taken 32 at a time: lane l
+// locates the l-th new bit and loads its target coordinate (all loads in flight together), then the warp walks the
+// batch in ascending sample order with shuffles -- a fixed order, so the last bit of every sum is the same on every
+// rank, in every run and in both search drivers.  t0_old / t1_old: the node's current values for this lane's grid point.
+template <bool COH>
+__device__ __forceinline__ void rvl_table_incr_warp(const double *__restrict__ u, const uint64_t *zold, const uint64_t *wrow,
+                                                    int words, double beta, double *out, double t0_old, double t1_old, int lane)
 {
-    __shared__ double part[RVL_SCORE_WARPS][2][RVL_MAXG];
-    __shared__ int s_nz_old, s_nz_new, s_win;
-    const int t = blockIdx.y, m = blockIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const double gi = (double)lane;
+    double d = 0.0;
+    for (int base = 0; base < words; base += 32) {
+        const int wl = base + lane;
+        const uint64_t mine = (wl < words) ? (rvl_ld<COH>(wrow + wl) & ~rvl_ld<COH>(zold + wl)) : 0ull; // entering z-class 1
+        const int cnt = __popcll(mine);
+        int pre = cnt; // inclusive prefix of the bit counts over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(FULL, pre, o);
+            if (lane >= o) pre += up;
+        }
+        const int total = __shfl_sync(FULL, pre, 31);
+        pre -= cnt;
+        const unsigned owners = __ballot_sync(FULL, cnt > 0);
+        for (int b0 = 0; b0 < total; b0 += 32) {
+            // lane l takes new bit number b0 + l (ascending sample order): find the word that holds it
+            const int j = b0 + lane;
+            uint64_t wv = 0ull;
+            int rank = 0, wi = 0;
+            for (unsigned rest = owners; rest; rest &= rest - 1u) {
+                const int src = __ffs((int)rest) - 1;
+                const int ps = __shfl_sync(FULL, pre, src), cs = __shfl_sync(FULL, cnt, src);
+                const uint64_t ms = __shfl_sync(FULL, mine, src);
+                if (j >= ps && j < ps + cs) { wv = ms; rank = j - ps; wi = base + src; }
+            }
+            double uval = 0.0;
+            if (j < total) {
+                const unsigned lo = (unsigned)wv, hi = (unsigned)(wv >> 32);
+                const int clo = __popc(lo);
+                const int bit = rank < clo ? (int)__fns(lo, 0, rank + 1) : 32 + (int)__fns(hi, 0, rank - clo + 1);
+                uval = u[wi * 64 + bit];
+            }
+            const int nb = min(32, total - b0);
+#pragma unroll 4
+            for (int k = 0; k < nb; k++) {
+                const double dd = gi - __shfl_sync(FULL, uval, k);
+                d += rvl_exp_neg(-beta * dd * dd);
+            }
+        }
+    }
+    out[lane] = t0_old - d;
+    out[RVL_MAXG + lane] = t1_old + d;
+}
+
+// One (table node m, target t) task of the merge step done by ONE warp (k_search): wait for the ranks' stamps, resolve
+// the global winner, node-0 duties (new seed, seed.iter, top, seed state), in-place table update.  Returns false when
+// the table of this target must be REBUILT (the dispatch mode changed): that takes a block (rvl_advance_task).
+template <bool COH>
+__device__ bool rvl_advance_warp(const RvlParams &P, RvlTarget *tg_all, const double *__restrict__ u_all, const uint64_t *seeds_in,
+                                 uint64_t *seeds_out, const double *__restrict__ bcvtab, double *tt, size_t rec_bytes, int iter,
+                                 int iters, int first_null, int64_t *__restrict__ top, double *__restrict__ top_score,
+                                 uint64_t *__restrict__ seed_iter, const RvlPeerXchg &X, int t, int m, bool last_iter, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    const RvlTarget tg = tg_all[t]; // only the per-target constants are used (never nz / mode / bcv_z)
+    const int owner = tg.seed_of;
+    const bool is_null = (first_null > 0 && t >= first_null);
+    const uint64_t *zold = seeds_in + (size_t)owner * P.words;
+    const unsigned char *recv = X.local + (size_t)X.parity * P.world * P.T * rec_bytes;
+    // what does not depend on the winner is fetched before the wait: this node's current values
+    double *out = tt + (((size_t)t * P.tt_nodes + m) * 2) * RVL_MAXG;
+    const bool table = !(P.dense_x || last_iter);
+    const double t0_old = table ? rvl_ld<COH>(out + lane) : 0.0, t1_old = table ? rvl_ld<COH>(out + RVL_MAXG + lane) : 0.0;
+    // the records of this iteration sit in the local buffer once every rank's stamp for (parity, rank, owner) is there
+    double bv = 0.0;
+    int64_t bi = -1;
+    int br = 0;
+    for (int r0 = 0; r0 < P.world; r0 += 32) {
+        const int r = r0 + lane;
+        double hs = 0.0;
+        int64_t hr = -1;
+        if (r < P.world) {
+            volatile unsigned int *st = reinterpret_cast<volatile unsigned int *>(X.local + X.stamps_off) +
+                                        ((size_t)X.parity * P.world + r) * P.T + owner;
+            const long long t0 = clock64();
+            while (*st != X.stamp) {
+                if (clock64() - t0 > 4000000000ll) { // ~2 s: a peer is gone; fail loudly instead of hanging
+                    *X.err = 1;
+                    break;
+                }
+            }
+            if (P.world > 1) __threadfence_system();
+            else __threadfence();
+            const unsigned char *rec = recv + ((size_t)r * P.T + owner) * rec_bytes;
+            hs = rvl_ld<true>(reinterpret_cast<const double *>(rec));
+            hr = (int64_t)rvl_ld<true>(reinterpret_cast<const uint64_t *>(rec + sizeof(double)));
+        }
+        if (rvl_ahead(hs, hr, bv, bi, P.negative)) { bv = hs; bi = hr; br = r; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { // the same total order on every lane, warp and rank: order()[1]
+        const double ov = __shfl_xor_sync(FULL, bv, o);
+        const long long oi = __shfl_xor_sync(FULL, (long long)bi, o);
+        const int orr = __shfl_xor_sync(FULL, br, o);
+        if (rvl_ahead(ov, oi, bv, bi, P.negative)) { bv = ov; bi = oi; br = orr; }
+    }
+    const uint64_t *wrow = reinterpret_cast<const uint64_t *>(recv + ((size_t)br * P.T + owner) * rec_bytes + sizeof(RvlCandHead));
+    int c0 = 0, c1 = 0;
+    for (int w = lane; w < P.words; w += 32) {
+        const uint64_t zo = rvl_ld<COH>(zold + w), zn = zo | rvl_ld<true>(wrow + w);
+        c0 += __popcll(zo);
+        c1 += __popcll(zn);
+    }
+    const int nz_old = rvl_warp_sum_i(c0), nz = rvl_warp_sum_i(c1);
+    const int mode_old = tg.is_const ? RVL_MODE_ZERO : ((nz_old == 0 || nz_old == P.n) ? RVL_MODE_IC : RVL_MODE_CIC);
+    const int mode = tg.is_const ? RVL_MODE_ZERO : ((nz == 0 || nz == P.n) ? RVL_MODE_IC : RVL_MODE_CIC);
+    if (m == 0) {
+        if (lane == 0) {
+            tg_all[t].nz = nz;
+            tg_all[t].bcv_z = bcvtab[nz];
+            tg_all[t].mode = mode;
+            if (!is_null) {
+                top[(size_t)t * iters + iter] = bi;
+                top_score[(size_t)t * iters + iter] = bv;
+            }
+        }
+        if (!is_null) { // apply(rbind(seed, m.2[top,]), 2, "max")  LIB:2168
+            uint64_t *zo = seeds_out + (size_t)t * P.words;
+            uint64_t *zi = seed_iter + ((size_t)t * iters + iter) * P.words;
+            for (int w = lane; w < P.words; w += 32) {
+                const uint64_t v = rvl_ld<COH>(zold + w) | rvl_ld<true>(wrow + w);
+                zo[w] = v;
+                zi[w] = v;
+            }
+        }
+    }
+    if (!table) return true; // no table kept / nobody will read it
+    if (mode == RVL_MODE_ZERO) {
+        out[lane] = 0.0;
+        out[RVL_MAXG + lane] = 0.0;
+        return true;
+    }
+    const double rmax = __longlong_as_double((long long)(mode == RVL_MODE_IC ? tg.rho_abs_max_bits : tg.rho_pos_max_bits));
+    const double cmin = 1.0 + P.bw_shrink * fmin(rmax * (1.0 + 1e-9) + 1e-12, 1.0);
+    const int needed = (int)ceil(-2.0 * log(cmin) / P.tt_dt) + 2 * P.tt_pad + 1;
+    if (m >= needed) return true;
+    const bool incr = mode == RVL_MODE_CIC &&
+                      (mode_old == RVL_MODE_CIC || (mode_old == RVL_MODE_IC && nz_old == 0 && P.bw_mult == 0.25));
+    if (!incr) return false;
+    const double hx0 = P.bw_mult * tg.bcv;
+    const double dx = (tg.xmax - tg.xmin) / (double)(P.G - 1);
+    const double beta0 = 0.5 * (dx / hx0) * (dx / hx0);
+    const double tau = (double)(m - P.tt_pad) * P.tt_dt;
+    const double beta = (m == P.tt_pad) ? beta0 : beta0 * exp(tau);
+    rvl_table_incr_warp<COH>(u_all + (size_t)t * P.n, zold, wrow, P.words, beta, out, t0_old, t1_old, lane);
+    return true;
+}
+
+// Block-shared workspace of rvl_advance_task: static in k_advance, carved out of the (idle) per-warp scratch in k_search.
+struct __align__(16) RvlAdvanceShared {
+    double part[RVL_SCORE_WARPS][2][RVL_MAXG];
+    double su[1024];      // staged samples of the full build
+    uint64_t sz[16];
+    int s_nz_old, s_nz_new, s_win;
+};
+
+// One (table node m, target t) task of the step between two scoring passes; see k_advance.  Whole block.
+template <bool COH>
+__device__ void rvl_advance_task(const RvlParams &P, RvlTarget *tg_all, const double *__restrict__ u_all, const uint64_t *seeds_in,
+                                 uint64_t *seeds_out, const double *__restrict__ bcvtab, double *tt, RvlCandHead *slots, int nslots,
+                                 unsigned long long *work, const unsigned char *recv, size_t rec_bytes, int iter, int iters,
+                                 int first_null, int64_t *__restrict__ top, double *__restrict__ top_score,
+                                 uint64_t *__restrict__ seed_iter, int allow_incr, const RvlPeerXchg &X, int t, int m, RvlAdvanceShared &sh,
+                                 bool full_only = false)
+{
+    double (&part)[RVL_SCORE_WARPS][2][RVL_MAXG] = sh.part;
+    int &s_nz_old = sh.s_nz_old, &s_nz_new = sh.s_nz_new, &s_win = sh.s_win;
+    __syncthreads(); // k_search runs several tasks per block: the shared arrays below are reused
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const RvlTarget tg = tg_all[t]; // only the per-target constants are used below (never nz / mode / bcv_z)
     const int owner = tg.seed_of;
     const bool is_null = (first_null > 0 && t >= first_null);
     const uint64_t *zold = seeds_in + (size_t)owner * P.words;
     const uint64_t *wrow = nullptr; // the winner's bit row (merge only)
-    if (recv && X.peers && fuse_rank && m == 0 && owner == t) {
-        // rank step fused in: the node-0 block of every seed owner reduces this rank's per-warp bests and
-        // publishes the record + stamp (it is the first block of its target in launch order, so it is
-        // resident before any block that waits for its stamp)
-        rvl_publish_best(P, slots + (size_t)t * nslots, nslots, bits, nullptr, rec_bytes, X, t);
-        __syncthreads();
-    }
     if (recv && X.peers) {
         // peer exchange: the records of this iteration sit in the local buffer once every rank's stamp
         // for (parity, rank, owner) has arrived
@@ -798,9 +996,10 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
             int64_t bi = -1;
             int br = 0;
             for (int r = 0; r < P.world; r++) {
-                const RvlCandHead *h =
-                    reinterpret_cast<const RvlCandHead *>(recv + ((size_t)r * P.T + owner) * rec_bytes);
-                if (rvl_ahead(h->score, h->row, bv, bi, P.negative)) { bv = h->score; bi = h->row; br = r; }
+                const unsigned char *rec = recv + ((size_t)r * P.T + owner) * rec_bytes;
+                const double hs = rvl_ld<COH>(reinterpret_cast<const double *>(rec));
+                const int64_t hr = (int64_t)rvl_ld<COH>(reinterpret_cast<const uint64_t *>(rec + sizeof(double)));
+                if (rvl_ahead(hs, hr, bv, bi, P.negative)) { bv = hs; bi = hr; br = r; }
             }
             s_win = br;
             if (m == 0 && !is_null) {
@@ -814,7 +1013,7 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
     if (warp == 0) {
         int c0 = 0, c1 = 0;
         for (int w = lane; w < P.words; w += 32) {
-            const uint64_t zo = zold[w], zn = wrow ? (zo | wrow[w]) : zo;
+            const uint64_t zo = rvl_ld<COH>(zold + w), zn = wrow ? (zo | rvl_ld<COH>(wrow + w)) : zo;
             c0 += __popcll(zo);
             c1 += __popcll(zn);
         }
@@ -831,9 +1030,9 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
             tg_all[t].nz = nz;
             tg_all[t].bcv_z = bcvtab[nz];
             tg_all[t].mode = mode;
-            if (t == 0) *work = 0ull;
+            if (work && t == 0) *work = 0ull;
         }
-        for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
+        for (int i = threadIdx.x; slots && i < nslots; i += blockDim.x) {
             RvlCandHead h;
             h.score = 0.0;
             h.row = -1;
@@ -843,7 +1042,7 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
             uint64_t *zo = seeds_out + (size_t)t * P.words;
             uint64_t *zi = seed_iter + ((size_t)t * iters + iter) * P.words;
             for (int w = threadIdx.x; w < P.words; w += blockDim.x) {
-                const uint64_t v = zold[w] | wrow[w];
+                const uint64_t v = rvl_ld<COH>(zold + w) | rvl_ld<COH>(wrow + w);
                 zo[w] = v;
                 zi[w] = v;
             }
@@ -873,57 +1072,12 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
     // class 0, IC dispatch) whose x bandwidth bcv/4 coincides with bw_mult*bcv when bw_mult = 0.25
     const bool incr = allow_incr && recv && mode == RVL_MODE_CIC &&
                       (mode_old == RVL_MODE_CIC || (mode_old == RVL_MODE_IC && nz_old == 0 && P.bw_mult == 0.25));
-    __shared__ double su[1024];
-    __shared__ uint64_t sz[16];
-    if (incr) {
-        // The words holding newly set bits are compacted, in ascending order, into shared memory by the
-        // whole block (coalesced loads, ballot prefix sums -- no atomics, so the order and with it the
-        // last bit of every sum is the same on every rank and in every run); the warps then share the
-        // samples and their partial sums are added in warp order.
-        __shared__ uint32_t s_idx[1024];
-        __shared__ int s_wcnt[RVL_SCORE_WARPS];
-        uint64_t *sval = reinterpret_cast<uint64_t *>(su); // [<= 1024] the new bits of those words
-        double d = 0.0;
-        for (int base = 0; base < P.words; base += 1024) {
-            int total = 0;
-            for (int sub = 0; sub < 1024 && base + sub < P.words; sub += blockDim.x) {
-                const int w = base + sub + threadIdx.x;
-                const uint64_t v = (w < P.words && w < base + 1024) ? (wrow[w] & ~zold[w]) : 0ull; // entering z-class 1
-                const unsigned bal = __ballot_sync(0xffffffffu, v != 0ull);
-                if (lane == 0) s_wcnt[warp] = __popc(bal);
-                __syncthreads();
-                int off = total;
-                for (int q = 0; q < warp; q++) off += s_wcnt[q];
-                int all = 0;
-                for (int q = 0; q < nwarps; q++) all += s_wcnt[q];
-                if (v) {
-                    const int pos = off + __popc(bal & ((1u << lane) - 1u));
-                    s_idx[pos] = (uint32_t)w;
-                    sval[pos] = v;
-                }
-                total += all;
-                __syncthreads();
-            }
-            for (int q = warp; q < total; q += nwarps) { // word q: warp-uniform
-                uint64_t v = sval[q];
-                const int w = (int)s_idx[q];
-                while (v) {
-                    const int bb = __ffsll((long long)v) - 1;
-                    v &= v - 1;
-                    const double dd = gi - u[w * 64 + bb];
-                    d += rvl_exp_neg(-beta * dd * dd);
-                }
-            }
-            __syncthreads();
-        }
-        part[warp][0][lane] = d;
-        __syncthreads();
-        if (warp == 0) {
-            double tot = 0.0;
-            for (int q = 0; q < nwarps; q++) tot += part[q][0][lane];
-            out[lane] -= tot;
-            out[RVL_MAXG + lane] += tot;
-        }
+    if (full_only && incr) return; // k_search: the per-warp pass has done this task
+    double *su = sh.su;
+    uint64_t *sz = sh.sz;
+    if (incr) { // O(new bits) per node: one warp is plenty (the same routine serves k_search's per-warp tasks)
+        if (warp == 0)
+            rvl_table_incr_warp<COH>(u, zold, wrow, P.words, beta, out, rvl_ld<COH>(out + lane), rvl_ld<COH>(out + RVL_MAXG + lane), lane);
         return;
     }
 
@@ -937,7 +1091,7 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
         if (threadIdx.x < 16) {
             const int w = (base >> 6) + threadIdx.x;
             uint64_t zz = 0ull;
-            if (use_z && w < P.words) zz = wrow ? (zold[w] | wrow[w]) : zold[w];
+            if (use_z && w < P.words) zz = wrow ? (rvl_ld<COH>(zold + w) | rvl_ld<COH>(wrow + w)) : rvl_ld<COH>(zold + w);
             sz[threadIdx.x] = zz;
         }
         __syncthreads();
@@ -970,14 +1124,28 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
     }
 }
 
+__global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
+k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, const uint64_t *__restrict__ seeds_in,
+          uint64_t *__restrict__ seeds_out, const double *__restrict__ bcvtab, double *__restrict__ tt,
+          RvlCandHead *__restrict__ slots, int nslots, unsigned long long *__restrict__ work,
+          const unsigned char *__restrict__ recv, size_t rec_bytes, int iter, int iters, int first_null,
+          int64_t *__restrict__ top, double *__restrict__ top_score, uint64_t *__restrict__ seed_iter, int allow_incr,
+          RvlPeerXchg X)
+{
+    __shared__ RvlAdvanceShared sh;
+    rvl_advance_task<false>(P, tg_all, u_all, seeds_in, seeds_out, bcvtab, tt, slots, nslots, work, recv, rec_bytes, iter, iters,
+                            first_null, top, top_score, seed_iter, allow_incr, X, blockIdx.y, blockIdx.x, sh);
+}
+
 // Per-class totals at shrink factor c for grid point `lane`.
-__device__ __forceinline__ void rvl_tt_lookup(const RvlParams &P, const double *__restrict__ tt_t, double c, int lane,
+template <bool COH>
+__device__ __forceinline__ void rvl_tt_lookup(const RvlParams &P, const double *tt_t, double c, int lane,
                                               double &tot0, double &tot1)
 {
     if (c == 1.0) {
         const double *nd = tt_t + (size_t)P.tt_pad * 2 * RVL_MAXG;
-        tot0 = nd[lane];
-        tot1 = nd[RVL_MAXG + lane];
+        tot0 = rvl_ld<COH>(nd + lane);
+        tot1 = rvl_ld<COH>(nd + RVL_MAXG + lane);
         return;
     }
     double pos = -2.0 * log(c) / P.tt_dt;
@@ -1005,8 +1173,8 @@ __device__ __forceinline__ void rvl_tt_lookup(const RvlParams &P, const double *
 #pragma unroll
     for (int q = 0; q < RVL_TT_STENCIL; q++) {
         double wq = __shfl_sync(0xffffffffu, wl, q);
-        tot0 = fma(wq, nd[(size_t)q * 2 * RVL_MAXG + lane], tot0);
-        tot1 = fma(wq, nd[(size_t)q * 2 * RVL_MAXG + RVL_MAXG + lane], tot1);
+        tot0 = fma(wq, rvl_ld<COH>(nd + (size_t)q * 2 * RVL_MAXG + lane), tot0);
+        tot1 = fma(wq, rvl_ld<COH>(nd + (size_t)q * 2 * RVL_MAXG + RVL_MAXG + lane), tot1);
     }
 }
 
@@ -1019,29 +1187,17 @@ __device__ __forceinline__ void rvl_tt_lookup(const RvlParams &P, const double *
 // Dynamic smem: per-warp scratch + the row's bits.  Besides the score of every row, each warp leaves
 // its best (score, local row) per target in part[target][global warp id] (pre-set to "none" by
 // k_advance) so that the rank step never re-reads the F scores.
-#ifndef RVL_SCORE_MIN_CTAS
-#define RVL_SCORE_MIN_CTAS 2
-#endif
-__global__ void __launch_bounds__(RVL_KSCORE_WARPS * 32, RVL_SCORE_MIN_CTAS)
-k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict__ u_all,
-        const double *__restrict__ xc_all, const RvlTarget *__restrict__ tg_all,
-        const uint64_t *__restrict__ seeds, const double *__restrict__ bcvtab, const double *__restrict__ tt,
-        double *__restrict__ scores, RvlCandHead *__restrict__ part, unsigned long long *__restrict__ work,
-        unsigned long long *__restrict__ ctr, const int64_t *__restrict__ uniq, int64_t U)
+// The scoring pass of one warp (see k_score): draws (target, row) items from *work until they run out.  COH: the seeds, the
+// per-iteration seed state and the x-axis table may have been written by other blocks of the SAME launch (k_search).
+template <bool COH>
+__device__ __forceinline__ void rvl_score_phase(const RvlParams &P, const uint64_t *__restrict__ bits, const double *__restrict__ u_all,
+                                                const double *__restrict__ xc_all, const RvlTarget *tg_all, const uint64_t *seeds,
+                                                const double *__restrict__ bcvtab, const double *tt, double *__restrict__ scores,
+                                                RvlCandHead *part, unsigned long long *work, unsigned long long *ctr,
+                                                const int64_t *__restrict__ uniq, int64_t U, RvlWarpScratch &S, uint64_t *yrow, int slot,
+                                                int nslots, int lane)
 {
-    // uniq[0..U): the rows to score (first row of every group of identical rows); NULL = all F rows
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n, words = P.words, G = P.G;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * RVL_KSCORE_WARPS + warp, nslots = gridDim.x * RVL_KSCORE_WARPS;
-
-    rvl_logtab_fill(rvl_logtab_g); // the only block barrier of the kernel
-
-    RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
-    uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_KSCORE_WARPS);
-    RvlWarpScratch &S = scr[warp];
-    uint64_t *yrow = yrows + (size_t)warp * words;
-
     const unsigned long long nrows = (unsigned long long)(uniq ? U : P.F);
     const unsigned long long total = nrows * (unsigned long long)P.T;
     int t = -1, mode = RVL_MODE_ZERO;
@@ -1063,7 +1219,7 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
         if (it != t) { // new target: flush the running best, switch the per-target pointers
             if (t >= 0 && lane == 0) { RvlCandHead h; h.score = best_v; h.row = best_i; part[(size_t)t * nslots + slot] = h; }
             t = it;
-            tg = tg_all[t];
+            tg = rvl_ld_target<COH>(tg_all + t);
             mode = tg.mode;
             xc = xc_all + (size_t)t * n;
             u = u_all + (size_t)t * n;
@@ -1099,13 +1255,13 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
         if (P.dense_x) {
             // validation mode: every sample visited for every feature
             if (lane < G)
-                rvl_accumulate_dense(u, yrow, mode == RVL_MODE_CIC ? zrow : nullptr, 0, n, 1, (double)lane, beta, acc);
+                rvl_accumulate_dense<COH>(u, yrow, mode == RVL_MODE_CIC ? zrow : nullptr, 0, n, 1, (double)lane, beta, acc);
             nexp = n;
         } else {
             // x-axis sums = (per-class totals over ALL samples at this feature's bandwidth, interpolated
             // from the per-iteration table) - (the minority y-class, visited bit by bit)
             double tot0, tot1;
-            rvl_tt_lookup(P, tt + (size_t)t * P.tt_nodes * 2 * RVL_MAXG, c, lane, tot0, tot1);
+            rvl_tt_lookup<COH>(P, tt + (size_t)t * P.tt_nodes * 2 * RVL_MAXG, c, lane, tot0, tot1);
             const bool flip = n1 > n - n1; // visit the zeros of y instead when they are fewer
             double m0 = 0.0, m1 = 0.0;     // minority-class sums split by z
             const double gi = (double)lane;
@@ -1132,7 +1288,7 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
                 for (int w = lane; w <= last; w += 32) {
                     uint64_t v = yrow[w];
                     if (flip) { v = ~v; if (w == last && (n & 63)) v &= (1ull << (n & 63)) - 1ull; }
-                    const uint64_t zw = use_z ? zrow[w] : 0ull;
+                    const uint64_t zw = use_z ? rvl_ld<COH>(zrow + w) : 0ull;
                     while (v) {
                         const int b = __ffsll((long long)v) - 1;
                         v &= v - 1;
@@ -1162,7 +1318,7 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
                         v = ~v;
                         if (w == last && (n & 63)) v &= (1ull << (n & 63)) - 1ull;
                     }
-                    const uint64_t zw = use_z ? zrow[w] : 0ull;
+                    const uint64_t zw = use_z ? rvl_ld<COH>(zrow + w) : 0ull;
                     while (v) { // warp-uniform loop: every lane sees the same word
                         int b = __ffsll((long long)v) - 1;
                         v &= v - 1;
@@ -1212,6 +1368,143 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
     if (t >= 0 && lane == 0) { RvlCandHead h; h.score = best_v; h.row = best_i; part[(size_t)t * nslots + slot] = h; }
 }
 
+#ifndef RVL_SCORE_MIN_CTAS
+#define RVL_SCORE_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(RVL_KSCORE_WARPS * 32, RVL_SCORE_MIN_CTAS)
+k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict__ u_all,
+        const double *__restrict__ xc_all, const RvlTarget *__restrict__ tg_all,
+        const uint64_t *__restrict__ seeds, const double *__restrict__ bcvtab, const double *__restrict__ tt,
+        double *__restrict__ scores, RvlCandHead *__restrict__ part, unsigned long long *__restrict__ work,
+        unsigned long long *__restrict__ ctr, const int64_t *__restrict__ uniq, int64_t U)
+{
+    // uniq[0..U): the rows to score (first row of every group of identical rows); NULL = all F rows
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * RVL_KSCORE_WARPS + warp, nslots = gridDim.x * RVL_KSCORE_WARPS;
+
+    rvl_logtab_fill(rvl_logtab_g); // the only block barrier of the kernel
+
+    RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
+    uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_KSCORE_WARPS);
+    rvl_score_phase<false>(P, bits, u_all, xc_all, tg_all, seeds, bcvtab, tt, scores, part, work, ctr, uniq, U, scr[warp],
+                           yrows + (size_t)warp * P.words, slot, nslots, lane);
+}
+
+// ---- k_search: the whole search in ONE persistent cooperative launch ---------------------------------------
+// grid = SMs x resident CTAs (the k_score grid), launched cooperatively so that every block is resident.  Per iteration:
+//   score     every warp draws (target, row) items from this iteration's counter (rvl_score_phase) and leaves its
+//             best per target in part[];
+//   rank      the block that finishes last (ticket on done[it]) reduces part[] per seed-owning target and stores the
+//             candidate record [score][global row][bit row] + a stamp into EVERY rank's exchange buffer -- peer memory
+//             over NVLink (CUDA IPC / peer access), the local buffer included; no collective call, no host;
+//   merge     every block waits for the `world` stamps of the targets whose tasks it owns, resolves the same global
+//             winner (ties -> lowest global row, NaN last), and runs its share of the (table node, target) tasks of
+//             rvl_advance_task: seed OR-merge, seed state, in-place x-axis table update;
+//   barrier   grid-wide (atomic counter), after which the next scoring pass sees the new seed, state and table.
+// Compared with the split-phase launches (k_score, k_argmax, k_advance per iteration) this removes 3 launches and
+// their gaps per iteration and the log-table fill of every k_score launch; the arithmetic and its order are the
+// same functions, so the results are bit-identical (tests: fused == split-phase).
+// Data written and read by different blocks inside the launch (table, seeds, seed state, part[], records) is read with
+// ld.global.cg (rvl_ld<true>); writers fence before the ticket / stamp / barrier.
+__device__ __forceinline__ void rvl_grid_barrier(unsigned int *bar, unsigned int target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*reinterpret_cast<volatile unsigned int *>(bar) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long rvl_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(RVL_KSCORE_WARPS * 32, RVL_SCORE_MIN_CTAS)
+k_search(const RvlSearchArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_last;
+    const RvlParams &P = a.P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * RVL_KSCORE_WARPS + warp, nslots = gridDim.x * RVL_KSCORE_WARPS;
+    rvl_logtab_fill(rvl_logtab_g);
+    RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
+    uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_KSCORE_WARPS);
+    const int nodes = P.dense_x ? 1 : P.tt_nodes;
+    const int ntasks = nodes * P.T;
+    unsigned int nbar = 0;
+    for (int it = 0; it < a.iters; it++) {
+        const uint64_t *seeds_cur = (it & 1) ? a.seed_b : a.seed_a;
+        uint64_t *seeds_nxt = (it & 1) ? a.seed_a : a.seed_b;
+        // ---- score
+        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[it * 8 + 0] = rvl_globaltimer();
+        for (int t = lane; t < P.T; t += 32) { // this warp's best slots: "none" for the targets it will not touch
+            RvlCandHead h;
+            h.score = 0.0;
+            h.row = -1;
+            a.part[(size_t)t * nslots + slot] = h;
+        }
+        __syncwarp();
+#ifndef RVL_KSEARCH_COH
+#define RVL_KSEARCH_COH true
+#endif
+        rvl_score_phase<RVL_KSEARCH_COH>(P, a.bits, a.u_all, a.xc_all, a.tg_all, seeds_cur, a.bcvtab, a.tt,
+                              a.scores + (size_t)it * P.T * P.F, a.part, a.work + it, a.ctr, a.uniq, a.U, scr[warp],
+                              yrows + (size_t)warp * P.words, slot, nslots, lane);
+        __threadfence(); // this warp's part[] entries before the block's ticket
+        __syncthreads();
+        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[it * 8 + 1] = rvl_globaltimer(); // block 0 done scoring
+        // ---- rank: the last block to finish publishes this rank's candidate records
+        RvlPeerXchg X = a.X;
+        X.stamp = (a.epoch << 16) | (unsigned int)(it + 1);
+        X.parity = (a.seq0 + it) & 1;
+        if (threadIdx.x == 0) s_last = (atomicAdd(a.done + it, 1u) == gridDim.x - 1u);
+        __syncthreads();
+        if (s_last) {
+            if (a.dbg && threadIdx.x == 0) a.dbg[it * 8 + 2] = rvl_globaltimer(); // every block done scoring
+            __threadfence();
+            for (int t = 0; t < a.nreal; t++)
+                rvl_publish_best<true>(P, a.part + (size_t)t * nslots, nslots, a.bits, nullptr, a.rec_bytes, X, t);
+            if (a.dbg && threadIdx.x == 0) a.dbg[it * 8 + 3] = rvl_globaltimer(); // records + stamps out
+        }
+        // ---- merge: one (node, target) task per WARP -- stamps, winner, seed, in-place table update -- all tasks of the
+        // grid in flight at once; a target whose dispatch mode changed (table rebuild, O(n G) per node) is left to a
+        // block-level pass of rvl_advance_task.  Nothing of the table is touched after the last iteration.
+        const bool last_iter = (it + 1 == a.iters);
+        bool rebuild = false;
+        for (int q = slot; q < ntasks; q += nslots) {
+            const int t = q / nodes, m = q - t * nodes;
+            if (!rvl_advance_warp<true>(P, a.tg_all, a.u_all, seeds_cur, seeds_nxt, a.bcvtab, a.tt, a.rec_bytes, it, a.iters,
+                                        a.first_null, a.top, a.top_score, a.seed_iter, X, t, m, last_iter, lane))
+                rebuild = true;
+        }
+        if (rebuild && lane == 0) atomicOr(a.need + it, 1u);
+        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[it * 8 + 4] = rvl_globaltimer(); // block 0's tasks done
+        if (!last_iter) {
+            nbar++;
+            rvl_grid_barrier(a.bar, nbar * gridDim.x);
+            if (__ldcg(a.need + it)) { // rare: some target's table must be rebuilt from all samples -- block-level tasks
+                for (int q = blockIdx.x; q < ntasks; q += gridDim.x) {
+                    const int t = q / nodes, m = q - t * nodes;
+                    rvl_advance_task<true>(P, a.tg_all, a.u_all, seeds_cur, seeds_nxt, a.bcvtab, a.tt, nullptr, 0, nullptr, X.local,
+                                           a.rec_bytes, it, a.iters, a.first_null, a.top, a.top_score, a.seed_iter, 1, X, t, m,
+                                           *reinterpret_cast<RvlAdvanceShared *>(smem_raw), true); // the per-warp scratch is idle
+                }
+                nbar++;
+                rvl_grid_barrier(a.bar, nbar * gridDim.x);
+            }
+        }
+        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[it * 8 + 5] = rvl_globaltimer(); // barrier passed
+    }
+}
+
 // assoc(x_t, y, "IC") by one block (8 warps): warps split the samples, lanes own grid points.
 // LIB:2491-2501 -> mutual.inf.v2.  Result written by thread 0.
 struct RvlAssocShared {
@@ -1254,7 +1547,7 @@ __device__ double rvl_assoc_block(const RvlParams &P, const RvlTarget &tg, const
     double dx = (tg.xmax - tg.xmin) / (double)(G - 1);
     double beta = 0.5 * (dx / hx) * (dx / hx);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    if (lane < G) rvl_accumulate_dense(u, y, nullptr, warp, n, nwarps, (double)lane, beta, acc);
+    if (lane < G) rvl_accumulate_dense<false>(u, y, nullptr, warp, n, nwarps, (double)lane, beta, acc);
     if (lane < G) { sh.part[warp][lane][0] = acc[0]; sh.part[warp][lane][1] = acc[2]; }
     __syncthreads();
     double score = 0.0;
@@ -1275,12 +1568,12 @@ __device__ double rvl_assoc_block(const RvlParams &P, const RvlTarget &tg, const
 __global__ void __launch_bounds__(RVL_SCORE_WARPS * 32)
 k_assoc(RvlParams P, const RvlTarget *__restrict__ tg_all, const int *__restrict__ target_of,
         const double *__restrict__ u_all, const double *__restrict__ xc_all, const uint64_t *__restrict__ y_all,
-        const double *__restrict__ bcvtab, double *__restrict__ out, size_t y_stride, size_t out_stride)
+        const double *__restrict__ bcvtab, double *__restrict__ out, size_t y_stride, size_t out_stride, int t_div)
 {
     __shared__ RvlAssocShared sh;
     rvl_logtab_fill(rvl_logtab_g);
     int q = blockIdx.x;
-    int t = target_of ? target_of[q] : q;
+    int t = target_of ? target_of[q] : (t_div > 0 ? q / t_div : q); // t_div: t_div consecutive vectors per target
     double v = rvl_assoc_block(P, tg_all[t], u_all + (size_t)t * P.n, xc_all + (size_t)t * P.n,
                                y_all + (size_t)q * y_stride, bcvtab, sh);
     if (threadIdx.x == 0) out[(size_t)q * out_stride] = v;
@@ -1297,7 +1590,7 @@ __global__ void k_argmax(RvlParams P, const RvlCandHead *__restrict__ part, int 
                          const uint64_t *__restrict__ bits, unsigned char *__restrict__ send, size_t rec_bytes,
                          RvlPeerXchg X)
 {
-    rvl_publish_best(P, part + (size_t)blockIdx.x * nparts, nparts, bits, send, rec_bytes, X, blockIdx.x);
+    rvl_publish_best<false>(P, part + (size_t)blockIdx.x * nparts, nparts, bits, send, rec_bytes, X, blockIdx.x);
 }
 
 // ---- bit packing ------------------------------------------------------------------------------
@@ -1455,7 +1748,7 @@ __global__ void k_pvalues(const double *__restrict__ cmi, int64_t F, const doubl
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= F) return;
     double v = cmi[i];
-    if (isnan(v)) { pval[i] = 0.0; return; } // (NaN > x) is NA in R; sum() would be NA -- reported as 0 here
+    if (isnan(v)) { pval[i] = v; return; } // (cmi.rand > NaN) is NA in R and so is its sum: NaN in, NaN out
     int64_t lo = 0, hi = n_valid;
     while (lo < hi) { // first index with rand > v
         int64_t mid = (lo + hi) >> 1;
@@ -1487,6 +1780,7 @@ extern "C" cudaError_t rvl_upload_log_table(void)
 extern "C" size_t rvl_score_smem_bytes(int n, int words)
 {
     (void)n;
+    static_assert(sizeof(RvlAdvanceShared) <= sizeof(RvlWarpScratch) * RVL_KSCORE_WARPS, "k_search overlays the merge workspace on the scratch");
     return sizeof(RvlWarpScratch) * RVL_KSCORE_WARPS + sizeof(uint64_t) * (size_t)words * RVL_KSCORE_WARPS;
 }
 
@@ -1507,6 +1801,32 @@ extern "C" cudaError_t rvl_score_configure(size_t smem, int device, int *grid_ou
 
 extern "C" int rvl_score_warps(void) { return RVL_KSCORE_WARPS; }
 
+// Persistent grid of k_search for `smem` bytes of dynamic shared memory: SMs x resident blocks (every block must be
+// resident: the launch is cooperative); 0 when the device cannot launch cooperatively.
+extern "C" cudaError_t rvl_search_configure(size_t smem, int device, int *grid_out)
+{
+    *grid_out = 0;
+    int coop = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (e != cudaSuccess) return e;
+    if (!coop) return cudaSuccess;
+    e = cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, RVL_KSCORE_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    *grid_out = sms * per_sm;
+    return cudaSuccess;
+}
+
+extern "C" cudaError_t rvl_launch_search(const RvlSearchArgs *a, int grid_x, size_t smem, cudaStream_t st)
+{
+    void *args[] = {(void *)a};
+    return cudaLaunchCooperativeKernel((const void *)k_search, dim3(grid_x), dim3(RVL_KSCORE_WARPS * 32), args, smem, st);
+}
+
 extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits,
                                  const double *u_all, const double *xc_all, const RvlTarget *tg,
                                  const uint64_t *seeds, const double *bcvtab, const double *tt, double *scores,
@@ -1521,13 +1841,12 @@ extern "C" void rvl_launch_advance(const RvlParams *P, RvlTarget *tg, const doub
                                    uint64_t *seeds_out, const double *bcvtab, double *tt, RvlCandHead *slots,
                                    int nslots, unsigned long long *work, const unsigned char *recv, size_t rec_bytes,
                                    int iter, int iters, int first_null, int64_t *top, double *top_score,
-                                   uint64_t *seed_iter, int allow_incr, const RvlPeerXchg *X, const uint64_t *bits,
-                                   int fuse_rank, cudaStream_t st)
+                                   uint64_t *seed_iter, int allow_incr, const RvlPeerXchg *X, cudaStream_t st)
 {
     dim3 grid(P->dense_x ? 1 : P->tt_nodes, P->T);
     k_advance<<<grid, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, u_all, seeds_in, seeds_out, bcvtab, tt, slots, nslots, work,
                                                      recv, rec_bytes, iter, iters, first_null, top, top_score, seed_iter,
-                                                     allow_incr, *X, bits, fuse_rank);
+                                                     allow_incr, *X);
 }
 
 // FP64 FMA peak micro-benchmark (MEASURED_PEAKS.json has no FP64 figure): 8 independent DFMA chains
@@ -1551,11 +1870,11 @@ extern "C" void rvl_launch_fp64_peak(int blocks, int threads, int iters, double 
 
 extern "C" void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of,
                                  const double *u_all, const double *xc_all, const uint64_t *y_all,
-                                 const double *bcvtab, double *out, size_t y_stride, size_t out_stride,
+                                 const double *bcvtab, double *out, size_t y_stride, size_t out_stride, int t_div,
                                  cudaStream_t st)
 {
     k_assoc<<<npairs, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, target_of, u_all, xc_all, y_all, bcvtab, out, y_stride,
-                                                     out_stride);
+                                                     out_stride, t_div);
 }
 
 extern "C" void rvl_launch_argmax(const RvlParams *P, const RvlCandHead *part, int nparts, const uint64_t *bits,

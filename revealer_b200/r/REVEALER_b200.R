@@ -1,7 +1,7 @@
 # REVEALER_b200.R -- R host side of the B200-native CMI search.
 #
-# Keeps REVEALER.v1's twelve formals (REVEALER_library.v5C.R:1504-1516, same names and defaults) and
-# adds the optional trailing grid/bandwidth arguments.  All scoring, ranking and seed merging is one
+# Defines REVEALER.v1 with the reference's twelve formals (REVEALER_library.v5C.R:1504-1516, same names and defaults)
+# plus the optional trailing n.grid, bandwidth.mult, bandwidth.shrink, n.gpus.  All scoring, ranking and seed merging is one
 # .Call into librevealer_b200.so through r_shim.c; nothing is computed in R and there is no CPU
 # fallback (a missing GPU or a non-binary feature matrix is an R error).
 #
@@ -19,9 +19,19 @@ revealer.b200.load <- function(lib.dir = ".") {
 
 # The iteration section of REVEALER.v1 (LIB:1837-1864, 2167-2171) as one call.
 #   target: numeric[n] in REVEALER.v1's sample order; m.2: F x n 0/1 matrix; seed: numeric[n] 0/1
+#   n.gpus > 1: the rows of m.2 are sharded over devices 0 .. n.gpus-1 of this R process (rvlR_search_multi)
 revealer.b200.search <- function(target, m.2, seed, max.n.iter = 5, target.match = "positive",
                                  target.rand = NULL, n.grid = 25, bandwidth.mult = 0.25,
-                                 bandwidth.shrink = -0.75, device = 0, ctx = NULL) {
+                                 bandwidth.shrink = -0.75, device = 0, ctx = NULL, n.gpus = 1) {
+   if (n.gpus > 1) {
+      if (is.null(m.2)) stop("n.gpus > 1 shards the R matrix m.2; it cannot be combined with a matrix already resident on one device")
+      storage.mode(m.2) <- "double"
+      res <- .Call("rvlR_search_multi", as.integer(device + 0:(n.gpus - 1)), as.double(target), m.2, as.double(seed),
+                   as.integer(max.n.iter), identical(target.match, "negative"), as.integer(n.grid),
+                   as.double(bandwidth.mult), as.double(bandwidth.shrink), target.rand)
+      res$ctx <- NULL
+      return(res)
+   }
    if (is.null(ctx)) ctx <- .Call("rvlR_create", as.integer(device))
    if (!is.null(m.2)) storage.mode(m.2) <- "double"        # NULL: the matrix is already resident in ctx
    res <- .Call("rvlR_search", ctx, as.double(target), m.2, as.double(seed), as.integer(max.n.iter),
@@ -31,18 +41,38 @@ revealer.b200.search <- function(target, m.2, seed, max.n.iter = 5, target.match
    res
 }
 
-REVEALER.v1.b200 <- function(
+# p.val[i] <- sum(cmi.rand > cmi[i]) / length(cmi.rand), LIB:1868-1869: on the scores still resident on the device
+# after a single-GPU search; from the gathered R arrays (one upload) after a sharded one.
+revealer.b200.pvalues <- function(res, iter) {
+   if (!is.null(res$ctx)) return(.Call("rvlR_pvalues_iter", res$ctx, as.integer(iter)))
+   tmp <- .Call("rvlR_create", 0L)
+   .Call("rvlR_pvalues", tmp, res$cmi[, iter], as.double(res$cmi.rand[, , iter]))
+}
+
+# REVEALER.v1 with the reference's twelve formals (LIB:1504-1516: same names, order and defaults), followed by the
+# optional grid / bandwidth arguments and n.gpus.  Sourcing this file after REVEALER_library.v5C.R replaces the
+# reference's REVEALER.v1 by this one (R binds the last definition), exactly as the library's own second copy
+# replaces its first.  pdf.output.file / locs.table.file are accepted for signature compatibility; plotting stays
+# in the reference (INTEGRATION.md section 3 shows the in-place patch that keeps the PDF).
+REVEALER.v1 <- function(
    ds1, target.name, target.match = "positive", ds2, seed.names = NULL, exclude.features = NULL,
-   max.n.iter = 5, pdf.output.file = NULL, count.thres.low = NULL, count.thres.high = NULL,
+   max.n.iter = 5, pdf.output.file, count.thres.low = NULL, count.thres.high = NULL,
    n.markers = 30, locs.table.file = NULL,
-   n.grid = 25, bandwidth.mult = 0.25, bandwidth.shrink = -0.75, n.perm = 10, r.seed = 34578, device = 0,
-   gct.ingest = TRUE, consolidate.identical.features = FALSE)   # the reference's internal switch, LIB:1532
+   n.grid = 25, bandwidth.mult = 0.25, bandwidth.shrink = -0.75, n.gpus = 1,
+   n.perm = 10, r.seed = 34578, device = 0,                 # the reference's internal constants LIB:1519, 1531
+   gct.ingest = FALSE,                                      # TRUE: ds2 is read by the device GCT tokeniser (opt-in)
+   consolidate.identical.features = FALSE)                  # the reference's internal switch, LIB:1532
 {
    set.seed(r.seed)                                        # LIB:1557
-   if (gct.ingest) return(REVEALER.v1.b200.gct(ds1, target.name, target.match, ds2, seed.names, exclude.features,
-                                               max.n.iter, count.thres.low, count.thres.high, n.markers, n.grid,
-                                               bandwidth.mult, bandwidth.shrink, n.perm, device,
-                                               consolidate.identical.features))
+   if (is.null(seed.names)) seed.names <- "NULLSEED"       # LIB:1554
+   null.seed <- identical(seed.names, "NULLSEED")          # (a vector condition in the reference, LIB:1658/1690)
+   if (gct.ingest) {
+      if (n.gpus > 1) stop("gct.ingest = TRUE loads ds2 onto one device; use gct.ingest = FALSE with n.gpus > 1")
+      return(REVEALER.v1.b200.gct(ds1, target.name, target.match, ds2, seed.names, exclude.features,
+                                  max.n.iter, count.thres.low, count.thres.high, n.markers, n.grid,
+                                  bandwidth.mult, bandwidth.shrink, n.perm, device,
+                                  consolidate.identical.features))
+   }
    read.gct <- function(f) {                               # same on-disk format as MSIG.Gct2Frame
       d <- read.delim(f, header = TRUE, sep = "\t", skip = 2, row.names = 1, blank.lines.skip = TRUE,
                       comment.char = "", as.is = TRUE, na.strings = "")
@@ -59,7 +89,6 @@ REVEALER.v1.b200 <- function(
    target <- target[ord]
    m.2 <- m.2[, ord, drop = FALSE]
    if (target.name %in% rownames(m.2)) m.2 <- m.2[rownames(m.2) != target.name, , drop = FALSE]
-   null.seed <- is.null(seed.names) || identical(seed.names, "NULLSEED")
    if (!is.null(count.thres.low) && !is.null(count.thres.high)) {
       s <- rowSums(m.2)
       keep <- (s >= count.thres.low & s <= count.thres.high)
@@ -80,18 +109,16 @@ REVEALER.v1.b200 <- function(
       for (i in 1:n.perm) target.rand[i, ] <- sample(target.rand[i, ])
    }
    res <- revealer.b200.search(target, m.2, seed, max.n.iter, target.match, target.rand, n.grid,
-                               bandwidth.mult, bandwidth.shrink, device)
+                               bandwidth.mult, bandwidth.shrink, device, n.gpus = n.gpus)
    res$feature.names <- rownames(m.2)
    res$seed.names.iter <- rownames(m.2)[res$top]           # seed.names.iter
    res$target <- target
    res$cmi.names <- apply(res$cmi, 2, function(v)          # display ranking, as order() at LIB:1858-1864
       rownames(m.2)[order(v, decreasing = !identical(target.match, "negative"))][1:min(n.markers, nrow(m.2))])
-   if (n.perm > 0) {
-      res$p.val <- sapply(1:max.n.iter, function(it)
-         .Call("rvlR_pvalues", res$ctx, res$cmi[, it], as.double(res$cmi.rand[, , it])))
-   }
+   if (n.perm > 0) res$p.val <- sapply(1:max.n.iter, function(it) revealer.b200.pvalues(res, it))
    res
 }
+REVEALER.v1.b200 <- REVEALER.v1                            # the name this file used in round 1
 
 # The same function with ds2 read by the device GCT ingest: the file is memory-mapped, its text goes over
 # PCIe and is tokenised on the GPU straight into the bit matrix -- no read.delim, no F x n matrix of doubles
@@ -150,9 +177,6 @@ REVEALER.v1.b200.gct <- function(ds1, target.name, target.match, ds2, seed.names
    res$target <- target
    res$cmi.names <- apply(res$cmi, 2, function(v)
       feature.names[order(v, decreasing = !identical(target.match, "negative"))][1:min(n.markers, length(feature.names))])
-   if (n.perm > 0) {
-      res$p.val <- sapply(1:max.n.iter, function(it)
-         .Call("rvlR_pvalues", res$ctx, res$cmi[, it], as.double(res$cmi.rand[, , it])))
-   }
+   if (n.perm > 0) res$p.val <- sapply(1:max.n.iter, function(it) revealer.b200.pvalues(res, it))
    res
 }

@@ -168,13 +168,14 @@ SEXP rvlR_search(SEXP sctx, SEXP starget, SEXP sm2, SEXP sseed, SEXP siters, SEX
 }
 
 /* .Call("rvlR_search_multi", devices, target, m2, seed, max.n.iter, negative, n.grid, bandwidth.mult,
- *       bandwidth.shrink)
- * The same search with the rows of m.2 sharded over several GPUs of this R process (n.gpus > 1):
- * one context per device, rows [lo, lo+cnt) of the column-major R matrix passed in place (pointer
- * offset, ld = F: no copy), rvl_group_connect + rvl_group_search, scores scattered back into F x iter.
- * No permutation targets in this form. */
+ *       bandwidth.shrink, target.rand)
+ * The same search with the rows of m.2 sharded over several GPUs of this R process (REVEALER.v1's n.gpus > 1):
+ * one context per device, rows [lo, lo+cnt) of the column-major R matrix passed in place (pointer offset,
+ * ld = F: only the block's rows are read and shipped), rvl_group_connect + rvl_group_search (one persistent
+ * launch per device; the devices meet through peer memory), scores scattered back into F x iter.
+ * target.rand: NULL or n.perm x n permuted targets (LIB:1843-1844) -> cmi.rand = F x n.perm x iter. */
 SEXP rvlR_search_multi(SEXP sdevices, SEXP starget, SEXP sm2, SEXP sseed, SEXP siters, SEXP snegative, SEXP sngrid,
-                       SEXP smult, SEXP sshrink)
+                       SEXP smult, SEXP sshrink, SEXP srand)
 {
     if (!Rf_isInteger(sdevices) || !Rf_isReal(starget) || !Rf_isReal(sm2) || !Rf_isMatrix(sm2) || !Rf_isReal(sseed))
         Rf_error("revealer_b200: bad argument types");
@@ -182,13 +183,23 @@ SEXP rvlR_search_multi(SEXP sdevices, SEXP starget, SEXP sm2, SEXP sseed, SEXP s
     const R_xlen_t n = XLENGTH(starget);
     const int F = Rf_nrows(sm2);
     const int iters = Rf_asInteger(siters);
-    if (world < 1 || world > 64 || Rf_ncols(sm2) != n || XLENGTH(sseed) != n) Rf_error("revealer_b200: dimension mismatch");
+    if (world < 1 || world > 64 || Rf_ncols(sm2) != n || XLENGTH(sseed) != n || iters < 1) Rf_error("revealer_b200: dimension mismatch");
+    int nperm = 0;
+    if (!Rf_isNull(srand)) {
+        if (!Rf_isReal(srand) || !Rf_isMatrix(srand) || Rf_ncols(srand) != n) Rf_error("revealer_b200: target.rand must be n.perm x n");
+        nperm = Rf_nrows(srand);
+    }
+    const int T = 1 + nperm;
     rvl_opts o;
     rvl_default_options(&o);
     o.n_grid = Rf_asInteger(sngrid);
     o.negative = Rf_asLogical(snegative) ? 1 : 0;
     o.bandwidth_mult = Rf_asReal(smult);
     o.bandwidth_shrink = Rf_asReal(sshrink);
+    double *tg = (double *)R_alloc((size_t)T * n, sizeof(double)); /* targets row-major [T][n] */
+    memcpy(tg, REAL(starget), sizeof(double) * n);
+    for (int j = 0; j < nperm; j++)
+        for (R_xlen_t s = 0; s < n; s++) tg[(size_t)(1 + j) * n + s] = REAL(srand)[j + (size_t)nperm * s];
     uint8_t *sd = (uint8_t *)R_alloc(n, 1);
     for (R_xlen_t s = 0; s < n; s++) {
         double v = REAL(sseed)[s];
@@ -206,49 +217,69 @@ SEXP rvlR_search_multi(SEXP sdevices, SEXP starget, SEXP sm2, SEXP sseed, SEXP s
         rc = rvl_set_options(ctxs[r], &o);
         if (!rc) rc = rvl_set_shard(ctxs[r], r, world, lo, F);
         if (!rc) rc = rvl_load_matrix_f64_colmajor(ctxs[r], REAL(sm2) + lo, hi - lo, n, F);
-        if (!rc) rc = rvl_set_targets(ctxs[r], REAL(starget), n, 1);
+        if (!rc) rc = rvl_set_targets(ctxs[r], tg, n, T);
+        if (!rc && nperm) rc = rvl_set_null_targets(ctxs[r], 1);
         if (!rc) rc = rvl_set_seed(ctxs[r], sd, n, 0);
         if (rc) msg = rvl_last_error(ctxs[r]);
     }
     if (!rc) { rc = rvl_group_connect(ctxs, world); if (rc) msg = rvl_last_error(ctxs[0]); }
     if (!rc) { rc = rvl_group_search(ctxs, world, iters); if (rc) msg = rvl_last_error(ctxs[0]); }
     SEXP out = R_NilValue;
+    int nprot = 0;
     if (!rc) {
-        out = PROTECT(Rf_allocVector(VECSXP, 5));
-        SEXP names = PROTECT(Rf_allocVector(STRSXP, 5));
-        const char *nm[5] = { "cmi", "top", "seed.iter", "cmi.seed", "cmi.seed.iter0" };
-        for (int i = 0; i < 5; i++) SET_STRING_ELT(names, i, Rf_mkChar(nm[i]));
+        out = PROTECT(Rf_allocVector(VECSXP, 7));
+        SEXP names = PROTECT(Rf_allocVector(STRSXP, 7));
+        const char *nm[7] = { "cmi", "top", "top.score", "seed.iter", "cmi.seed", "cmi.seed.iter0", "cmi.rand" };
+        for (int i = 0; i < 7; i++) SET_STRING_ELT(names, i, Rf_mkChar(nm[i]));
         Rf_setAttrib(out, R_NamesSymbol, names);
         SEXP cmi = PROTECT(Rf_allocMatrix(REALSXP, F, iters));
         SEXP rtop = PROTECT(Rf_allocVector(INTSXP, iters));
+        SEXP rts = PROTECT(Rf_allocVector(REALSXP, iters));
         SEXP rcs = PROTECT(Rf_allocVector(REALSXP, iters));
         SEXP rsi = PROTECT(Rf_allocMatrix(REALSXP, iters, (int)n));
+        nprot = 7;
+        SEXP cr = R_NilValue;
+        if (nperm) {
+            SEXP dims = PROTECT(Rf_allocVector(INTSXP, 3));
+            INTEGER(dims)[0] = F; INTEGER(dims)[1] = nperm; INTEGER(dims)[2] = iters;
+            cr = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)F * nperm * iters));
+            Rf_setAttrib(cr, R_DimSymbol, dims);
+            nprot += 2;
+        }
         for (int r = 0; r < world && !rc; r++) {
             int64_t lo = ((int64_t)r * F) / world, cnt = ((int64_t)(r + 1) * F) / world - lo;
-            double *loc = (double *)R_alloc((size_t)iters * (cnt ? cnt : 1), sizeof(double));
-            int64_t *top = (int64_t *)R_alloc(iters, sizeof(int64_t));
-            uint8_t *si = (uint8_t *)R_alloc((size_t)iters * n, 1);
-            double *cs = (double *)R_alloc(iters, sizeof(double));
-            double ic0 = 0.0;
-            rvl_result res = { loc, top, NULL, si, cs, &ic0 };
+            double *loc = (double *)R_alloc((size_t)T * iters * (cnt ? cnt : 1), sizeof(double)); /* [T][iters][cnt] */
+            int64_t *top = (int64_t *)R_alloc((size_t)T * iters, sizeof(int64_t));
+            double *ts = (double *)R_alloc((size_t)T * iters, sizeof(double));
+            uint8_t *si = (uint8_t *)R_alloc((size_t)T * iters * n, 1);
+            double *cs = (double *)R_alloc((size_t)T * iters, sizeof(double));
+            double *ic0 = (double *)R_alloc((size_t)T, sizeof(double));
+            rvl_result res = { loc, top, ts, si, cs, ic0 };
             rc = rvl_search_fetch(ctxs[r], &res);
             if (rc) { msg = rvl_last_error(ctxs[r]); break; }
-            for (int it = 0; it < iters; it++)
+            for (int it = 0; it < iters; it++) {
                 memcpy(REAL(cmi) + (size_t)F * it + lo, loc + (size_t)it * cnt, sizeof(double) * (size_t)cnt);
+                for (int j = 0; j < nperm; j++)
+                    memcpy(REAL(cr) + ((size_t)it * nperm + j) * F + lo, loc + ((size_t)(1 + j) * iters + it) * cnt,
+                           sizeof(double) * (size_t)cnt);
+            }
             if (r == 0) {
                 for (int it = 0; it < iters; it++) {
                     INTEGER(rtop)[it] = (int)top[it] + 1;
+                    REAL(rts)[it] = ts[it];
                     REAL(rcs)[it] = cs[it];
                     for (R_xlen_t s = 0; s < n; s++) REAL(rsi)[it + (size_t)iters * s] = (double)si[(size_t)it * n + s];
                 }
-                SET_VECTOR_ELT(out, 4, Rf_ScalarReal(ic0));
+                SET_VECTOR_ELT(out, 5, Rf_ScalarReal(ic0[0]));
             }
         }
         SET_VECTOR_ELT(out, 0, cmi);
         SET_VECTOR_ELT(out, 1, rtop);
-        SET_VECTOR_ELT(out, 2, rsi);
-        SET_VECTOR_ELT(out, 3, rcs);
-        UNPROTECT(6);
+        SET_VECTOR_ELT(out, 2, rts);
+        SET_VECTOR_ELT(out, 3, rsi);
+        SET_VECTOR_ELT(out, 4, rcs);
+        SET_VECTOR_ELT(out, 6, cr);
+        UNPROTECT(nprot);
     }
     /* copy the message before the contexts that own it go away, then raise */
     char buf[512];
@@ -285,6 +316,20 @@ SEXP rvlR_pvalues(SEXP sctx, SEXP scmi, SEXP srand)
     R_xlen_t F = XLENGTH(scmi), R = XLENGTH(srand);
     SEXP out = PROTECT(Rf_allocVector(REALSXP, F));
     int rc = rvl_pvalues(ctx, REAL(scmi), F, REAL(srand), R, REAL(out));
+    UNPROTECT(1);
+    if (rc) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    return out;
+}
+
+/* .Call("rvlR_pvalues_iter", ctx, iter) -> p.val of iteration `iter` (1-based) of the last rvlR_search on ctx, from the
+ * scores still resident on the device (LIB:1868-1869); NA for a NaN score. */
+SEXP rvlR_pvalues_iter(SEXP sctx, SEXP siter)
+{
+    rvl_ctx *ctx = get_ctx(sctx);
+    int64_t rows = 0, samples = 0;
+    if (rvl_get_matrix_dims(ctx, &rows, &samples)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)rows));
+    int rc = rvl_pvalues_iter(ctx, Rf_asInteger(siter) - 1, REAL(out));
     UNPROTECT(1);
     if (rc) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
     return out;

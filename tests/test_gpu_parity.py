@@ -490,6 +490,16 @@ def test_permutation_null_and_pvalues(oracle):
             assert ok, (it, j, err)
         want = oracle.pvals(out["cmi"][:, it], out["cmi_rand"][it])
         assert np.array_equal(out["p_val"][it], want)
+    # the stand-alone call on host arrays gives the same numbers; a NaN score gives NaN (R: NA), NaN nulls are not counted
+    with _ctx() as ctx:
+        it = 1
+        assert np.array_equal(ctx.pvalues(out["cmi"][:, it], out["cmi_rand"][it]), want)
+        c2 = out["cmi"][:, it].copy()
+        c2[3] = np.nan
+        r2 = out["cmi_rand"][it].copy()
+        r2[0, 0] = np.nan
+        got = ctx.pvalues(c2, r2)
+        assert np.isnan(got[3]) and np.array_equal(got, oracle.pvals(c2, r2), equal_nan=True)
     assert out["FDR"].shape == out["p_val"].shape and np.all((out["FDR"] >= 0) & (out["FDR"] <= 1))
     assert np.all(out["FDR"] >= np.where(out["cmi"].T < 0, 1 - out["p_val"], out["p_val"]) - 1e-15)
 
@@ -585,6 +595,50 @@ def test_two_shards_equal_single_shard():
         assert np.array_equal(o["cmi"][0], single["cmi"][0][:, lo:lo + cnt])
     for c in ctxs:
         c.close()
+
+
+# ------------------------------------------------------------------ one persistent launch == split-phase launches
+
+@pytest.mark.parametrize("n,F,iters,T,kw", [(140, 900, 5, 1, {}), (82, 300, 3, 1, {"null_seed": True}),
+                                            (1000, 3000, 4, 3, {}), (64, 50, 2, 2, {}), (300, 40, 3, 1, {})])
+def test_fused_search_kernel_equals_split_phase_launches(n, F, iters, T, kw):
+    """rvl_search runs the whole search as ONE cooperative launch (k_search).  It must reproduce the split-phase
+    launches (k_score / k_argmax / k_advance per iteration) bit for bit: same functions, same order.  Covered:
+    single and several targets, NULLSEED (IC dispatch -> CIC after the first merge), target.match = negative,
+    the literal x-axis pass chosen for few rows (F <= 64), permutation-null targets, repeated searches."""
+    w = _workload(n, F, **kw)
+    rng = np.random.default_rng(F)
+    targets = np.stack([w["target"]] + [rng.standard_normal(n) for _ in range(T - 1)])
+    for negative in (False, True):
+        res = {}
+        for fused in (True, False):
+            with _ctx(negative=negative) as ctx:
+                ctx.set_fused(fused)
+                ctx.load_matrix(w["m2"])
+                ctx.set_targets(targets)
+                ctx.set_seed(w["seed"])
+                a = ctx.search(iters)
+                b = ctx.search(iters)                  # a second search on the same context (odd iters: slot parity)
+                l0 = ctx.launch_count()
+                ctx.search(iters, fetch=False)
+                res[fused] = (a, b, ctx.launch_count() - l0)
+        for k in ("cmi", "top", "top_score", "seed_iter", "cmi_seed", "ic_seed0"):
+            assert np.array_equal(res[True][0][k], res[False][0][k], equal_nan=True), (k, negative)
+            assert np.array_equal(res[True][1][k], res[True][0][k], equal_nan=True), (k, negative)
+        assert res[True][2] < res[False][2]            # 1 + a few launches instead of 3 per iteration
+    # permutation-null targets ride along (scored against target 0's seed, never selected)
+    perm = np.stack([w["target"]] + [rng.permutation(w["target"]) for _ in range(3)])
+    out = {}
+    for fused in (True, False):
+        with _ctx() as ctx:
+            ctx.set_fused(fused)
+            ctx.load_matrix(w["m2"])
+            ctx.set_targets(perm, first_null=1, permuted=True)
+            ctx.set_seed(w["seed"])
+            out[fused] = ctx.search(iters)
+    for k in ("cmi", "top", "seed_iter", "cmi_seed"):
+        assert np.array_equal(out[True][k][:1] if k != "cmi" else out[True][k], out[False][k][:1] if k != "cmi" else out[False][k],
+                              equal_nan=True), k
 
 
 # ------------------------------------------------------------------ config C1's shape (gpunit example: 82 x ~17.8k)
