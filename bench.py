@@ -75,6 +75,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other named configs")
     ap.add_argument("--no-single-rank-check", action="store_true")
+    ap.add_argument("--fused", action="store_true",
+                    help="the one persistent k_search launch per search instead of the per-iteration launches (k_score / k_argmax / "
+                         "k_advance); bit-identical results, measured 2-3 %% slower on B200")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="candidate exchange between ranks: peer-memory stores over NVLink (CUDA IPC) or NCCL all-gather")
     return ap.parse_args()
@@ -345,6 +348,7 @@ class Bench:
         if not by_target:
             ctx.set_shard(rank, world, lo, F)
         ctx.set_profiling(main)
+        ctx.set_fused(args.fused)
         # ---- resident inputs (outside the timed region for `value`)
         ctx.load_matrix(m2_u8)
         ctx.set_targets(targets)
@@ -355,7 +359,7 @@ class Bench:
             use_p2p, use_nccl, send, recv = self.connect(ctx)
 
         def one_search():
-            if not use_nccl:       # one persistent launch per search (k_search); ranks meet through peer memory inside it
+            if not use_nccl:       # every launch of the search enqueued by one call; ranks meet through peer memory on the device
                 ctx.search_run(iters)
                 return
             ctx.search_begin(iters)

@@ -202,13 +202,15 @@ int rvl_p2p_disable(rvl_ctx *ctx);
  * seed ICs identical on every context). */
 int rvl_group_connect(rvl_ctx **ctxs, int n);
 int rvl_group_search(rvl_ctx **ctxs, int n, int iters);
-/* The whole search of this shard enqueued without waiting (rvl_search_fetch / rvl_synchronize wait): ONE persistent
- * cooperative launch (k_search: score, rank, peer exchange over NVLink, merge and table update of every iteration
- * inside the kernel) when the device allows it, the split-phase launches otherwise.  world > 1 needs the peer exchange
- * (rvl_p2p_import or rvl_group_connect) and every rank must call it.  Results are bit-identical either way. */
+/* The whole search of this shard enqueued without waiting (rvl_search_fetch / rvl_synchronize wait): the split-phase
+ * launches back to back (k_score, k_argmax, k_advance per iteration; nothing synchronises with the host), or -- after
+ * rvl_set_fused(ctx, 1) -- ONE persistent cooperative launch (k_search: score, rank, peer exchange over NVLink, merge
+ * and table update of every iteration inside the kernel).  world > 1 needs the peer exchange (rvl_p2p_import or
+ * rvl_group_connect) and every rank must call it.  Results are bit-identical either way. */
 int rvl_search_run(rvl_ctx *ctx, int iters);
-/* on = 0 keeps rvl_search / rvl_search_run / rvl_group_search on the split-phase launches (validation, profiling of
- * the individual kernels).  Default 1. */
+/* on = 1 makes rvl_search / rvl_search_run / rvl_group_search use the single persistent launch (k_search) when the
+ * device can launch it cooperatively.  Default 0: on B200 the persistent form measured 2-3 % slower than the
+ * split-phase launches at 1 and at 8 GPUs, so it is kept as an option, tested bit-identical. */
 int rvl_set_fused(rvl_ctx *ctx, int on);
 int rvl_search_begin(rvl_ctx *ctx, int iters);
 size_t rvl_candidate_bytes(const rvl_ctx *ctx);

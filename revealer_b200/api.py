@@ -636,6 +636,39 @@ def revealer_search_multi_gpu(target, m2, seed=None, max_n_iter=5, target_match=
             c.close()
 
 
+def revealer_search_target_batch_multi_gpu(targets, m2, seed=None, max_n_iter=1, target_match="positive", devices=(0, 1),
+                                           n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75):
+    """A batch of independent searches (one per target row of `targets`, e.g. 256 drug-response profiles against
+    one matrix: BASELINE config C5) sharded by TARGET over several GPUs of this process: every device holds the
+    whole bit matrix and its own contiguous block of targets, so nothing is exchanged at all ("prefer
+    target-sharding when n_targets >= P").  All devices are enqueued before the first fetch.  Returns dict(cmi
+    [T][iters][F], top, top_score, seed_iter, cmi_seed, ic_seed0) in target order -- equal to the T single runs."""
+    if target_match not in ("positive", "negative"):
+        raise RevealerError(_lib.RVL_ERR_ARG, 'target.match must be "positive" or "negative"')
+    targets = np.ascontiguousarray(np.atleast_2d(np.asarray(targets, dtype=np.float64)))
+    T, n = targets.shape
+    world = len(devices)
+    if T < world:
+        raise RevealerError(_lib.RVL_ERR_ARG, "target sharding needs at least one target per device; shard rows instead")
+    ctxs, spans = [], []
+    try:
+        for r, dev in enumerate(devices):
+            lo, cnt = shard_rows(T, world, r)
+            c = RevealerContext(dev, n_grid=n_grid, bandwidth_mult=bandwidth_mult, bandwidth_shrink=bandwidth_shrink,
+                                negative=(target_match == "negative"))
+            ctxs.append(c)
+            spans.append((lo, cnt))
+            c.load_matrix(m2)
+            c.set_targets(targets[lo:lo + cnt])
+            c.set_seed(np.zeros(n, dtype=np.uint8) if seed is None else seed)
+            c.search_run(max_n_iter)                      # asynchronous: the devices run concurrently
+        parts = [c.search_fetch(max_n_iter) for c in ctxs]
+        return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def p_adjust_fdr(p):
     """R's p.adjust(p, method = "fdr") (Benjamini-Hochberg): pmin(1, cummin(n / i * p[o]))[ro], o = decreasing order."""
     p = np.asarray(p, dtype=np.float64)

@@ -176,7 +176,7 @@ struct rvl_ctx {
     unsigned int epoch = 0;
 
     // fused search (k_search): one persistent cooperative launch per search
-    int fused = 1;                  // rvl_set_fused
+    int fused = 0;                  // rvl_set_fused (default off: measured 2-3 % slower than the split-phase launches)
     int search_grid_x = -1;         // -1: not configured; 0: cooperative launch unavailable
     size_t search_smem = 0;
     unsigned long long *d_swork = nullptr; // [sctr_cap] per-iteration item counters

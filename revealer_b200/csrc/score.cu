@@ -842,6 +842,31 @@ __device__ __forceinline__ void rvl_table_incr_warp(const double *__restrict__ u
     out[RVL_MAXG + lane] = t1_old + d;
 }
 
+// k_search: every block waits ONCE per iteration for the stamps of all `world` ranks and all seed-owning targets (its
+// first warp polls, with a short back-off so that a few hundred pollers do not crowd the L2 line the peers' stores and
+// stamps land in); afterwards the candidate records of the iteration are readable by every thread of the block.
+__device__ __forceinline__ void rvl_wait_stamps(const RvlParams &P, const RvlPeerXchg &X, int nreal)
+{
+    if (threadIdx.x < 32) {
+        for (int idx = threadIdx.x; idx < nreal * P.world; idx += 32) {
+            const int r = idx / nreal, t = idx - r * nreal;
+            volatile unsigned int *st = reinterpret_cast<volatile unsigned int *>(X.local + X.stamps_off) +
+                                        ((size_t)X.parity * P.world + r) * P.T + t;
+            const long long t0 = clock64();
+            while (*st != X.stamp) {
+                __nanosleep(100);
+                if (clock64() - t0 > 4000000000ll) { // ~2 s: a peer is gone; fail loudly instead of hanging
+                    *X.err = 1;
+                    break;
+                }
+            }
+        }
+        if (P.world > 1) __threadfence_system();
+        else __threadfence();
+    }
+    __syncthreads();
+}
+
 // One (table node m, target t) task of the merge step done by ONE warp (k_search): wait for the ranks' stamps, resolve
 // the global winner, node-0 duties (new seed, seed.iter, top, seed state), in-place table update.  Returns false when
 // the table of this target must be REBUILT (the dispatch mode changed): that takes a block (rvl_advance_task).
@@ -851,6 +876,8 @@ __device__ bool rvl_advance_warp(const RvlParams &P, RvlTarget *tg_all, const do
                                  int iters, int first_null, int64_t *__restrict__ top, double *__restrict__ top_score,
                                  uint64_t *__restrict__ seed_iter, const RvlPeerXchg &X, int t, int m, bool last_iter, int lane)
 {
+    // m >= 0: table node m of target t.  m == -1: the target's bookkeeping instead (new seed, seed.iter, top, seed state)
+    // -- a task of its own so that no table node waits for it.
     const unsigned FULL = 0xffffffffu;
     const RvlTarget tg = tg_all[t]; // only the per-target constants are used (never nz / mode / bcv_z)
     const int owner = tg.seed_of;
@@ -858,8 +885,8 @@ __device__ bool rvl_advance_warp(const RvlParams &P, RvlTarget *tg_all, const do
     const uint64_t *zold = seeds_in + (size_t)owner * P.words;
     const unsigned char *recv = X.local + (size_t)X.parity * P.world * P.T * rec_bytes;
     // what does not depend on the winner is fetched before the wait: this node's current values
-    double *out = tt + (((size_t)t * P.tt_nodes + m) * 2) * RVL_MAXG;
-    const bool table = !(P.dense_x || last_iter);
+    double *out = tt + (((size_t)t * P.tt_nodes + (m < 0 ? 0 : m)) * 2) * RVL_MAXG;
+    const bool table = !(P.dense_x || last_iter) && m >= 0;
     const double t0_old = table ? rvl_ld<COH>(out + lane) : 0.0, t1_old = table ? rvl_ld<COH>(out + RVL_MAXG + lane) : 0.0;
     // the records of this iteration sit in the local buffer once every rank's stamp for (parity, rank, owner) is there
     double bv = 0.0;
@@ -869,18 +896,7 @@ __device__ bool rvl_advance_warp(const RvlParams &P, RvlTarget *tg_all, const do
         const int r = r0 + lane;
         double hs = 0.0;
         int64_t hr = -1;
-        if (r < P.world) {
-            volatile unsigned int *st = reinterpret_cast<volatile unsigned int *>(X.local + X.stamps_off) +
-                                        ((size_t)X.parity * P.world + r) * P.T + owner;
-            const long long t0 = clock64();
-            while (*st != X.stamp) {
-                if (clock64() - t0 > 4000000000ll) { // ~2 s: a peer is gone; fail loudly instead of hanging
-                    *X.err = 1;
-                    break;
-                }
-            }
-            if (P.world > 1) __threadfence_system();
-            else __threadfence();
+        if (r < P.world) { // (the block has waited for every stamp of this iteration: rvl_wait_stamps)
             const unsigned char *rec = recv + ((size_t)r * P.T + owner) * rec_bytes;
             hs = rvl_ld<true>(reinterpret_cast<const double *>(rec));
             hr = (int64_t)rvl_ld<true>(reinterpret_cast<const uint64_t *>(rec + sizeof(double)));
@@ -904,7 +920,7 @@ __device__ bool rvl_advance_warp(const RvlParams &P, RvlTarget *tg_all, const do
     const int nz_old = rvl_warp_sum_i(c0), nz = rvl_warp_sum_i(c1);
     const int mode_old = tg.is_const ? RVL_MODE_ZERO : ((nz_old == 0 || nz_old == P.n) ? RVL_MODE_IC : RVL_MODE_CIC);
     const int mode = tg.is_const ? RVL_MODE_ZERO : ((nz == 0 || nz == P.n) ? RVL_MODE_IC : RVL_MODE_CIC);
-    if (m == 0) {
+    if (m < 0) {
         if (lane == 0) {
             tg_all[t].nz = nz;
             tg_all[t].bcv_z = bcvtab[nz];
@@ -923,6 +939,7 @@ __device__ bool rvl_advance_warp(const RvlParams &P, RvlTarget *tg_all, const do
                 zi[w] = v;
             }
         }
+        return true;
     }
     if (!table) return true; // no table kept / nobody will read it
     if (mode == RVL_MODE_ZERO) {
@@ -1426,6 +1443,9 @@ __device__ __forceinline__ unsigned long long rvl_globaltimer()
     return t;
 }
 
+#ifndef RVL_KSEARCH_COH
+#define RVL_KSEARCH_COH true
+#endif
 __global__ void __launch_bounds__(RVL_KSCORE_WARPS * 32, RVL_SCORE_MIN_CTAS)
 k_search(const RvlSearchArgs a)
 {
@@ -1434,9 +1454,8 @@ k_search(const RvlSearchArgs a)
     const RvlParams &P = a.P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * RVL_KSCORE_WARPS + warp, nslots = gridDim.x * RVL_KSCORE_WARPS;
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[6] = rvl_globaltimer(); // kernel entry (block 0)
     rvl_logtab_fill(rvl_logtab_g);
-    RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
-    uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_KSCORE_WARPS);
     const int nodes = P.dense_x ? 1 : P.tt_nodes;
     const int ntasks = nodes * P.T;
     unsigned int nbar = 0;
@@ -1452,12 +1471,13 @@ k_search(const RvlSearchArgs a)
             a.part[(size_t)t * nslots + slot] = h;
         }
         __syncwarp();
-#ifndef RVL_KSEARCH_COH
-#define RVL_KSEARCH_COH true
-#endif
-        rvl_score_phase<RVL_KSEARCH_COH>(P, a.bits, a.u_all, a.xc_all, a.tg_all, seeds_cur, a.bcvtab, a.tt,
-                              a.scores + (size_t)it * P.T * P.F, a.part, a.work + it, a.ctr, a.uniq, a.U, scr[warp],
-                              yrows + (size_t)warp * P.words, slot, nslots, lane);
+        {
+            RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
+            uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_KSCORE_WARPS);
+            rvl_score_phase<RVL_KSEARCH_COH>(P, a.bits, a.u_all, a.xc_all, a.tg_all, seeds_cur, a.bcvtab, a.tt,
+                                             a.scores + (size_t)it * P.T * P.F, a.part, a.work + it, a.ctr, a.uniq, a.U, scr[warp],
+                                             yrows + (size_t)warp * P.words, slot, nslots, lane);
+        }
         __threadfence(); // this warp's part[] entries before the block's ticket
         __syncthreads();
         if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[it * 8 + 1] = rvl_globaltimer(); // block 0 done scoring
@@ -1467,6 +1487,7 @@ k_search(const RvlSearchArgs a)
         X.parity = (a.seq0 + it) & 1;
         if (threadIdx.x == 0) s_last = (atomicAdd(a.done + it, 1u) == gridDim.x - 1u);
         __syncthreads();
+#ifndef RVL_KSEARCH_SCORE_ONLY
         if (s_last) {
             if (a.dbg && threadIdx.x == 0) a.dbg[it * 8 + 2] = rvl_globaltimer(); // every block done scoring
             __threadfence();
@@ -1479,13 +1500,17 @@ k_search(const RvlSearchArgs a)
         // block-level pass of rvl_advance_task.  Nothing of the table is touched after the last iteration.
         const bool last_iter = (it + 1 == a.iters);
         bool rebuild = false;
-        for (int q = slot; q < ntasks; q += nslots) {
-            const int t = q / nodes, m = q - t * nodes;
+        rvl_wait_stamps(P, X, a.nreal);
+        for (int q = slot; q < ntasks + P.T; q += nslots) { // the last T tasks are the targets' bookkeeping (m = -1)
+            const int t = q < ntasks ? q / nodes : q - ntasks, m = q < ntasks ? q - t * nodes : -1;
             if (!rvl_advance_warp<true>(P, a.tg_all, a.u_all, seeds_cur, seeds_nxt, a.bcvtab, a.tt, a.rec_bytes, it, a.iters,
                                         a.first_null, a.top, a.top_score, a.seed_iter, X, t, m, last_iter, lane))
                 rebuild = true;
         }
         if (rebuild && lane == 0) atomicOr(a.need + it, 1u);
+#else
+        const bool last_iter = (it + 1 == a.iters);
+#endif
         if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[it * 8 + 4] = rvl_globaltimer(); // block 0's tasks done
         if (!last_iter) {
             nbar++;

@@ -174,6 +174,33 @@ def test_group_search_over_two_gpus_equals_one_gpu():
         assert np.array_equal(two["cmi_seed"], one["cmi_seed"])
 
 
+def test_target_sharded_batch_equals_single_gpu_batch_and_individual_runs():
+    """Config C5's multi-GPU form: targets sharded over the devices (whole matrix on each, no exchange).  The batch
+    must equal the same batch on one GPU and the targets run one at a time, bit for bit."""
+    import torch
+    import revealer_b200 as rb
+    from revealer_b200 import synth
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    w = synth.make_workload(n=200, F=3000)
+    rng = np.random.default_rng(5)
+    targets = np.stack([w["target"]] + [rng.standard_normal(200) for _ in range(6)])      # 7 targets over 2 devices: 3 + 4
+    multi = rb.revealer_search_target_batch_multi_gpu(targets, w["m2"], w["seed"], max_n_iter=2, devices=(0, 1))
+    with _ctx() as ctx:
+        ctx.load_matrix(w["m2"])
+        ctx.set_targets(targets)
+        ctx.set_seed(w["seed"])
+        one = ctx.search(2)
+        for k in ("cmi", "top", "top_score", "seed_iter", "cmi_seed", "ic_seed0"):
+            assert np.array_equal(multi[k], one[k], equal_nan=True), k
+        for t in (0, 3, 6):
+            ctx.set_targets(targets[t])
+            ctx.set_seed(w["seed"])
+            single = ctx.search(2)
+            assert np.array_equal(single["top"][0], multi["top"][t])
+            assert np.array_equal(single["cmi"][0], multi["cmi"][t], equal_nan=True)
+
+
 def test_row_block_of_a_larger_r_matrix_loads_in_place():
     """rvl_load_matrix_f64_colmajor with ld > F: a shard's row block of the whole column-major R matrix, read
     where it lies (what rvlR_search_multi passes).  Only the block's rows may be read and shipped."""

@@ -186,3 +186,13 @@ def test_r_golden_vectors_if_present(oracle):
         assert abs(oracle.bcv(y) - c["bcv_y"]) <= 1e-9 * c["bcv_y"]
         assert abs(oracle.assoc(x, y) - c["IC"]) <= 1e-6 * abs(c["IC"]) + 1e-7
         assert abs(oracle.cond_assoc(x, y, z) - c["CIC"]) <= 1e-6 * abs(c["CIC"]) + 1e-7
+    if "search" in g:      # the iteration loop run by R with the reference's own functions (tools/make_golden.R)
+        from parity_tol import score_close
+        s = g["search"]
+        r = oracle.search(np.array(s["target"], dtype=float), np.array(s["m2"], dtype=float), np.array(s["seed"], dtype=float),
+                          int(s["iters"]))
+        assert list(r["top"]) == [int(v) for v in s["top"]]
+        assert np.array_equal(r["seed_iter"], np.array(s["seed_iter"], dtype=float))
+        assert score_close(r["cmi"], np.array(s["cmi"], dtype=float))[0]
+        assert score_close(r["cmi_seed"], np.array(s["cmi_seed"], dtype=float))[0]
+        assert score_close([r["ic_seed0"]], [float(s["ic_seed0"])])[0]

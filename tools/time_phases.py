@@ -15,11 +15,17 @@ with rb.RevealerContext(0) as ctx:
     for _ in range(3):
         ctx.search(iters, fetch=False)
     ctx._ck(ctx._lib.rvl_debug_phase_times(ctx._h, None, 0))
+    import torch
+    ctx.set_profiling(True)
+    ctx.score_kernel_time(reset=True)
     ctx.search(iters, fetch=False)
+    kms, kn = ctx.score_kernel_time(reset=True)
     out = (C.c_uint64 * (8 * iters))()
     ctx._ck(ctx._lib.rvl_debug_phase_times(ctx._h, out, iters))
     t = np.array(out, dtype=np.int64).reshape(iters, 8)
     t0 = t[0, 0]
+    print("k_search by events: %.1f us (%d launch); entry -> first scoring %.1f us; entry -> last barrier-stamp %.1f us" %
+          (kms * 1e3, kn, (t[0, 0] - t[0, 6]) / 1e3, (t[iters - 1, 5] - t[0, 6]) / 1e3))
     print("it  score(b0)  all_done-b0  publish  merge(b0)-after-publish  barrier-wait  iteration")
     for it in range(iters):
         s, b0, alld, pub, mrg, bar = t[it, :6]
