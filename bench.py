@@ -347,7 +347,6 @@ class Bench:
         ctx.set_stream(self.stream.cuda_stream)
         if not by_target:
             ctx.set_shard(rank, world, lo, F)
-        ctx.set_profiling(main)
         ctx.set_fused(args.fused)
         # ---- resident inputs (outside the timed region for `value`)
         ctx.load_matrix(m2_u8)
@@ -371,8 +370,6 @@ class Bench:
         for _ in range(warmup):
             one_search()
         self.barrier()
-        ctx.score_kernel_time(reset=True)
-        ctx.counters(reset=True)
         launches0 = ctx.launch_count()
         sampler = ClockSampler(local) if main else None
         if sampler:
@@ -388,10 +385,28 @@ class Bench:
         clocks = sampler.stop() if sampler else None
         ms = self.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / steps)
         gpu_launches = ctx.launch_count() - launches0      # this rank's own kernels (NCCL's are not counted)
-        k_ms, k_n = ctx.score_kernel_time(reset=True)
-        ctr = ctx.counters(reset=True)
         value = F * T * iters / (ms * 1e-3)
         res = ctx.search_fetch(iters)
+        # the timed region above runs the product path as shipped (no instrumentation); the dominant kernel's own duration
+        # and work counters come from a few more searches with the profiling switch on (CUDA events around every launch)
+        k_ms, k_n, ctr, ms_prof = 0.0, 0, None, None
+        if main:
+            ctx.set_profiling(True)
+            ctx.score_kernel_time(reset=True)
+            ctx.counters(reset=True)
+            nprof = max(1, min(steps, 3))
+            self.barrier()
+            pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nprof)]
+            for a, b in pe:
+                self.flush.zero_()
+                a.record(self.stream)
+                one_search()
+                b.record(self.stream)
+            self.barrier()
+            ms_prof = sum(a.elapsed_time(b) for a, b in pe) / nprof
+            k_ms, k_n = ctx.score_kernel_time(reset=True)
+            ctr = ctx.counters(reset=True)
+            ctx.set_profiling(False)
         check = result_check(res, lo, F, dist, world, t_offset=t_lo, gather_targets=by_target)
         uniq = ctx.unique_rows()
         executed = self.max_over_ranks(0.0)  # placeholder overwritten below
@@ -568,10 +583,13 @@ class Bench:
             except Exception:
                 pass
             out["roofline"] = {
-                "kernel": "k_score", "bound": "fp64", "achieved": flops / dur / 1e12, "peak": fp64_peak,
+                "kernel": "k_search" if args.fused else "k_score", "bound": "fp64", "achieved": flops / dur / 1e12, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": flops / dur / 1e12 / fp64_peak if fp64_peak else None, "traffic": traffic,
                 "peak_source": "measured live: rvl_measure_fp64_peak (DFMA chain); MEASURED_PEAKS.json has no FP64 figure",
-                "launch_ms": dur * 1e3, "launches": int(k_n), "share_of_step": k_ms / (ms * steps),
+                "launch_ms": dur * 1e3, "launches": int(k_n), "share_of_step": k_ms / (ms_prof * nprof),
+                "measured": "CUDA events around every launch of the kernel on its stream, in %d extra searches with the "
+                            "profiling switch on (%.3f ms per search there, %.3f ms in the uninstrumented timed region)"
+                            % (nprof, ms_prof, ms),
                 "convention": "EXECUTED work from kernel counters: exp=%d flop, log=%d flop (FP64-pipe SASS "
                               "instructions x2), + plain FMA/ADD" % (FLOP_PER_EXP, FLOP_PER_LOG),
                 "per_launch": {"evaluations": evals, "exp": exps, "log": logs, "flop": flops},

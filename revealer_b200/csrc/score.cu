@@ -414,33 +414,35 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
     const unsigned m4 = mDirect & rvl_bits(G1 - im, iM);            // both classes visible
     const unsigned m2m = mDirect & ~rvl_bits(0, iM);                // majority invisible: the minority class's two terms
     const unsigned m2M = mDirect & ~m4 & ~m2m;                      // minority invisible: the majority class's two terms
-    const int c4 = __popc(m4), c2 = __popc(m2m | m2M);
+    const int c4 = __popc(m4), c2M = __popc(m2M), c2m = __popc(m2m);
     const int ndead = active ? G - __popc(mAlive) : 0;
     double accF = 0.0;
     if (bF >= 0) // sum over the factorised interval: g (log g SV + LV) + eps' (G log g + LLV + G)
         accF = fma(SV, S.tab[1][bF], LV * S.tab[0][bF]) + epsq * fma((double)G, S.tab[2][bF], (double)(bF + 1) * (LLV + (double)G));
     // list offsets: four-term columns from the front of S.items, two-term columns from the back (bit 15: the
-    // surviving class is the minority one)
-    int o4 = c4, o2 = c2;
+    // surviving class is the minority one) -- the majority class's columns first, then the minority's, so that the
+    // lanes of a pass-C round read the same class rows (broadcast loads) except in the one round where the kinds meet
+    int o4 = c4, oM = c2M, om = c2m;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int u4 = __shfl_up_sync(FULL, o4, o), u2 = __shfl_up_sync(FULL, o2, o);
-        if (lane >= o) { o4 += u4; o2 += u2; }
+        const int u4 = __shfl_up_sync(FULL, o4, o), uM = __shfl_up_sync(FULL, oM, o), um = __shfl_up_sync(FULL, om, o);
+        if (lane >= o) { o4 += u4; oM += uM; om += um; }
     }
-    const int n4 = __shfl_sync(FULL, o4, 31), n2 = __shfl_sync(FULL, o2, 31);
+    const int n4 = __shfl_sync(FULL, o4, 31), n2M = __shfl_sync(FULL, oM, 31), n2 = n2M + __shfl_sync(FULL, om, 31);
     o4 -= c4;
-    o2 -= c2;
+    oM -= c2M;
+    om += n2M - c2m;
     for (unsigned m = m4; m; m &= m - 1u) {
         const int jp = __ffs((int)m) - 1, j = am ? G1 - jp : jp;
         S.items[o4++] = (uint16_t)((j << 5) | lane);
     }
     for (unsigned m = m2M; m; m &= m - 1u) {
         const int jp = __ffs((int)m) - 1, j = am ? G1 - jp : jp;
-        S.items[RVL_MAXG * RVL_MAXG - 1 - (o2++)] = (uint16_t)((j << 5) | lane);
+        S.items[RVL_MAXG * RVL_MAXG - 1 - (oM++)] = (uint16_t)((j << 5) | lane);
     }
     for (unsigned m = m2m; m; m &= m - 1u) {
         const int jp = __ffs((int)m) - 1, j = am ? G1 - jp : jp;
-        S.items[RVL_MAXG * RVL_MAXG - 1 - (o2++)] = (uint16_t)((j << 5) | lane | 0x8000);
+        S.items[RVL_MAXG * RVL_MAXG - 1 - (om++)] = (uint16_t)((j << 5) | lane | 0x8000);
     }
     *ndirect_out = n4 + n2;
     *nfact_out = rvl_warp_sum_i(bF + 1);
