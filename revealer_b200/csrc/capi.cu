@@ -610,7 +610,7 @@ extern "C" int rvl_load_matrix_f64_colmajor(rvl_ctx *ctx, const double *m2, int6
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof set, &set) == 0) avail = CPU_COUNT(&set);
         nthreads = avail / (ctx->world > 0 ? ctx->world : 1);
-        if (nthreads > 16) nthreads = 16;
+        if (nthreads > 32) nthreads = 32;
         if ((double)F * (double)n < 4e6 || W < 2) nthreads = 0; // small matrices: not worth starting threads
     }
     void *plan = nullptr;

@@ -491,7 +491,22 @@ extern "C" int rvl_gct_parse_to_bits(rvl_gct *g, const int32_t *cols, int64_t n,
         GCK(cudaMalloc((void **)&S.d_inv, sizeof(int32_t) * (size_t)g->ncol));
         S.inv_cap = (size_t)g->ncol;
     }
-    GCK(cudaMemsetAsync(S.d_rowbase, 0, sizeof(long long), st));
+    // A shard that loads its own row block ships only that block's bytes: the host line index (memchr scan, a few
+    // threads) gives the byte range of rows [first_row, first_row + n_rows), and the device row counter starts at
+    // first_row.  The whole file: no index needed, every line is counted on the device.
+    const bool partial = (first_row > 0 || first_row + n_rows < g->nrow);
+    size_t byte_lo = g->data_off, byte_hi = g->size;
+    long long expect_rows = (long long)g->nrow;
+    if (partial) {
+        if (gct_index(g)) { snprintf(errbuf, errcap, "%s", g->err.c_str()); return -2; }
+        byte_lo = n_rows > 0 ? g->line_start[(size_t)first_row] : g->size;
+        byte_hi = (first_row + n_rows < g->nrow) ? g->line_start[(size_t)(first_row + n_rows)] : g->size;
+        if (n_rows == 0) byte_hi = byte_lo;
+        expect_rows = (long long)(first_row + n_rows);
+    }
+    const long long row0 = partial ? (long long)first_row : 0ll;
+    GCK(cudaMemcpyAsync(S.d_rowbase, &row0, sizeof(long long), cudaMemcpyHostToDevice, st));
+    GCK(cudaStreamSynchronize(st)); // row0 is a stack variable
     GCK(cudaMemcpyAsync(S.d_inv, inv.data(), sizeof(int32_t) * (size_t)g->ncol, cudaMemcpyHostToDevice, st));
     GCK(cudaMemsetAsync(d_bits, 0, sizeof(uint64_t) * (size_t)n_rows * words, st)); // rows the file lacks stay empty
     int dev = 0, sms = 148;
@@ -502,7 +517,7 @@ extern "C" int rvl_gct_parse_to_bits(rvl_gct *g, const int32_t *cols, int64_t n,
     GCK(cudaEventRecord(S.ev_done[0], st));
     GCK(cudaEventRecord(S.ev_done[1], st));
 
-    const char *p = g->base + g->data_off, *fend = g->base + g->size;
+    const char *p = g->base + byte_lo, *fend = g->base + byte_hi;
     int half = 0;
     while (p < fend) {
         // a chunk of whole lines: up to CH bytes, cut back to the last newline
@@ -541,7 +556,7 @@ extern "C" int rvl_gct_parse_to_bits(rvl_gct *g, const int32_t *cols, int64_t n,
     GCK(cudaMemcpyAsync(&flag, d_flag, sizeof flag, cudaMemcpyDeviceToHost, st));
     GCK(cudaStreamSynchronize(st));
     GCK(cudaStreamSynchronize(S.copy));
-    if (rows_seen != g->nrow) {
+    if (rows_seen != expect_rows) {
         snprintf(errbuf, errcap, "file has %lld data lines, header says %lld", rows_seen, (long long)g->nrow);
         return -2;
     }
