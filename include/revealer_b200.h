@@ -233,6 +233,12 @@ int rvl_pvalues(rvl_ctx *ctx, const double *cmi, int64_t F, const double *cmi_ra
  * the F p-values come back.  A NaN score gives a NaN p-value (R: NA).  Single shard only. */
 int rvl_pvalues_iter(rvl_ctx *ctx, int iter, double *out_pval);
 
+/* The first k entries of R's order(cmi[, iter], decreasing = !negative) for one target of the last search (the
+ * n.markers rows REVEALER.v1 displays, LIB:1858-1864), ranked on the device from the resident scores: stable (ties ->
+ * lower row), NaN last.  out_rows: GLOBAL row indices (this shard's rows only: with world > 1 merge the shards'
+ * lists with the same rule); out_scores may be NULL.  k is clipped to the shard's row count. */
+int rvl_topk(rvl_ctx *ctx, int iter, int64_t target_index, int64_t k, int64_t *out_rows, double *out_scores);
+
 /* ---- introspection (parity tests, INTEGRATION checks) ----------------------------------- */
 
 /* bcv(target_t) as computed on the device. */

@@ -83,6 +83,7 @@ SIGNATURES = {
     "rvl_assoc": (_i, [_vp, _i64, _u8p, _i64, _dp]),
     "rvl_pvalues": (_i, [_vp, _dp, _i64, _dp, _i64, _dp]),
     "rvl_pvalues_iter": (_i, [_vp, _i, _dp]),
+    "rvl_topk": (_i, [_vp, _i, _i64, _i64, _i64p, _dp]),
     "rvl_get_target_bandwidth": (_i, [_vp, _i64, _dp]),
     "rvl_get_binary_bandwidth_table": (_i, [_vp, _dp]),
     "rvl_get_matrix_dims": (_i, [_vp, _i64p, _i64p]),

@@ -412,6 +412,14 @@ class RevealerContext:
         self._ck(self._lib.rvl_pvalues(self._h, _dp(c), len(c), _dp(r), len(r), _dp(out)))
         return out
 
+    def topk(self, it, k, target_index=0):
+        """(rows, scores): the first k entries of R's order() of iteration `it`'s scores, ranked on the device."""
+        k = int(min(k, self.F or 0))
+        rows = np.empty(k, dtype=np.int64)
+        sc = np.empty(k, dtype=np.float64)
+        self._ck(self._lib.rvl_topk(self._h, int(it), int(target_index), k, rows.ctypes.data_as(C.POINTER(C.c_int64)), _dp(sc)))
+        return rows, sc
+
     def pvalues_iter(self, it):
         """p-values of iteration `it` of the last search from the resident scores (rvl_pvalues_iter)."""
         out = np.empty(self.F, dtype=np.float64)
@@ -544,7 +552,8 @@ def revealer_search(target, m2, seed=None, max_n_iter=5, target_match="positive"
         # display-side ranking (R's order(); stable, NaN last)
         key = np.where(np.isnan(cmi), np.inf, cmi if negative else -cmi)
         out["order"] = np.stack([np.argsort(key[:, it], kind="stable") for it in range(max_n_iter)])
-        out["top_markers"] = out["order"][:, :n_markers]
+        # the n.markers rows REVEALER.v1 displays (LIB:1858-1864): ranked on the device from the resident scores
+        out["top_markers"] = np.stack([ctx.topk(it, n_markers)[0] for it in range(max_n_iter)])
         if target_rand is not None:
             out["cmi_rand"] = np.transpose(res["cmi"][1:], (1, 2, 0)).copy()  # iters x F x n.perm
             # p-values on the scores still resident in HBM (LIB:1868-1869); NaN score -> NaN p-value (R: NA)
@@ -879,21 +888,22 @@ def prepare_inputs_device(ctx, ds1, target_name, target_match="positive", ds2=No
 
 def REVEALER_v1(ds1, target_name, target_match="positive", ds2=None, seed_names=None, exclude_features=None,
                 max_n_iter=5, pdf_output_file=None, count_thres_low=None, count_thres_high=None, n_markers=30,
-                locs_table_file=None, n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75, n_perm=0,
-                r_seed=34578, device=0, ingest=None, consolidate_identical_features=False):
+                locs_table_file=None, n_grid=25, bandwidth_mult=0.25, bandwidth_shrink=-0.75, n_perm=10,
+                r_seed=34578, device=0, ingest="host", consolidate_identical_features=False):
     """REVEALER.v1 with its 12 formals (LIB:1504-1516) plus the optional grid/bandwidth arguments.
     ds1 / ds2: GCT path or dict(ds, row_names, names) as MSIG.Gct2Frame returns.  Preprocessing
     mirrors LIB:1575-1707: drop NA-target samples, intersect samples, sort by target, drop the target
     row from the features, count filter (seeds always kept), build the seed as the column-wise max of
     the seed rows and remove those rows.  No plots/PDF (pdf_output_file and locs_table_file are accepted
-    and ignored).  ingest: "device" reads ds2 with the device GCT tokeniser (default when ds2 is a path),
-    "host" builds the F x n host matrix first (default for in-memory ds2).  consolidate_identical_features: the
+    and ignored).  ingest: "host" (default, the drop-in behaviour) reads ds2 like MSIG.Gct2Frame and builds the F x n
+    host matrix first; "device" opts into the device GCT tokeniser, which is faster but accepts only 0/1 spelled with
+    an optional ".000" (read.delim also takes NA, exponents, padded fields) -- a file it rejects raises an error.  consolidate_identical_features: the
     reference's internal switch (LIB:1532, default F); "identical" runs LIB:1727-1748 (on the device with
-    ingest="device").  n_perm > 0 adds the permutation null with numpy's PCG64(r_seed) (R's sample() stream is
-    not reproduced)."""
+    ingest="device").  n_perm (default 10, the reference's internal n.perm, LIB:1519) adds the permutation null with numpy's
+    PCG64(r_seed) -- R's sample() stream is not reproduced, so p-values match R's in distribution, not draw by draw."""
     ctx = None
-    if ingest is None:
-        ingest = "device" if isinstance(ds2, (str, GctFile)) else "host"
+    if ingest not in ("host", "device"):
+        raise RevealerError(_lib.RVL_ERR_ARG, 'ingest must be "host" or "device"')
     if ingest == "device":   # ds2: file -> text on the device -> bit matrix (no F x n host array)
         ctx = RevealerContext(device, n_grid=n_grid, bandwidth_mult=bandwidth_mult, bandwidth_shrink=bandwidth_shrink,
                               negative=(target_match == "negative"))

@@ -23,6 +23,7 @@
 #include <thrust/scan.h>
 #include <thrust/transform.h>
 #include <thrust/copy.h>
+#include <thrust/gather.h>
 #include <thrust/functional.h>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -1693,6 +1694,73 @@ extern "C" int rvl_pvalues_iter(rvl_ctx *ctx, int iter, double *out_pval)
     cudaFree(d_r); cudaFree(d_p);
     if (e != cudaSuccess || e2 != cudaSuccess)
         return fail(ctx, RVL_ERR_CUDA, "rvl_pvalues_iter: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return RVL_OK;
+}
+
+// R's order(cmi[, iter], decreasing = !negative) restricted to its first k entries (the n.markers rows REVEALER.v1
+// displays, LIB:1858-1864), on the scores resident in HBM: scores become sort keys that are ascending in R's order
+// (NaN last, -0 == +0), a stable radix sort keeps the lower row first among ties.
+struct rvl_order_key {
+    const double *v;
+    int negative;
+    __host__ __device__ unsigned long long operator()(int64_t i) const
+    {
+        double s = v[i];
+        if (s != s) return ~0ull;                      // NaN / NA: last
+        if (s == 0.0) s = 0.0;                         // -0 and +0 tie
+        unsigned long long u;
+        memcpy(&u, &s, sizeof u);
+        u = (u >> 63) ? ~u : (u | 0x8000000000000000ull); // ascending in s
+        return negative ? u : ~u - 1ull;               // decreasing unless target.match == "negative"; never the NaN key
+    }
+};
+
+extern "C" int rvl_topk(rvl_ctx *ctx, int iter, int64_t target_index, int64_t k, int64_t *out_rows, double *out_scores)
+{
+    GUARD();
+    if (ctx->iters < 1 || iter < 0 || iter >= ctx->iters) return fail(ctx, RVL_ERR_STATE, "no search result for iteration %d", iter);
+    if (target_index < 0 || target_index >= ctx->T || k < 0 || (k > 0 && !out_rows)) return fail(ctx, RVL_ERR_ARG, "bad rvl_topk arguments");
+    const int64_t F = ctx->F;
+    if (k > F) k = F;
+    if (k == 0) return RVL_OK;
+    int jrc = join_side(ctx);
+    if (jrc) return jrc;
+    if (ctx->fill_pending) {
+        rvl_launch_fill_duplicates(ctx->d_scores, F, (int64_t)ctx->iters * ctx->T, ctx->d_rep, ctx->stream);
+        ctx->launches++;
+        ctx->fill_pending = false;
+    }
+    const double *col = ctx->d_scores + ((size_t)iter * ctx->T + (size_t)target_index) * F;
+    unsigned long long *d_key = nullptr;
+    int64_t *d_idx = nullptr;
+    double *d_top = nullptr;
+    CK(dalloc(&d_key, (size_t)F));
+    CK(dalloc(&d_idx, (size_t)F));
+    CK(dalloc(&d_top, (size_t)k));
+    int rc = RVL_OK;
+    try {
+        rvl_pool_alloc alloc{ctx};
+        auto pol = thrust::cuda::par(alloc).on(ctx->stream);
+        thrust::device_ptr<unsigned long long> key(d_key);
+        thrust::device_ptr<int64_t> idx(d_idx);
+        thrust::copy(pol, thrust::counting_iterator<int64_t>(0), thrust::counting_iterator<int64_t>(F), idx);
+        thrust::transform(pol, idx, idx + F, key, rvl_order_key{col, ctx->opts.negative});
+        thrust::stable_sort_by_key(pol, key, key + F, idx);
+        thrust::gather(pol, idx, idx + k, thrust::device_ptr<const double>(col), thrust::device_ptr<double>(d_top));
+        ctx->launches += 4;
+    } catch (...) {
+        rc = fail(ctx, RVL_ERR_CUDA, "device sort failed");
+    }
+    cudaError_t e = cudaSuccess;
+    if (!rc) {
+        e = cudaMemcpyAsync(out_rows, d_idx, sizeof(int64_t) * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && out_scores) e = cudaMemcpyAsync(out_scores, d_top, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_key); cudaFree(d_idx); cudaFree(d_top);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, RVL_ERR_CUDA, "rvl_topk: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    for (int64_t i = 0; i < k; i++) out_rows[i] += ctx->row_offset; // global rows, like rvl_result.top
     return RVL_OK;
 }
 

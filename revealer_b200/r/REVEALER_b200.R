@@ -113,8 +113,10 @@ REVEALER.v1 <- function(
    res$feature.names <- rownames(m.2)
    res$seed.names.iter <- rownames(m.2)[res$top]           # seed.names.iter
    res$target <- target
-   res$cmi.names <- apply(res$cmi, 2, function(v)          # display ranking, as order() at LIB:1858-1864
-      rownames(m.2)[order(v, decreasing = !identical(target.match, "negative"))][1:min(n.markers, nrow(m.2))])
+   res$cmi.names <- sapply(1:max.n.iter, function(it) {    # display ranking, as order() at LIB:1858-1864
+      if (!is.null(res$ctx)) return(rownames(m.2)[.Call("rvlR_topk", res$ctx, as.integer(it), as.integer(n.markers))])
+      rownames(m.2)[order(res$cmi[, it], decreasing = !identical(target.match, "negative"))][1:min(n.markers, nrow(m.2))]
+   })
    if (n.perm > 0) res$p.val <- sapply(1:max.n.iter, function(it) revealer.b200.pvalues(res, it))
    res
 }

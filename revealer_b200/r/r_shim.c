@@ -335,6 +335,25 @@ SEXP rvlR_pvalues_iter(SEXP sctx, SEXP siter)
     return out;
 }
 
+/* .Call("rvlR_topk", ctx, iter, k) -> integer[k]: the first k rows (1-based) of order(cmi[, iter], decreasing = !negative)
+ * of the last rvlR_search on ctx, ranked on the device (the n.markers rows of LIB:1858-1864). */
+SEXP rvlR_topk(SEXP sctx, SEXP siter, SEXP sk)
+{
+    rvl_ctx *ctx = get_ctx(sctx);
+    int64_t rows = 0, samples = 0;
+    if (rvl_get_matrix_dims(ctx, &rows, &samples)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    int64_t k = Rf_asInteger(sk);
+    if (k < 0) k = 0;
+    if (k > rows) k = rows;
+    int64_t *idx = (int64_t *)R_alloc((size_t)(k ? k : 1), sizeof(int64_t));
+    int rc = rvl_topk(ctx, Rf_asInteger(siter) - 1, 0, k, idx, NULL);
+    if (rc) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)k));
+    for (int64_t i = 0; i < k; i++) INTEGER(out)[i] = (int)idx[i] + 1;
+    UNPROTECT(1);
+    return out;
+}
+
 /* ---- GCT ingest (replaces MSIG.Gct2Frame + data.matrix for ds2, LIB:2616-2626 / 1582) -------------------- */
 
 static void rvl_r_gct_finalizer(SEXP ptr)

@@ -128,6 +128,18 @@ def test_reference_formals_are_preserved():
     assert d["target_match"] == "positive" and d["max_n_iter"] == 5 and d["n_markers"] == 30
     assert d["seed_names"] is None and d["count_thres_low"] is None and d["n_grid"] == 25
     assert d["bandwidth_mult"] == 0.25 and d["bandwidth_shrink"] == -0.75
+    # the reference's internal constants (LIB:1519, 1531) and the drop-in reader: GCT files go through the host reader unless
+    # the caller opts into the device tokeniser (which accepts fewer spellings than read.delim)
+    assert d["n_perm"] == 10 and d["r_seed"] == 34578 and d["ingest"] == "host"
+    r = open(os.path.join(ROOT, "revealer_b200", "r", "REVEALER_b200.R")).read()
+    assert "REVEALER.v1 <- function(" in r and "gct.ingest = FALSE" in r and "n.gpus = 1" in r
+    assert 'identical(seed.names, "NULLSEED")' in r and "rvlR_search_multi" in r
+    head = r[r.index("REVEALER.v1 <- function("):]
+    formals = ["ds1", "target.name", "target.match", "ds2", "seed.names", "exclude.features", "max.n.iter", "pdf.output.file",
+               "count.thres.low", "count.thres.high", "n.markers", "locs.table.file", "n.grid", "bandwidth.mult",
+               "bandwidth.shrink", "n.gpus"]
+    pos = [head.index(f) for f in formals]
+    assert pos == sorted(pos)                    # the 12 reference formals first and in order, then the optional four
 
 
 def test_prepare_inputs_mirrors_reveler_v1_preprocessing(tmp_path):

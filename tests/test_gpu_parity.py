@@ -280,6 +280,26 @@ def test_r_golden_vectors_through_cuda_if_present():
         assert score_close([out["ic_seed0"]], [float(s["ic_seed0"])])[0]
 
 
+def test_device_topk_is_r_order(oracle):
+    """rvl_topk == the head of R's order(): stable among exact ties (duplicate rows), NaN last, -0 == +0, and the
+    increasing order for target.match = "negative"."""
+    import revealer_b200 as rb
+    w = _workload(120, 700)
+    for match in ("positive", "negative"):
+        out = rb.revealer_search(w["target"], w["m2"], w["seed"], max_n_iter=2, target_match=match, n_markers=40)
+        for it in range(2):
+            want = oracle.order(out["cmi"][:, it], negative=(match == "negative"))[:40]
+            assert np.array_equal(out["top_markers"][it], want), (match, it)
+            assert out["top_markers"][it][0] == out["top"][it]
+    with _ctx() as ctx:
+        ctx.load_matrix(w["m2"][:50])
+        ctx.set_targets(w["target"])
+        ctx.set_seed(w["seed"])
+        ctx.search(1)
+        rows, sc = ctx.topk(0, 1000)                                   # k clipped to the row count
+        assert len(rows) == 50 and sorted(rows.tolist()) == list(range(50)) and np.all(np.diff(sc[~np.isnan(sc)]) <= 0)
+
+
 def test_input_layouts_agree():
     import revealer_b200 as rb
     w = _workload(130, 200)
