@@ -180,6 +180,8 @@ def test_r_golden_vectors_if_present(oracle):
     if not os.path.exists(path):
         pytest.skip("no R-generated golden file (tests/golden/r_golden.json): parity with R stays unpinned")
     g = json.load(open(path))
+    if g.get("provenance", "").startswith("STAND-IN") and not os.environ.get("RVL_ALLOW_STANDIN"):
+        pytest.skip("r_golden.json is the oracle-made stand-in of tools/dryrun_r_golden.py, not R output: parity stays unpinned")
     for c in g["cases"]:
         x, y, z = (np.array(c[k], dtype=float) for k in ("x", "y", "z"))
         assert abs(oracle.bcv(x) - c["bcv_x"]) <= 1e-9 * c["bcv_x"]
