@@ -276,3 +276,34 @@ def test_bench_reference_arm_prints_the_contract_line():
     env["WORLD_SIZE"] = "2"
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_bench_score_checksum_is_independent_of_the_sharding():
+    """bench.py's `check.cmi_checksum` (position-weighted sum of the score bit patterns, mod 2^64) must be the same
+    number whether the rows, or the targets, are split over ranks: that is what lets the driver compare the lines of
+    N = 1, 2, 4, 8 -- and it must notice a single flipped bit or two swapped scores."""
+    sys.path.insert(0, ROOT)
+    import bench
+    rng = np.random.default_rng(4)
+    T, iters, F = 3, 4, 1000
+    cmi = rng.standard_normal((T, iters, F))
+    cmi[1, 2, 17] = np.nan
+    whole = bench.score_checksum(cmi, 0, F)
+    M = (1 << 64) - 1
+    for world in (2, 3, 8):
+        tot = 0
+        for r in range(world):
+            lo, hi = r * F // world, (r + 1) * F // world
+            tot = (tot + bench.score_checksum(cmi[:, :, lo:hi], lo, F)) & M
+        assert tot == whole
+        tot = 0
+        for r in range(min(world, T)):
+            lo, hi = r * T // min(world, T), (r + 1) * T // min(world, T)
+            tot = (tot + bench.score_checksum(cmi[lo:hi], 0, F, t_offset=lo)) & M
+        assert tot == whole
+    flipped = cmi.copy()
+    flipped.view(np.uint64)[0, 1, 5] ^= np.uint64(1)
+    assert bench.score_checksum(flipped, 0, F) != whole
+    swapped = cmi.copy()
+    swapped[0, 0, [3, 4]] = swapped[0, 0, [4, 3]]
+    assert bench.score_checksum(swapped, 0, F) != whole
