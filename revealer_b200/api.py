@@ -12,6 +12,7 @@ Everything numerical is done by librevealer_b200.so through its C ABI (include/r
 This module never computes a score itself and has no CPU fallback.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -622,6 +623,8 @@ def revealer_search_multi_gpu(target, m2, seed=None, max_n_iter=5, target_match=
                                 negative=negative)
             ctxs.append(c)
             c.set_shard(r, world, lo, F)
+            if np.asarray(m2).dtype == np.float64:     # shards are loaded one after the other: each load may use all the cores
+                c.set_host_threads(min(32, len(os.sched_getaffinity(0))))
             c.load_matrix(m2[lo:lo + cnt])
             c.set_targets(target)
             c.set_seed(np.zeros(n, dtype=np.uint8) if seed is None else seed)

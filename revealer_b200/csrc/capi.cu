@@ -607,10 +607,13 @@ extern "C" int rvl_load_matrix_f64_colmajor(rvl_ctx *ctx, const double *m2, int6
     const int64_t W = (n + 63) / 64;
     int nthreads = ctx->host_threads;
     if (nthreads < 0) {
-        int avail = (int)std::thread::hardware_concurrency();
+        const int total = (int)std::thread::hardware_concurrency();
+        int avail = total;
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof set, &set) == 0) avail = CPU_COUNT(&set);
-        nthreads = avail / (ctx->world > 0 ? ctx->world : 1);
+        // one process per GPU: a process already confined to its share of the cores (bench.py binds every rank to the
+        // cores local to its GPU) uses all of them; an unconfined one takes 1/world of the machine
+        nthreads = (total > 0 && avail < total) ? avail : avail / (ctx->world > 0 ? ctx->world : 1);
         if (nthreads > 32) nthreads = 32;
         if ((double)F * (double)n < 4e6 || W < 2) nthreads = 0; // small matrices: not worth starting threads
     }

@@ -20,6 +20,7 @@
 #include <Rinternals.h>
 #include <stdint.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "revealer_b200.h"
 
@@ -216,6 +217,10 @@ SEXP rvlR_search_multi(SEXP sdevices, SEXP starget, SEXP sm2, SEXP sseed, SEXP s
         int64_t lo = ((int64_t)r * F) / world, hi = ((int64_t)(r + 1) * F) / world;
         rc = rvl_set_options(ctxs[r], &o);
         if (!rc) rc = rvl_set_shard(ctxs[r], r, world, lo, F);
+        if (!rc) { /* the shards are loaded one after the other by this one process: every load may use all the cores */
+            long cores = sysconf(_SC_NPROCESSORS_ONLN);
+            rc = rvl_set_host_threads(ctxs[r], cores < 1 ? 1 : (cores > 32 ? 32 : (int)cores));
+        }
         if (!rc) rc = rvl_load_matrix_f64_colmajor(ctxs[r], REAL(sm2) + lo, hi - lo, n, F);
         if (!rc) rc = rvl_set_targets(ctxs[r], tg, n, T);
         if (!rc && nperm) rc = rvl_set_null_targets(ctxs[r], 1);
