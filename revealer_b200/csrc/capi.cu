@@ -142,7 +142,7 @@ struct rvl_ctx {
     int *d_bin = nullptr, *d_cnt = nullptr, *d_flag = nullptr;
     RvlTarget *d_tg = nullptr;
 
-    // per-iteration x-axis table [T][nodes][2][RVL_MAXG] (score.cu, k_ttable)
+    // per-iteration x-axis table [T][nodes][2][RVL_MAXG] (score.cu, k_advance)
     double *d_tt = nullptr;
     size_t tt_cap = 0;
     int dense_x = 0;
@@ -1208,7 +1208,7 @@ static int ensure_results(rvl_ctx *ctx, int iters)
 static int launch_score(rvl_ctx *ctx, double *base)
 {
     RvlParams P = make_params(ctx);
-    if (ctx->F == 0) return RVL_OK; // k_seed_prep already left every best slot at "none"
+    if (ctx->F == 0) return RVL_OK; // k_advance already left every best slot at "none"
     const bool prof = ctx->profiling != 0;
     if (prof && ctx->score_events_used == ctx->score_events.size()) {
         cudaEvent_t a, b;
@@ -1217,7 +1217,7 @@ static int launch_score(rvl_ctx *ctx, double *base)
         ctx->score_events.push_back({a, b});
     }
     if (ctx->work_dirty) CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned long long), ctx->stream));
-    ctx->work_dirty = true; // k_seed_prep re-arms the counter; a repeated launch without it must do so here
+    ctx->work_dirty = true; // k_advance re-arms the counter; a repeated launch without it must do so here
     if (prof) CK(cudaEventRecord(ctx->score_events[ctx->score_events_used].first, ctx->stream));
     rvl_launch_score(&P, ctx->score_grid_x, ctx->score_smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed,
                      ctx->d_bcvtab, ctx->d_tt, base, ctx->d_part, ctx->d_work, prof ? ctx->d_ctr : nullptr,

@@ -25,7 +25,7 @@ struct RvlTarget {
     // bandwidth shrink factor c, hence how many nodes of the x-axis table are ever read
     unsigned long long rho_pos_max_bits, rho_abs_max_bits;
     unsigned long long fingerprint; // order-independent hash of the multiset of target values
-    // --- per iteration (written by k_seed_prep)
+    // --- per iteration (written by k_advance / k_search's merge tasks)
     int32_t nz;       // popcount(seed)
     int32_t mode;     // RVL_MODE_*
     double bcv_z;     // bcv(seed) from the binary table

@@ -6,6 +6,8 @@
 //   k_advance    global winner from `world` candidate records, seed <- max(seed, m.2[top,])
 //                (LIB:2167-2168), seed state (dispatch of cond.assoc LIB:2507-2517), x-axis table
 //   k_assoc      cmi.seed[iter] <- assoc(target, seed)                 (LIB:2170), side stream
+//   k_search     all of the above for every iteration in ONE persistent cooperative launch, the candidate exchange
+//                between ranks done with peer-memory stores over NVLink inside the kernel (optional: rvl_set_fused)
 //
 // Algebra.  With y, z in {0,1}^n the 25^3 KDE cube of misc3d::kde3d is
 //   d[i,j,k] = kappa * sum_{a,b in {0,1}} A_ab[i] * gy_a[j] * gz_b[k],
@@ -698,9 +700,9 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
 // the per-z-class total over ALL samples, depends on the feature only through the scalar t.  As a
 // function of tau = ln t it is a sum of exp(-a_s e^tau): entire, and 8-point Lagrange interpolation
 // on nodes spaced 1/128 in tau reproduces it to ~1e-16 of the class size (checked in
-// tests/test_ttable_interp.py against direct summation).  The table is rebuilt once per
-// (target, iteration) by k_ttable -- M * n * G exps, the cost of ~M dense passes instead of one per
-// feature -- and k_score only visits the minority y-class of each row bit by bit.
+// tests/test_ttable_interp.py against direct summation).  The table is built once per (target, search) by
+// k_advance -- M * n * G exps, the cost of ~M dense passes instead of one per feature -- then updated in place
+// after every merge, and k_score only visits the minority y-class of each row bit by bit.
 // Node tt_pad is tau = 0 exactly (c = 1: every feature with rho <= 0), so those use it unweighted.
 // Layout: tt[target][node][b][RVL_MAXG].
 
