@@ -463,7 +463,11 @@ class Bench:
         # H2D + bit-packing + search + D2H of the score matrix and winners inside the timed region.
         tgt_h, seed_h = targets.copy(), w["seed"].copy()
         reps = max(1, min(steps, 3))
-        if not args.no_e2e:
+        if not args.no_e2e and cnt * n * 8 > (4 << 30):
+            out["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                          "skipped": "the R-layout copy of this rank's shard would take %.1f GB of host memory (twice: pageable and "
+                                     "pinned); run with fewer rows per rank" % (cnt * n * 8 / 1e9)}
+        elif not args.no_e2e:
             def e2e_leg(m2_r):
                 phases = {}
 
