@@ -1950,6 +1950,8 @@ extern "C" int rvl_p2p_import(rvl_ctx *ctx, const unsigned char *handles, int wo
     CK(dalloc(&ctx->d_peers, (size_t)world));
     CK(cudaMemcpy(ctx->d_peers, ptrs.data(), sizeof(unsigned char *) * world, cudaMemcpyHostToDevice));
     ctx->p2p = true;
+    ctx->epoch = 0; // every rank (re)connects at the same point of its history: stamps and slot parity start over together,
+    ctx->xseq = 0;  // whatever searches this context ran on its own before
     return RVL_OK;
 }
 
@@ -2009,6 +2011,7 @@ extern "C" int rvl_group_connect(rvl_ctx **ctxs, int n)
         CK(cudaMemcpy(ctx->d_peers, bufs.data(), sizeof(unsigned char *) * n, cudaMemcpyHostToDevice));
         ctx->p2p = true;
         ctx->epoch = 0;
+        ctx->xseq = 0;
     }
     return RVL_OK;
 }

@@ -174,6 +174,53 @@ def test_group_search_over_two_gpus_equals_one_gpu():
         assert np.array_equal(two["cmi_seed"], one["cmi_seed"])
 
 
+def test_connected_contexts_repeat_searches_with_odd_iteration_counts():
+    """The two exchange slots alternate on a running counter, not on the iteration's parity: back-to-back searches with
+    an odd iteration count on the SAME connected contexts must neither tear a record nor wait for a stamp that went to
+    the other slot -- also when one context ran searches of its own before the group was connected, and with the
+    one-launch k_search on both devices."""
+    import ctypes as C
+    import torch
+    import revealer_b200 as rb
+    from revealer_b200 import synth
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    w = synth.make_workload(n=200, F=3001)
+    iters = 3
+    one = rb.revealer_search(w["target"], w["m2"], w["seed"], max_n_iter=iters)
+    F, world = 3001, 2
+    ctxs = []
+    try:
+        for r in range(world):
+            lo, cnt = rb.shard_rows(F, world, r)
+            c = rb.RevealerContext(r)
+            ctxs.append(c)
+            c.load_matrix(w["m2"][lo:lo + cnt])
+            c.set_targets(w["target"])
+            c.set_seed(w["seed"])
+            if r == 0:
+                c.search(5)                       # a history of its own (world of one) before joining the group
+            c.set_shard(r, world, lo, F)
+        lib = ctxs[0]._lib
+        arr = (C.c_void_p * world)(*[c._h for c in ctxs])
+        assert lib.rvl_group_connect(arr, world) == 0
+        for fused in (False, True):
+            for c in ctxs:
+                c.set_fused(fused)
+            for rep in range(4):
+                rc = lib.rvl_group_search(arr, world, iters)
+                assert rc == 0, [lib.rvl_last_error(c._h) for c in ctxs]
+                parts = [c.search_fetch(iters) for c in ctxs]
+                cmi = np.concatenate([p["cmi"][0] for p in parts], axis=1).T
+                assert np.array_equal(cmi, one["cmi"], equal_nan=True), (fused, rep)
+                for p in parts:
+                    assert np.array_equal(p["top"][0], one["top"]) and np.array_equal(p["seed_iter"][0], one["seed_iter"])
+                    assert np.array_equal(p["cmi_seed"][0], one["cmi_seed"])
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_target_sharded_batch_equals_single_gpu_batch_and_individual_runs():
     """Config C5's multi-GPU form: targets sharded over the devices (whole matrix on each, no exchange).  The batch
     must equal the same batch on one GPU and the targets run one at a time, bit for bit."""
