@@ -49,6 +49,30 @@ revealer.b200.pvalues <- function(res, iter) {
    .Call("rvlR_pvalues", tmp, res$cmi[, iter], as.double(res$cmi.rand[, , iter]))
 }
 
+# The numerical core of REVEALER_assess_features.v1 (LIB:2870-2890) for a 0/1 feature matrix: IC of every row against
+# the target and its permutation p-value, n.perm shuffled targets scored in one device pass per 60000 permutations.
+# Same p-value rule as LIB:2886-2890 (">=" for IC >= 0, "<=" otherwise).  set.seed(5209761) is the reference's own
+# (LIB:2689), so sample() yields the stream the reference would draw for the FIRST feature; the reference redraws
+# for every feature, this draws once and shares the permutations across features (documented in DESIGN.md 8).
+# Plots, ROC and the squared error stay in the reference.
+REVEALER_assess_features.b200 <- function(target, feature.mat, n.perm = 10000, n.grid = 25, r.seed = 5209761,
+                                          device = 0, target.rand = NULL) {
+   ctx <- .Call("rvlR_create", as.integer(device))
+   if (is.null(target.rand) && n.perm > 0) {
+      set.seed(r.seed)
+      target.rand <- matrix(0, nrow = n.perm, ncol = length(target))
+      for (h in 1:n.perm) target.rand[h, ] <- sample(target)
+   }
+   storage.mode(feature.mat) <- "double"
+   res <- .Call("rvlR_assess", ctx, as.double(target), feature.mat, target.rand, as.integer(n.grid))
+   IC <- res$IC
+   if (is.null(res$null.IC)) return(list(IC = IC, p.val = rep(NA_real_, length(IC)), null.IC = NULL))
+   n.perm <- ncol(res$null.IC)
+   p.val <- ifelse(IC >= 0, rowSums(res$null.IC >= IC), rowSums(res$null.IC <= IC)) / n.perm
+   names(IC) <- names(p.val) <- row.names(feature.mat)
+   list(IC = IC, p.val = p.val, null.IC = res$null.IC)
+}
+
 # REVEALER.v1 with the reference's twelve formals (LIB:1504-1516: same names, order and defaults), followed by the
 # optional grid / bandwidth arguments and n.gpus.  Sourcing this file after REVEALER_library.v5C.R replaces the
 # reference's REVEALER.v1 by this one (R binds the last definition), exactly as the library's own second copy

@@ -359,6 +359,73 @@ SEXP rvlR_topk(SEXP sctx, SEXP siter, SEXP sk)
     return out;
 }
 
+/* .Call("rvlR_assess", ctx, target, m, target.rand, n.grid)
+ * The numerical core of REVEALER_assess_features.v1 (LIB:2870-2890): for every row of the 0/1 matrix m (F x n,
+ * column-major; or NULL: the matrix resident in ctx), IC = mutual.inf.v2(target, row)$IC (LIB:2875) and the same
+ * against every row of target.rand (n.perm x n, the sample(target) draws of LIB:2885; or NULL).
+ * Returns list(IC = double[F], null.IC = F x n.perm or NULL).  Counting the p-value (LIB:2886-2890) stays in R. */
+SEXP rvlR_assess(SEXP sctx, SEXP starget, SEXP sm, SEXP srand, SEXP sngrid)
+{
+    rvl_ctx *ctx = get_ctx(sctx);
+    const int resident = Rf_isNull(sm);
+    if (!Rf_isReal(starget) || (!resident && (!Rf_isReal(sm) || !Rf_isMatrix(sm))))
+        Rf_error("revealer_b200: target and m must be double (m a matrix or NULL)");
+    const R_xlen_t n = XLENGTH(starget);
+    int64_t F, samples = n;
+    if (resident) {
+        if (rvl_get_matrix_dims(ctx, &F, &samples)) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    } else {
+        F = Rf_nrows(sm);
+        samples = Rf_ncols(sm);
+    }
+    if (samples != n) Rf_error("revealer_b200: dimension mismatch (n = %ld)", (long)n);
+    int nperm = 0;
+    if (!Rf_isNull(srand)) {
+        if (!Rf_isReal(srand) || !Rf_isMatrix(srand) || Rf_ncols(srand) != n) Rf_error("revealer_b200: target.rand must be n.perm x n");
+        nperm = Rf_nrows(srand);
+    }
+    rvl_opts o;
+    rvl_default_options(&o);
+    o.n_grid = Rf_asInteger(sngrid);
+    int rc = rvl_set_options(ctx, &o);
+    if (!rc && !resident) rc = rvl_load_matrix_f64_colmajor(ctx, REAL(sm), F, n, F);
+    if (rc) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP names = PROTECT(Rf_allocVector(STRSXP, 2));
+    SET_STRING_ELT(names, 0, Rf_mkChar("IC"));
+    SET_STRING_ELT(names, 1, Rf_mkChar("null.IC"));
+    Rf_setAttrib(out, R_NamesSymbol, names);
+    SEXP ic = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)F));
+    SEXP null_ic = nperm ? PROTECT(Rf_allocMatrix(REALSXP, (int)F, nperm)) : PROTECT(R_NilValue);
+    SET_VECTOR_ELT(out, 0, ic);
+    SET_VECTOR_ELT(out, 1, null_ic);
+
+    /* the target and its permutations go up in chunks of <= 60000 rows (the ABI takes <= 65535 targets); row 0 of
+     * every chunk is the target itself, so that the chunk is "one vector and its permutations" (shared bandwidths) */
+    enum { CHUNK = 60000 };
+    const int first = nperm < CHUNK ? nperm : CHUNK;
+    double *tg = (double *)R_alloc((size_t)(1 + first) * n, sizeof(double));
+    double *sc = (double *)R_alloc((size_t)(1 + first) * (size_t)F, sizeof(double));
+    uint8_t *zero = (uint8_t *)R_alloc(n, 1);
+    memset(zero, 0, n);
+    memcpy(tg, REAL(starget), sizeof(double) * n);
+    for (int lo = 0; lo == 0 || lo < nperm; lo += CHUNK) {
+        const int cnt = nperm - lo < CHUNK ? nperm - lo : CHUNK;
+        for (int j = 0; j < cnt; j++)
+            for (R_xlen_t s = 0; s < n; s++) tg[(size_t)(1 + j) * n + s] = REAL(srand)[(lo + j) + (size_t)nperm * s];
+        rc = rvl_set_targets_permuted(ctx, tg, n, 1 + cnt);
+        if (!rc) rc = rvl_set_seed(ctx, zero, n, 0); /* constant z: cond.assoc reduces to mutual.inf.v2 (LIB:2509) */
+        if (!rc) rc = rvl_score_once(ctx, sc);
+        if (rc) break;
+        if (lo == 0) memcpy(REAL(ic), sc, sizeof(double) * (size_t)F);
+        if (cnt) memcpy(REAL(null_ic) + (size_t)lo * (size_t)F, sc + (size_t)F, sizeof(double) * (size_t)cnt * (size_t)F);
+    }
+    UNPROTECT(4);
+    if (rc) Rf_error("revealer_b200: %s", rvl_last_error(ctx));
+    return out;
+}
+
 /* ---- GCT ingest (replaces MSIG.Gct2Frame + data.matrix for ds2, LIB:2616-2626 / 1582) -------------------- */
 
 static void rvl_r_gct_finalizer(SEXP ptr)

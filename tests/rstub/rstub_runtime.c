@@ -191,6 +191,8 @@ SEXP rstub_call(void *fn, int nargs, SEXP *a)
         case 1: out = ((SEXP(*)(SEXP))fn)(a[0]); break;
         case 2: out = ((SEXP(*)(SEXP, SEXP))fn)(a[0], a[1]); break;
         case 3: out = ((SEXP(*)(SEXP, SEXP, SEXP))fn)(a[0], a[1], a[2]); break;
+        case 4: out = ((SEXP(*)(SEXP, SEXP, SEXP, SEXP))fn)(a[0], a[1], a[2], a[3]); break;
+        case 5: out = ((SEXP(*)(SEXP, SEXP, SEXP, SEXP, SEXP))fn)(a[0], a[1], a[2], a[3], a[4]); break;
         case 9: out = ((SEXP(*)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP))fn)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]); break;
         case 10: out = ((SEXP(*)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP))fn)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]); break;
         default: snprintf(err_msg, sizeof err_msg, "rstub_call: %d arguments not supported", nargs); break;

@@ -142,6 +142,30 @@ def test_reference_formals_are_preserved():
     assert pos == sorted(pos)                    # the 12 reference formals first and in order, then the optional four
 
 
+def test_every_dot_call_in_the_r_wrapper_matches_a_shim_entry_point():
+    """Each .Call("rvlR_x", a, b, ...) in REVEALER_b200.R names a function r_shim.c defines, with that many SEXP arguments
+    (R would only find a mismatch at run time, and there is no R here to run it)."""
+    import re
+    r = open(os.path.join(ROOT, "revealer_b200", "r", "REVEALER_b200.R")).read()
+    c = open(os.path.join(ROOT, "revealer_b200", "r", "r_shim.c")).read()
+    defs = {m.group(1): len([a for a in m.group(2).split(",") if a.strip()])
+            for m in re.finditer(r"^SEXP (rvlR_\w+)\(([^)]*)\)\s*\{", c, flags=re.M | re.S)}
+    assert "rvlR_search" in defs and "rvlR_assess" in defs
+    calls = 0
+    for m in re.finditer(r'\.Call\("(rvlR_\w+)"', r):
+        name, i, depth, nargs = m.group(1), m.end(), 1, 0
+        while depth:                                   # count the top-level commas up to the closing parenthesis
+            ch = r[i]
+            depth += ch in "([" 
+            depth -= ch in ")]"
+            nargs += ch == "," and depth == 1
+            i += 1
+        assert name in defs, name + " is not defined in r_shim.c"
+        assert nargs == defs[name], "%s: called with %d arguments, defined with %d" % (name, nargs, defs[name])
+        calls += 1
+    assert calls >= 10
+
+
 def test_prepare_inputs_mirrors_reveler_v1_preprocessing(tmp_path):
     """Host-side preprocessing of REVEALER.v1 (LIB:1575-1720): NA-target samples dropped, samples
     intersected, sorted by target, target row dropped from the features, count filter with seeds kept,

@@ -132,6 +132,28 @@ def test_rvlr_search_matches_the_python_host(shim):
     assert ic == rb.assoc(w["target"], w["m2"][7])
 
 
+def test_rvlr_assess_matches_the_python_host(shim):
+    """rvlR_assess (REVEALER_assess_features.v1's IC + permutation scores, LIB:2875 / 2885): F x n.perm layout, the target
+    in row 0 of every chunk, a NULL target.rand, and the resident-matrix form."""
+    import revealer_b200 as rb
+    w = _workload(80, 250)
+    rng = np.random.default_rng(5)
+    perm = np.stack([rng.permutation(w["target"]) for _ in range(7)])
+    ref = rb.assess_features(w["target"], w["m2"], target_rand=perm)
+    ctx = shim.call("rvlR_create", shim.integer(0))
+    res = shim.as_list(shim.call("rvlR_assess", ctx, shim.real(w["target"]), shim.matrix(w["m2"]), shim.matrix(perm),
+                                 shim.integer(25)))
+    assert list(res) == ["IC", "null.IC"]
+    ic, null = shim.as_real(res["IC"]), shim.as_real(res["null.IC"])
+    assert null.shape == (250, 7)
+    assert np.array_equal(ic, ref["IC"], equal_nan=True) and np.array_equal(null.T, ref["null_IC"], equal_nan=True)
+    res0 = shim.as_list(shim.call("rvlR_assess", ctx, shim.real(w["target"]), shim.L.rstub_nil(), shim.L.rstub_nil(),
+                                  shim.integer(25)))                  # resident matrix, no permutations
+    assert np.array_equal(shim.as_real(res0["IC"]), ic, equal_nan=True) and shim.L.rstub_type(res0["null.IC"]) == 0
+    with pytest.raises(RuntimeError, match="n.perm x n"):
+        shim.call("rvlR_assess", ctx, shim.real(w["target"]), shim.L.rstub_nil(), shim.matrix(perm[:, :-1]), shim.integer(25))
+
+
 def test_rvlr_errors_become_r_errors_not_crashes(shim):
     w = _workload(60, 50)
     ctx = shim.call("rvlR_create", shim.integer(0))
