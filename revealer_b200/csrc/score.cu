@@ -676,7 +676,7 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
     double epsq = RVL_DBL_EPS * (dn * RVL_TWO_PI * sqrt(RVL_TWO_PI) * hx * hy * hz);
     // every Q lies in [eps', 4 n G^3]: normal doubles unless eps' itself is tiny (degenerate bandwidths)
     double cmi;
-    if (epsq < 1e-290) {
+    if (epsq < 1e-140) { // also keeps 1/(6 E^2) of the small-regime closed forms finite
         int nl;
         cmi = rvl_cmi_epilogue<false>(S, G, epsq, P.prune_theta, lane, &nl);
         *nitems_out = nl * G;
