@@ -57,10 +57,9 @@ void rvl_launch_unpack_rows(const uint64_t *src, const int64_t *rows, int64_t k,
 void rvl_launch_bcv_binary_table(int n, double *table, cudaStream_t st);
 void rvl_launch_target_setup(const double *x_all, int n, int T, int G, RvlTarget *tg, double *u_all, double *xc_all,
                              int *bin_all, int *cnt_all, int *nonfinite, int permuted, cudaStream_t st);
-size_t rvl_score_smem_bytes(int n, int words);
-cudaError_t rvl_score_configure(size_t smem, int device, int *grid_out);
-int rvl_score_warps(void);
-void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits, const double *u_all,
+size_t rvl_score_plan(int words, int G, size_t budget, int *warps_out);
+cudaError_t rvl_score_configure(size_t smem, int warps, int device, int *grid_out);
+void rvl_launch_score(const RvlParams *P, int grid_x, int warps, size_t smem, const uint64_t *bits, const double *u_all,
                       const double *xc_all, const RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
                       const double *tt, double *scores, RvlCandHead *part, unsigned long long *work,
                       unsigned long long *ctr, const int64_t *uniq, int64_t U, cudaStream_t st);
@@ -73,8 +72,8 @@ void rvl_launch_fp64_peak(int blocks, int threads, int iters, double *out, cudaS
 void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget *tg, const int *target_of, const double *u_all,
                       const double *xc_all, const uint64_t *y_all, const double *bcvtab, double *out,
                       size_t y_stride, size_t out_stride, int t_div, cudaStream_t st);
-cudaError_t rvl_search_configure(size_t smem, int device, int *grid_out);
-cudaError_t rvl_launch_search(const RvlSearchArgs *a, int grid_x, size_t smem, cudaStream_t st);
+cudaError_t rvl_search_configure(size_t smem, int warps, int device, int *grid_out);
+cudaError_t rvl_launch_search(const RvlSearchArgs *a, int grid_x, int warps, size_t smem, cudaStream_t st);
 void rvl_launch_argmax(const RvlParams *P, const RvlCandHead *part, int nparts, const uint64_t *bits,
                        unsigned char *send, size_t rec_bytes, const RvlPeerXchg *X, cudaStream_t st);
 void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols, int words,
@@ -180,6 +179,7 @@ struct rvl_ctx {
     int fused = 0;                  // rvl_set_fused (default off: measured 2-3 % slower than the split-phase launches)
     int search_grid_x = -1;         // -1: not configured; 0: cooperative launch unavailable
     size_t search_smem = 0;
+    int search_warps = 0;
     unsigned long long *d_swork = nullptr; // [sctr_cap] per-iteration item counters
     unsigned int *d_sdone = nullptr;       // [sctr_cap] per-iteration block tickets, then the barrier counter
     int sctr_cap = 0;
@@ -197,6 +197,7 @@ struct rvl_ctx {
     RvlCandHead *d_part = nullptr;
     size_t part_cap = 0;
     int score_grid_x = 0; // persistent grid of k_score (SMs x resident CTAs)
+    int score_warps = 0;  // worker warps per block (rvl_score_plan)
     size_t score_smem = 0;
     unsigned long long *d_work = nullptr; // k_score's item counter
     bool work_dirty = true;
@@ -569,8 +570,11 @@ static int begin_matrix(rvl_ctx *ctx, int64_t F, int64_t n)
     quiesce_side(ctx);
     if (F < 0 || n < 2 || n > (1 << 24)) return fail(ctx, RVL_ERR_ARG, "need F >= 0 and 2 <= n <= 2^24 (F=%lld n=%lld)", (long long)F, (long long)n);
     if (ctx->T > 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "matrix has n=%lld but targets have n=%d", (long long)n, ctx->n);
-    if (rvl_score_smem_bytes((int)n, (int)(((n + 63) / 64 + 1) & ~1ll)) > RVL_SCORE_DYN_SMEM_MAX)
-        return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (8 bit rows of n/8 bytes per block; n <= ~150 000)", (long long)n);
+    {
+        int w = 0;
+        if (!rvl_score_plan((int)(((n + 63) / 64 + 1) & ~1ll), RVL_MAX_GRID, RVL_SCORE_DYN_SMEM_MAX, &w))
+            return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (one bit row of n/8 bytes per worker warp; n <= ~1 400 000)", (long long)n);
+    }
     free_matrix(ctx);
     ctx->n = (int)n;
     ctx->words = (int)(((n + 63) / 64 + 1) & ~1ll); // rows padded to 16 B
@@ -994,8 +998,11 @@ static int set_targets_impl(rvl_ctx *ctx, const double *targets, int64_t n, int6
     quiesce_side(ctx);
     if (!targets || n < 2 || n_targets < 1 || n_targets > 65535) return fail(ctx, RVL_ERR_ARG, "bad targets (n=%lld, n_targets=%lld; need n >= 2, 1 <= n_targets <= 65535)", (long long)n, (long long)n_targets);
     if (ctx->F >= 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "targets have n=%lld but matrix has n=%d", (long long)n, ctx->n);
-    if (rvl_score_smem_bytes((int)n, (int)(((n + 63) / 64 + 1) & ~1ll)) > RVL_SCORE_DYN_SMEM_MAX)
-        return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (8 bit rows of n/8 bytes per block; n <= ~150 000)", (long long)n);
+    {
+        int w = 0;
+        if (!rvl_score_plan((int)(((n + 63) / 64 + 1) & ~1ll), RVL_MAX_GRID, RVL_SCORE_DYN_SMEM_MAX, &w))
+            return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (one bit row of n/8 bytes per worker warp; n <= ~1 400 000)", (long long)n);
+    }
     free_targets(ctx);
     if (ctx->F < 0) { ctx->n = (int)n; ctx->words = (int)(((n + 63) / 64 + 1) & ~1ll); }
     int T = (int)n_targets;
@@ -1077,15 +1084,17 @@ extern "C" int rvl_set_seed(rvl_ctx *ctx, const uint8_t *seed, int64_t n, int pe
 // resident CTAs, the per-warp best slots and the work counter.
 static int configure_score(rvl_ctx *ctx)
 {
-    size_t smem = rvl_score_smem_bytes(ctx->n, ctx->words);
-    if (smem > RVL_SCORE_DYN_SMEM_MAX) return fail(ctx, RVL_ERR_ARG, "n=%d needs %zu B of dynamic shared memory per block (> 194 KB)", ctx->n, smem);
-    if (smem != ctx->score_smem || ctx->score_grid_x <= 0) {
+    int warps = 0;
+    size_t smem = rvl_score_plan(ctx->words, ctx->opts.n_grid, RVL_SCORE_DYN_SMEM_MAX, &warps);
+    if (!smem) return fail(ctx, RVL_ERR_ARG, "n=%d needs more than 194 KB of dynamic shared memory per worker warp", ctx->n);
+    if (smem != ctx->score_smem || warps != ctx->score_warps || ctx->score_grid_x <= 0) {
         int grid = 0;
-        CK(rvl_score_configure(smem, ctx->device, &grid));
+        CK(rvl_score_configure(smem, warps, ctx->device, &grid));
         ctx->score_smem = smem;
+        ctx->score_warps = warps;
         ctx->score_grid_x = grid;
     }
-    size_t pneed = (size_t)ctx->T * (size_t)ctx->score_grid_x * rvl_score_warps();
+    size_t pneed = (size_t)ctx->T * (size_t)ctx->score_grid_x * ctx->score_warps;
     if (pneed > ctx->part_cap) {
         dfree(ctx->d_part);
         CK(dalloc(&ctx->d_part, pneed));
@@ -1117,7 +1126,7 @@ static int prep_iteration(rvl_ctx *ctx)
         }
         ctx->rho_dirty = false;
     }
-    const int nslots = ctx->score_grid_x * rvl_score_warps();
+    const int nslots = ctx->score_grid_x * ctx->score_warps;
     // no merge here (recv = NULL): seed state + full table build for the seeds as they are
     RvlPeerXchg Xnone;
     memset(&Xnone, 0, sizeof Xnone);
@@ -1219,7 +1228,7 @@ static int launch_score(rvl_ctx *ctx, double *base)
     if (ctx->work_dirty) CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned long long), ctx->stream));
     ctx->work_dirty = true; // k_advance re-arms the counter; a repeated launch without it must do so here
     if (prof) CK(cudaEventRecord(ctx->score_events[ctx->score_events_used].first, ctx->stream));
-    rvl_launch_score(&P, ctx->score_grid_x, ctx->score_smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed,
+    rvl_launch_score(&P, ctx->score_grid_x, ctx->score_warps, ctx->score_smem, ctx->d_bits, ctx->d_u, ctx->d_xc, ctx->d_tg, ctx->d_seed,
                      ctx->d_bcvtab, ctx->d_tt, base, ctx->d_part, ctx->d_work, prof ? ctx->d_ctr : nullptr,
                      ctx->dedup ? ctx->d_uniq : nullptr, ctx->U, ctx->stream);
     ctx->fill_pending = ctx->dedup && ctx->U < ctx->F;
@@ -1321,7 +1330,7 @@ extern "C" int rvl_iter_score(rvl_ctx *ctx, int iter)
     // (fusing this reduction into k_advance -- its `fuse_rank` path -- was measured 9 us per iteration
     //  slower on one GPU: 363 blocks then spin on the stamp that one 256-thread block has yet to write)
     RvlPeerXchg X = make_xchg(ctx, iter);
-    rvl_launch_argmax(&P2, ctx->d_part, ctx->score_grid_x * rvl_score_warps(), ctx->d_bits, ctx->d_send,
+    rvl_launch_argmax(&P2, ctx->d_part, ctx->score_grid_x * ctx->score_warps, ctx->d_bits, ctx->d_send,
                       sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, &X, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1336,7 +1345,7 @@ extern "C" int rvl_iter_merge(rvl_ctx *ctx, int iter)
     // merge + seed state + x-axis table in one launch; seeds ping-pong between the two buffers
     RvlPeerXchg X = make_xchg(ctx, iter);
     rvl_launch_advance(&P, ctx->d_tg, ctx->d_u, ctx->d_seed, ctx->d_seed_alt, ctx->d_bcvtab, ctx->d_tt, ctx->d_part,
-                       ctx->score_grid_x * rvl_score_warps(), ctx->d_work, ctx->p2p ? ctx->d_xchg : ctx->d_recv,
+                       ctx->score_grid_x * ctx->score_warps, ctx->d_work, ctx->p2p ? ctx->d_xchg : ctx->d_recv,
                        sizeof(RvlCandHead) + sizeof(uint64_t) * (size_t)ctx->words, iter, ctx->iters, ctx->first_null,
                        ctx->d_top, ctx->d_top_score, ctx->d_seed_iter, 1, &X, ctx->stream);
     { uint64_t *tmp = ctx->d_seed; ctx->d_seed = ctx->d_seed_alt; ctx->d_seed_alt = tmp; }
@@ -1432,12 +1441,15 @@ static bool fused_possible(rvl_ctx *ctx)
 {
     if (!ctx->fused || ctx->F < 0 || ctx->T <= 0) return false;
     if (ctx->world > 1 && !ctx->p2p) return false;
-    size_t smem = rvl_score_smem_bytes(ctx->n, ctx->words);
-    if (ctx->search_grid_x < 0 || smem != ctx->search_smem) {
+    int warps = 0;
+    size_t smem = rvl_score_plan(ctx->words, ctx->opts.n_grid, RVL_SCORE_DYN_SMEM_MAX, &warps);
+    if (!smem) return false;
+    if (ctx->search_grid_x < 0 || smem != ctx->search_smem || warps != ctx->search_warps) {
         int grid = 0;
-        if (rvl_search_configure(smem, ctx->device, &grid) != cudaSuccess) { cudaGetLastError(); grid = 0; }
+        if (rvl_search_configure(smem, warps, ctx->device, &grid) != cudaSuccess) { cudaGetLastError(); grid = 0; }
         ctx->search_grid_x = grid;
         ctx->search_smem = smem;
+        ctx->search_warps = warps;
     }
     return ctx->search_grid_x > 0;
 }
@@ -1462,7 +1474,7 @@ static int search_enqueue_fused(rvl_ctx *ctx, int iters)
     CK(cudaMemsetAsync(ctx->d_swork, 0, sizeof(unsigned long long) * (size_t)iters, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_sdone, 0, sizeof(unsigned int) * (2 * (size_t)iters + 1), ctx->stream));
     // the k_search grid equals the k_score grid the best slots were sized for (same block shape and shared memory)
-    if ((size_t)ctx->T * (size_t)ctx->search_grid_x * rvl_score_warps() > ctx->part_cap)
+    if ((size_t)ctx->T * (size_t)ctx->search_grid_x * ctx->search_warps > ctx->part_cap)
         return fail(ctx, RVL_ERR_STATE, "internal: k_search grid exceeds the best-slot buffer");
     RvlSearchArgs a;
     memset(&a, 0, sizeof a);
@@ -1491,7 +1503,7 @@ static int search_enqueue_fused(rvl_ctx *ctx, int iters)
         ctx->search_events.push_back({e0, e1});
     }
     if (prof) CK(cudaEventRecord(ctx->search_events[ctx->search_events_used].first, ctx->stream));
-    if (ctx->F > 0 || ctx->world > 1) CK(rvl_launch_search(&a, ctx->search_grid_x, ctx->search_smem, ctx->stream));
+    if (ctx->F > 0 || ctx->world > 1) CK(rvl_launch_search(&a, ctx->search_grid_x, ctx->search_warps, ctx->search_smem, ctx->stream));
     if (prof) CK(cudaEventRecord(ctx->search_events[ctx->search_events_used++].second, ctx->stream));
     ctx->launches++;
     if (iters & 1) { uint64_t *tmp = ctx->d_seed; ctx->d_seed = ctx->d_seed_alt; ctx->d_seed_alt = tmp; }

@@ -31,7 +31,8 @@
 
 #define RVL_SCORE_WARPS 8 // warps per block of k_advance / k_assoc (fixes their summation order)
 #ifndef RVL_KSCORE_WARPS
-#define RVL_KSCORE_WARPS 8 // independent worker warps per block of k_score
+#define RVL_KSCORE_WARPS 16 // most independent worker warps per block of k_score (one block per SM; the host launches
+                            // fewer when the per-warp scratch of a long bit row would not fit, rvl_score_plan)
 #endif
 #define RVL_TWO_PI 6.283185307179586476925286766559
 
@@ -43,12 +44,12 @@ __device__ double2 rvl_logtab_g[RVL_LOGTAB_ENTRIES];
 #define RVL_ITEMS_CAP 1024  // direct (j,k) columns: four-term ones from the front, two-term ones from the back
 struct __align__(16) RvlWarpScratch {
     double A[RVL_MAXG][4];     // A[i][a*2+b]: x-axis kernel sums of the four (y,z) classes
-    double AT[4][RVL_MAXG];    // the same numbers class-major (pass C loads four consecutive grid points per class)
     double gy[2][RVL_MAXG];    // gy[a][j]
     double gz[2][RVL_MAXG];    // gz[b][k]
     // y-axis tables of the entropy epilogue, indexed by the distance d from a y-class's own end of the axis:
     // prefix sums PG = sum g, PGL = sum g log g, PL = sum log g (d' <= d); suffix sums SG1..3 = sum g^1..3 (d' >= d)
     double tab[6][RVL_MAXG + 1];
+    float lgf[RVL_MAXG];       // log2(g[d] / eps') as float: the column constant of the soft-floor cells (pass C)
     union {
         uint32_t list[RVL_LIST_MAX];   // minority-class samples of the row being scored (before the epilogue)
         uint16_t items[RVL_ITEMS_CAP]; // (j << 5 | k) codes of the density columns evaluated cell by cell (epilogue)
@@ -310,28 +311,58 @@ __device__ __forceinline__ unsigned rvl_bits(int lo, int hi)
     return (lo <= hi) ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
 }
 
+// ---- soft-floor cells: the part of pass C that needs no double-precision log ------------------------------------
+// A density column in which only ONE y-class is visible has Q_i = g X_i + E (X = V or W of pass A, E = eps') and
+//   sum_i Q_i log Q_i = g (log g SX + LX) + E (G log g + LLX)            closed form, pass A's per-k sums of X, X log X, log X
+//                     + E ln2 sum_i (1 + t_i) log2(1 + 1/t_i),           t_i = g X_i / E
+// exactly.  The second line is O(E) per cell whatever t is -- it IS the whole effect of the eps floor on the column --
+// so single precision carries it: a relative error of 1e-5 there moves CMI by < 1e-16 (tools/proto/epilogue_softfloor.py:
+// the column sums come out closer to a long-double evaluation than the cell-by-cell double-precision logs were).
+// With d = log2 t = lf[cls][k][i] + lgf[dist] (float copies of log2 X from pass A and of log2(g / E)), a = |d|, e = 2^-a
+// (one MUFU.EX2) and P(e) = log2(1 + e) / e (degree 5, relative error 8.4e-6):
+//   d > 0  (cell above the floor):   (1 + t) log2(1 + 1/t) = (1 + e) P(e)
+//   d <= 0 (cell at the floor):      (1 + t) log2(1 + 1/t) = (1 + e) (a + e P(e))
+// -- 13 FP32-pipe instructions and one MUFU per cell against 11 FP64 + table gather + I2F for Q = fma(..), log Q, Q log Q.
+// A clamped X (pass A takes the log of max(X, 1e-290)) stays consistent: closed form and correction use the same log X.
+__device__ __forceinline__ float rvl_soft_cell(float d)
+{
+    const float a = fabsf(d);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a));
+    float p = fmaf(e, -0.034435972571372986f, 0.14603309333324432f);
+    p = fmaf(p, e, -0.3030364513397217f);
+    p = fmaf(p, e, 0.46917417645454407f);
+    p = fmaf(p, e, -0.7204262018203735f);
+    p = fmaf(p, e, 1.4426828622817993f);
+    const bool up = d > 0.f;
+    const float r = fmaf(up ? 1.0f : e, p, up ? 0.0f : a);
+    return fmaf(e, r, r);
+}
+
+// stride (in floats) of one k row of the float table lf[class][k][i]: a multiple of 4 (16-byte rows, LDS.128) whose
+// quarter is odd, so that the rows of 8 consecutive k start in 8 distinct 16-byte bank groups
+__host__ __device__ __forceinline__ int rvl_lf_stride(int G) { return (((G + 3) >> 2) | 1) * 4; }
+
 // 3-D epilogue, production form.  Same quantity as rvl_cmi_epilogue, organised around the majority
 // y-class `am` (the class holding most samples; a = 0 for the usual sparse alteration row):
 //   Q_ijk = g_M[j] * V_k[i] + g_m[j] * W_k[i] + eps',   V_k[i] = A_{am,0}[i] gz_0[k] + A_{am,1}[i] gz_1[k]
-// (W likewise for the minority class).  Pass A (lanes = k) builds V, W once per (i,k) and takes the
-// x-z marginal log there.  Pass B (lanes = k) sorts the G density columns above every k into
-//   dead        largest possible density below the pruning threshold  -> constant G eps' log eps'
-//   factorised  minority term cannot change fl(Q) (g_m maxW < 2^-54 eps') and eps' <= g_M minV / 16: then
-//               sum_i Q log Q = g (log g * SV + LV) + eps' (G log g + LLV + G)
-//               with SV = sum V, LV = sum V log V, LLV = sum log V from pass A and log g known in closed
-//               form.  This is (a + e) log(a + e) expanded to first order in e = eps'; the neglected
-//               part is < eps'/32 per cell, i.e. < G^3 eps' / (32 S) ~ 1e-16 on CMI -- O(1) per column
-//   direct      everything else: G cells, one log each (pass C, lanes = columns, 4 logs in flight)
-// The y-axis kernel g[d] = exp(-kappa d^2) is monotone in the distance d from a class's end of the axis, so all
-// three sets are INTERVALS of j whose ends follow in closed form from log maxV, log minV, log maxW (five sqrt bounds
-// per lane) -- no loop over j: the factorised interval is summed with the prefix tables of the y-axis kernel, the
-// direct columns are written to the lists at offsets from a warp scan, and the y-z marginal comes from the cell
-// closed forms above (cells = k).  (Round 1 classified column by column in 25 serial trips of ballots: 23 % of the
-// kernel's time.)  For a sparse row every column on the majority side of the y axis is factorised, which removes
-// roughly half of the logs.
+// (W likewise for the minority class).  Pass A (lanes = k) builds V, W once per (i,k) with their logs, the per-k sums
+// of X, X log X, log X for both classes, a float copy of log2 X (lf), and takes the x-z marginal log.  Pass B (lanes = k)
+// sorts the G density columns above every k, in j' = distance from the majority class's end of the y axis, into
+//   dead        neither class term can reach the pruning threshold        -> constant G eps' log eps'
+//   majority    minority term cannot change fl(Q) (g_m maxW < 2^-54 eps'): the closed form above with X = V; where also
+//               eps' <= g_M minV / 16 ("factorised") the correction is G eps' to first order (neglected < eps'/32 per
+//               cell, ~1e-16 on CMI), elsewhere it is summed cell by cell in single precision (pass C, soft cells)
+//   minority    majority term cannot change fl(Q): the same with X = W, always with the cell-by-cell correction
+//   four-term   both classes visible: G cells, one double-precision log each (pass C)
+// The y-axis kernel g[d] = exp(-kappa d^2) is monotone in the distance d from a class's end of the axis, so all sets
+// are INTERVALS whose ends follow in closed form from log maxV, log minV, log maxW (five sqrt bounds per lane): the
+// closed forms are summed with prefix tables of the y-axis kernel, the columns of pass C are written to the lists at
+// offsets from a warp scan, and the y-z marginal comes from the cell closed forms above (cells = k).
+// lf: this warp's float table [2][G][rvl_lf_stride(G)].
 template <bool FAST>
-__device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, double theta, double hy, int am, int lane,
-                                     int *ndirect_out, int *nfact_out, int *ntwo_out, int *nyz_out)
+__device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, float *__restrict__ lf, int G, double epsq, double theta, double hy, int am,
+                                     int lane, int *nfour_out, int *nfact_out, int *nsoft_out, int *nyz_out)
 {
     const unsigned FULL = 0xffffffffu;
     const int M0 = am * 2, M1 = am * 2 + 1, m0 = (1 - am) * 2, m1 = (1 - am) * 2 + 1;
@@ -348,6 +379,8 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
     const double dead_thr = fmax(epsq * 0x1p-55, theta * Stot / ((double)GG * (double)G));
     const int kk = active ? lane : 0;
     const double gz0 = S.gz[0][kk], gz1 = S.gz[1][kk];
+    const double lEps = rvl_logq<FAST>(epsq);
+    const int stride = rvl_lf_stride(G);
 
     // ---- y-axis tables over d = lane (the argument of exp in rvl_fill_axis is log g)
     const double inv = 1.0 / ((double)G1 * hy);
@@ -365,14 +398,16 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
         S.tab[0][lane] = p0; S.tab[1][lane] = p1; S.tab[2][lane] = p2;
         S.tab[3][lane] = s1; S.tab[4][lane] = s2; S.tab[5][lane] = s3;
         if (lane == 0) { S.tab[3][32] = 0.0; S.tab[4][32] = 0.0; S.tab[5][32] = 0.0; }
+        S.lgf[lane] = (float)((lg - lEps) * 1.4426950408889634);
     }
 
     // ---- pass A: per-k tables over i, and the x-z marginal
     // min / max of V and max of W are only used in the (conservative) column tests of pass B, so they are
     // tracked on the high words (non-negative doubles order like their bit patterns: one integer min/max
     // instead of a NaN-aware FP64 compare-select) and widened outwards afterwards.
-    double SV = 0.0, LV = 0.0, LLV = 0.0, accxz = 0.0;
+    double SV = 0.0, LV = 0.0, LLV = 0.0, SW = 0.0, LW = 0.0, LLW = 0.0, accxz = 0.0;
     int minVh = 0x7ff00000, maxVh = 0, maxWh = 0;
+    float *lfV = lf + kk * stride, *lfW = lf + (G + kk) * stride;
 #pragma unroll 1
     for (int i = 0; i < G; i++) {
         const double V = fma(S.A[i][M0], gz0, S.A[i][M1] * gz1);
@@ -380,13 +415,20 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
         minVh = min(minVh, __double2hiint(V));
         maxVh = max(maxVh, __double2hiint(V));
         maxWh = max(maxWh, __double2hiint(W));
-        const double Vs = fmax(V, 1e-290); // keeps the fast log in range; such a column is never factorised
-        const double lv = rvl_logq<FAST>(Vs);
+        const double qxz = fma(Gy, V + W, gE);
+        const double Vs = fmax(V, 1e-290), Ws = fmax(W, 1e-290); // keeps the fast log in range (see rvl_soft_cell)
+        const double lv = rvl_logq<FAST>(Vs), lw = rvl_logq<FAST>(Ws), lq = rvl_logq<FAST>(qxz);
         SV += V;
         LV = fma(V, lv, LV);
         LLV += lv;
-        const double qxz = fma(Gy, V + W, gE);
-        accxz = fma(qxz, rvl_logq<FAST>(qxz), accxz);
+        SW += W;
+        LW = fma(W, lw, LW);
+        LLW += lw;
+        if (active) {
+            lfV[i] = (float)lv * 1.4426950408889634f;
+            lfW[i] = (float)lw * 1.4426950408889634f;
+        }
+        accxz = fma(qxz, lq, accxz);
     }
     const double minV = __hiloint2double(minVh, 0);                 // <= the true minimum
     const double maxV = __hiloint2double(maxVh, (int)0xffffffff);   // >= the true maxima
@@ -396,34 +438,37 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
     const double sm = am ? fma(sa[0], gz0, sa[1] * gz1) : fma(sa[2], gz0, sa[3] * gz1);
     __syncwarp();
 
-    // ---- pass B: the column intervals of this k, in d_M coordinates (j' = distance from the majority class's end)
+    // ---- pass B: the column intervals of this k
     const double inv_kappa = 2.0 * ((double)G1 * hy) * ((double)G1 * hy);
     const float ik = (float)inv_kappa;
-    const double lEps = rvl_logq<FAST>(epsq);
     const double lmaxV = rvl_logq<FAST>(fmax(maxV, 1e-290)), lminV = rvl_logq<FAST>(fmax(minV, 1e-290)),
                  lmaxW = rvl_logq<FAST>(fmax(maxW, 1e-290));
     const double Ld = rvl_logq<FAST>(fmax(0.5 * dead_thr, 1e-300)); // each class term below half the threshold
     const double L54 = lEps - 37.429947750237048;                  // log(2^-54 eps'): below it a term cannot change fl(Q)
-    const int vM = rvl_sqrt_bound((float)(lmaxV - Ld) * ik, G1);   // last j' where the majority term can reach the threshold
-    const int vm = rvl_sqrt_bound((float)(lmaxW - Ld) * ik, G1);   // last d_m where the minority term can
-    const int fM = rvl_sqrt_bound((float)(lminV - (lEps + 2.772588722239781)) * ik, G1); // last j' with g_M minV >= 16 eps'
     const int iM = rvl_sqrt_bound((float)(lmaxV - L54) * ik, G1);  // last j' where the majority term is visible at all
     const int im = rvl_sqrt_bound((float)(lmaxW - L54) * ik, G1);  // last d_m where the minority term is visible at all
-    const int bF = active ? min(fM, G - 2 - im) : -1;              // factorised: j' in [0, bF]
-    const unsigned mFact = rvl_bits(0, bF);
-    const unsigned mAlive = active ? (rvl_bits(0, vM) | rvl_bits(G1 - vm, G1) | mFact) : 0u;
-    const unsigned mDirect = mAlive & ~mFact;
-    const unsigned m4 = mDirect & rvl_bits(G1 - im, iM);            // both classes visible
-    const unsigned m2m = mDirect & ~rvl_bits(0, iM);                // majority invisible: the minority class's two terms
-    const unsigned m2M = mDirect & ~m4 & ~m2m;                      // minority invisible: the majority class's two terms
-    const int c4 = __popc(m4), c2M = __popc(m2M), c2m = __popc(m2m);
-    const int ndead = active ? G - __popc(mAlive) : 0;
+    // last j' / d_m where a class term can reach the threshold -- never beyond where it is visible: an invisible term
+    // leaves fl(Q) = eps' exactly, which is what a dead column contributes
+    const int vM = min(rvl_sqrt_bound((float)(lmaxV - Ld) * ik, G1), iM);
+    const int vm = min(rvl_sqrt_bound((float)(lmaxW - Ld) * ik, G1), im);
+    const int fM = rvl_sqrt_bound((float)(lminV - (lEps + 2.772588722239781)) * ik, G1); // last j' with g_M minV >= 16 eps'
+    const int jM = active ? min(vM, G - 2 - im) : -1;              // majority columns: j' in [0, jM] (minority invisible)
+    const int hm = active ? min(vm, G - 2 - iM) : -1;              // minority columns: d_m in [0, hm] (majority invisible)
+    const int bF = active ? min(fM, G - 2 - im) : -1;              // of the majority columns, factorised: j' in [0, bF]
+    const int bC = max(bF, jM);
+    const unsigned mSoftM = rvl_bits(bF + 1, jM);                   // majority columns with the cell-by-cell correction
+    const unsigned mMin = (hm >= 0) ? rvl_bits(G1 - hm, G1) : 0u;   // minority columns, in j' coordinates
+    const unsigned m4 = active ? (rvl_bits(G1 - im, iM) & (rvl_bits(0, vM) | rvl_bits(G1 - vm, G1))) : 0u; // both visible
+    const int c4 = __popc(m4), c2M = __popc(mSoftM), c2m = hm + 1;
+    const int ndead = active ? G - __popc(rvl_bits(0, bC) | mMin | m4) : 0;
     double accF = 0.0;
-    if (bF >= 0) // sum over the factorised interval: g (log g SV + LV) + eps' (G log g + LLV + G)
-        accF = fma(SV, S.tab[1][bF], LV * S.tab[0][bF]) + epsq * fma((double)G, S.tab[2][bF], (double)(bF + 1) * (LLV + (double)G));
-    // list offsets: four-term columns from the front of S.items, two-term columns from the back (bit 15: the
-    // surviving class is the minority one) -- the majority class's columns first, then the minority's, so that the
-    // lanes of a pass-C round read the same class rows (broadcast loads) except in the one round where the kinds meet
+    if (bC >= 0) // closed form over the majority columns: g (log g SV + LV) + eps' (G log g + LLV), + G eps' when factorised
+        accF = fma(SV, S.tab[1][bC], LV * S.tab[0][bC]) +
+               epsq * (fma((double)G, S.tab[2][bC], (double)(bC + 1) * LLV) + (double)((bF + 1) * G));
+    if (hm >= 0)
+        accF += fma(SW, S.tab[1][hm], LW * S.tab[0][hm]) + epsq * fma((double)G, S.tab[2][hm], (double)(hm + 1) * LLW);
+    // list offsets: four-term columns (j << 5 | k) from the front of S.items; soft columns (class << 15 | d << 5 | k, d the
+    // distance from the class's own end of the axis) from the back, the majority class's first
     int o4 = c4, oM = c2M, om = c2m;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -438,17 +483,11 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
         const int jp = __ffs((int)m) - 1, j = am ? G1 - jp : jp;
         S.items[o4++] = (uint16_t)((j << 5) | lane);
     }
-    for (unsigned m = m2M; m; m &= m - 1u) {
-        const int jp = __ffs((int)m) - 1, j = am ? G1 - jp : jp;
-        S.items[RVL_MAXG * RVL_MAXG - 1 - (oM++)] = (uint16_t)((j << 5) | lane);
-    }
-    for (unsigned m = m2m; m; m &= m - 1u) {
-        const int jp = __ffs((int)m) - 1, j = am ? G1 - jp : jp;
-        S.items[RVL_MAXG * RVL_MAXG - 1 - (om++)] = (uint16_t)((j << 5) | lane | 0x8000);
-    }
-    *ndirect_out = n4 + n2;
-    *nfact_out = rvl_warp_sum_i(bF + 1);
-    *ntwo_out = n2;
+    for (int d = bF + 1; d <= jM; d++) S.items[RVL_ITEMS_CAP - 1 - (oM++)] = (uint16_t)((d << 5) | lane);
+    for (int d = 0; d <= hm; d++) S.items[RVL_ITEMS_CAP - 1 - (om++)] = (uint16_t)((d << 5) | lane | 0x8000);
+    *nfour_out = n4;
+    *nfact_out = rvl_warp_sum_i(max(bF + 1, 0));
+    *nsoft_out = n2;
 
     // ---- y-z marginal: Q_jk = g[d_M] sM_k + g[d_m] sm_k + G eps', cells = k
     double accyz = 0.0;
@@ -472,9 +511,8 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
     *nyz_out = rvl_warp_sum_i(nyz);
     __syncwarp();
 
-    // ---- pass C: direct columns, lanes = columns; four grid points per trip, level by level: the four cells'
-    // FMA chains and the four logs advance side by side (class-major AT: two 16-byte loads fetch one class
-    // for all four points)
+    // ---- pass C, four-term columns: lanes = columns; four grid points per trip, level by level: the four cells'
+    // FMA chains and the four logs advance side by side
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     for (int idx = lane; idx < n4; idx += 32) {
         const int p = S.items[idx];
@@ -484,14 +522,14 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
         int i = 0;
 #pragma unroll 1
         for (; i + 3 < G; i += 4) {
-            double2 lo = *reinterpret_cast<const double2 *>(&S.AT[3][i]), hi = *reinterpret_cast<const double2 *>(&S.AT[3][i + 2]);
-            double q0 = fma(lo.x, w11, epsq), q1 = fma(lo.y, w11, epsq), q2 = fma(hi.x, w11, epsq), q3 = fma(hi.y, w11, epsq);
-            lo = *reinterpret_cast<const double2 *>(&S.AT[2][i]); hi = *reinterpret_cast<const double2 *>(&S.AT[2][i + 2]);
-            q0 = fma(lo.x, w10, q0); q1 = fma(lo.y, w10, q1); q2 = fma(hi.x, w10, q2); q3 = fma(hi.y, w10, q3);
-            lo = *reinterpret_cast<const double2 *>(&S.AT[1][i]); hi = *reinterpret_cast<const double2 *>(&S.AT[1][i + 2]);
-            q0 = fma(lo.x, w01, q0); q1 = fma(lo.y, w01, q1); q2 = fma(hi.x, w01, q2); q3 = fma(hi.y, w01, q3);
-            lo = *reinterpret_cast<const double2 *>(&S.AT[0][i]); hi = *reinterpret_cast<const double2 *>(&S.AT[0][i + 2]);
-            q0 = fma(lo.x, w00, q0); q1 = fma(lo.y, w00, q1); q2 = fma(hi.x, w00, q2); q3 = fma(hi.y, w00, q3);
+            double2 lo = *reinterpret_cast<const double2 *>(&S.A[i][0]), hi = *reinterpret_cast<const double2 *>(&S.A[i][2]);
+            const double q0 = fma(lo.x, w00, fma(lo.y, w01, fma(hi.x, w10, fma(hi.y, w11, epsq))));
+            lo = *reinterpret_cast<const double2 *>(&S.A[i + 1][0]); hi = *reinterpret_cast<const double2 *>(&S.A[i + 1][2]);
+            const double q1 = fma(lo.x, w00, fma(lo.y, w01, fma(hi.x, w10, fma(hi.y, w11, epsq))));
+            lo = *reinterpret_cast<const double2 *>(&S.A[i + 2][0]); hi = *reinterpret_cast<const double2 *>(&S.A[i + 2][2]);
+            const double q2 = fma(lo.x, w00, fma(lo.y, w01, fma(hi.x, w10, fma(hi.y, w11, epsq))));
+            lo = *reinterpret_cast<const double2 *>(&S.A[i + 3][0]); hi = *reinterpret_cast<const double2 *>(&S.A[i + 3][2]);
+            const double q3 = fma(lo.x, w00, fma(lo.y, w01, fma(hi.x, w10, fma(hi.y, w11, epsq))));
             double l0, l1, l2, l3;
             if (FAST) rvl_log_pos4(q0, q1, q2, q3, l0, l1, l2, l3);
             else { l0 = log(q0); l1 = log(q1); l2 = log(q2); l3 = log(q3); }
@@ -502,39 +540,32 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, int G, double epsq, doub
         }
 #pragma unroll 1
         for (; i < G; i++) {
-            const double q0 = fma(S.AT[0][i], w00, fma(S.AT[1][i], w01, fma(S.AT[2][i], w10, fma(S.AT[3][i], w11, epsq))));
+            const double q0 = fma(S.A[i][0], w00, fma(S.A[i][1], w01, fma(S.A[i][2], w10, fma(S.A[i][3], w11, epsq))));
             acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
         }
     }
-    for (int idx = lane; idx < n2; idx += 32) { // two-term columns: classes (ra, ra + 1) of one y value
-        const int e = S.items[RVL_MAXG * RVL_MAXG - 1 - idx];
-        const int ra = (e >> 15) ? m0 : M0;
-        const int j = (e >> 5) & 31, k = e & 31;
-        const double gg = S.gy[ra >> 1][j];
-        const double wa = gg * S.gz[0][k], wb = gg * S.gz[1][k];
-        const double *Aa = S.AT[ra], *Ab = S.AT[ra + 1];
+    // ---- pass C, soft cells: the single-precision correction of the one-class columns (see rvl_soft_cell); four grid
+    // points per 16-byte load, one float sum per column widened to double
+    double accS = 0.0;
+    for (int idx = lane; idx < n2; idx += 32) {
+        const int e = S.items[RVL_ITEMS_CAP - 1 - idx];
+        const int k = e & 31;
+        const float lg = S.lgf[(e >> 5) & 31];
+        const float *row = lf + (((e >> 15) ? G : 0) + k) * stride;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int i = 0;
 #pragma unroll 1
         for (; i + 3 < G; i += 4) {
-            double2 lo = *reinterpret_cast<const double2 *>(Ab + i), hi = *reinterpret_cast<const double2 *>(Ab + i + 2);
-            double q0 = fma(lo.x, wb, epsq), q1 = fma(lo.y, wb, epsq), q2 = fma(hi.x, wb, epsq), q3 = fma(hi.y, wb, epsq);
-            lo = *reinterpret_cast<const double2 *>(Aa + i); hi = *reinterpret_cast<const double2 *>(Aa + i + 2);
-            q0 = fma(lo.x, wa, q0); q1 = fma(lo.y, wa, q1); q2 = fma(hi.x, wa, q2); q3 = fma(hi.y, wa, q3);
-            double l0, l1, l2, l3;
-            if (FAST) rvl_log_pos4(q0, q1, q2, q3, l0, l1, l2, l3);
-            else { l0 = log(q0); l1 = log(q1); l2 = log(q2); l3 = log(q3); }
-            acc0 = fma(q0, l0, acc0);
-            acc1 = fma(q1, l1, acc1);
-            acc2 = fma(q2, l2, acc2);
-            acc3 = fma(q3, l3, acc3);
+            const float4 v = *reinterpret_cast<const float4 *>(row + i);
+            a0 += rvl_soft_cell(v.x + lg);
+            a1 += rvl_soft_cell(v.y + lg);
+            a2 += rvl_soft_cell(v.z + lg);
+            a3 += rvl_soft_cell(v.w + lg);
         }
-#pragma unroll 1
-        for (; i < G; i++) {
-            const double q0 = fma(Aa[i], wa, fma(Ab[i], wb, epsq));
-            acc0 = fma(q0, rvl_logq<FAST>(q0), acc0);
-        }
+        for (; i < G; i++) a0 += rvl_soft_cell(row[i] + lg);
+        accS += (double)((a0 + a1) + (a2 + a3));
     }
-    const double L3 = rvl_warp_sum((acc0 + acc1) + (acc2 + acc3) + accF) +
+    const double L3 = rvl_warp_sum((acc0 + acc1) + (acc2 + acc3) + fma(epsq * 0.6931471805599453094, accS, accF)) +
                       (double)rvl_warp_sum_i(ndead) * ((double)G * (epsq * lEps));
     const double Lyz = rvl_warp_sum(accyz);
     const double Lxz = rvl_warp_sum(accxz);
@@ -649,9 +680,9 @@ __global__ void k_rho_max(RvlParams P, const uint64_t *__restrict__ bits, const 
 // mode: RVL_MODE_IC (2-D) or RVL_MODE_CIC (3-D).  c is the bandwidth shrink factor already applied
 // to hx (beta); here it is applied to hy / hz.
 // am: majority y-class (0 unless the row has more ones than zeros).  nitems_out: cube cells evaluated with a log of
-// their own; nyz_out: the same for the y-z marginal; nfact_out: columns in factorised form; ntwo_out: direct columns
-// evaluated with two of the four class terms.
-__device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, double rho, double c, double hx,
+// their own; nyz_out: the same for the y-z marginal; nfact_out: columns in factorised form; ntwo_out: one-class columns
+// whose eps-floor correction is summed cell by cell in single precision (soft cells).  lf: the warp's float table.
+__device__ double rvl_finish(RvlWarpScratch &S, float *lf, const RvlParams &P, int mode, double rho, double c, double hx,
                              double bcv_y, double bcv_z, int am, int lane, int *nitems_out, int *nyz_out, int *nfact_out,
                              int *ntwo_out)
 {
@@ -686,7 +717,7 @@ __device__ double rvl_finish(RvlWarpScratch &S, const RvlParams &P, int mode, do
         *nitems_out = nl * G;
     } else {
         int nd, nf, n2;
-        cmi = rvl_cmi_epilogue_f<true>(S, G, epsq, P.prune_theta, hy, am, lane, &nd, &nf, &n2, nyz_out);
+        cmi = rvl_cmi_epilogue_f<true>(S, lf, G, epsq, P.prune_theta, hy, am, lane, &nd, &nf, &n2, nyz_out);
         *nitems_out = nd * G;
         *nfact_out = nf;
         *ntwo_out = n2;
@@ -1215,8 +1246,8 @@ __device__ __forceinline__ void rvl_score_phase(const RvlParams &P, const uint64
                                                 const double *__restrict__ xc_all, const RvlTarget *tg_all, const uint64_t *seeds,
                                                 const double *__restrict__ bcvtab, const double *tt, double *__restrict__ scores,
                                                 RvlCandHead *part, unsigned long long *work, unsigned long long *ctr,
-                                                const int64_t *__restrict__ uniq, int64_t U, RvlWarpScratch &S, uint64_t *yrow, int slot,
-                                                int nslots, int lane)
+                                                const int64_t *__restrict__ uniq, int64_t U, RvlWarpScratch &S, uint64_t *yrow, float *lf,
+                                                int slot, int nslots, int lane)
 {
     const int n = P.n, words = P.words, G = P.G;
     const unsigned long long nrows = (unsigned long long)(uniq ? U : P.F);
@@ -1356,30 +1387,30 @@ __device__ __forceinline__ void rvl_score_phase(const RvlParams &P, const uint64
         }
         if (lane < G) {
             S.A[lane][0] = acc[0]; S.A[lane][1] = acc[1]; S.A[lane][2] = acc[2]; S.A[lane][3] = acc[3];
-            S.AT[0][lane] = acc[0]; S.AT[1][lane] = acc[1]; S.AT[2][lane] = acc[2]; S.AT[3][lane] = acc[3];
         }
         __syncwarp();
         int nitems, nyz, nfact, ntwo;
-        double score = rvl_finish(S, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, n1 > n - n1 ? 1 : 0, lane, &nitems, &nyz, &nfact,
+        double score = rvl_finish(S, lf, P, mode, rho, c, hx, bcvtab[n1], tg.bcv_z, n1 > n - n1 ? 1 : 0, lane, &nitems, &nyz, &nfact,
                                   &ntwo);
         if (lane == 0) {
             out[f] = score;
             if (ctr) { // instrumentation (rvl_set_profiling): work actually executed, bench.py's roofline numerator
                 atomicAdd(&ctr[0], 1ull);                          // evaluations that ran the KDE path
-                atomicAdd(&ctr[1], (unsigned long long)(nitems / G)); // (j,k) density columns evaluated cell by cell
+                atomicAdd(&ctr[1], (unsigned long long)(nitems / G)); // (j,k) density columns evaluated cell by cell with a double-precision log
                 atomicAdd(&ctr[2], (unsigned long long)nexp * G);  // x-axis exp() evaluations
                 atomicAdd(&ctr[3], (unsigned long long)nfact);     // (j,k) columns in factorised form
-                atomicAdd(&ctr[4], (unsigned long long)ntwo);      // direct columns evaluated with two of the four terms
-                // log() calls and plain FP64 flops (outside exp / log) of this evaluation.  CIC: pass A 2 logs per (i,k),
-                // one per cell of a direct column, 7 per lane in pass B and the y-z marginal + its direct entries, G for
-                // the z marginal, 1 in the table lookup; FMAs of pass A (~26 flop per cell), 10 flop per direct cell (6 when
-                // two-term).  IC / literal: one log per cell.
+                atomicAdd(&ctr[4], (unsigned long long)ntwo);      // one-class columns corrected cell by cell in single precision
+                // log() calls and plain FP64 flops (outside exp / log) of this evaluation.  CIC: pass A 3 logs per (i,k),
+                // one per cell of a four-term column, 8 per lane in pass B and the y-z marginal + its direct entries, G for
+                // the z marginal, 1 in the table lookup; FMAs of pass A (~34 flop per cell), 10 flop per four-term cell.
+                // The soft cells (ntwo * G) run on the FP32 pipe: ctr[7].  IC / literal: one log per cell.
                 const unsigned long long GG = (unsigned long long)G * G;
                 const bool cols = (mode == RVL_MODE_CIC) && !P.literal;
-                atomicAdd(&ctr[5], cols ? 2ull * GG + nitems + 8ull * G + nyz + 1ull
+                atomicAdd(&ctr[5], cols ? 3ull * GG + nitems + 9ull * G + nyz + 1ull
                                         : (mode == RVL_MODE_CIC ? (unsigned long long)nitems + 2ull * GG + G : GG + 2ull * G) + 1ull);
-                atomicAdd(&ctr[6], (cols ? 26ull * GG + 10ull * nitems - 4ull * (unsigned long long)ntwo * G + 60ull * G
+                atomicAdd(&ctr[6], (cols ? 34ull * GG + 10ull * nitems + 2ull * (unsigned long long)ntwo + 70ull * G
                                          : 10ull * (unsigned long long)nitems + 6ull * GG) + (unsigned long long)nexp * G * 6ull);
+                atomicAdd(&ctr[7], (unsigned long long)ntwo * G);  // soft cells (13 FP32 instructions + 1 MUFU each)
             }
         }
         if (rvl_ahead(score, f, best_v, best_i, P.negative)) { best_v = score; best_i = f; }
@@ -1390,7 +1421,7 @@ __device__ __forceinline__ void rvl_score_phase(const RvlParams &P, const uint64
 }
 
 #ifndef RVL_SCORE_MIN_CTAS
-#define RVL_SCORE_MIN_CTAS 2
+#define RVL_SCORE_MIN_CTAS 1
 #endif
 __global__ void __launch_bounds__(RVL_KSCORE_WARPS * 32, RVL_SCORE_MIN_CTAS)
 k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict__ u_all,
@@ -1401,15 +1432,17 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
 {
     // uniq[0..U): the rows to score (first row of every group of identical rows); NULL = all F rows
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * RVL_KSCORE_WARPS + warp, nslots = gridDim.x * RVL_KSCORE_WARPS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int slot = blockIdx.x * nwarps + warp, nslots = gridDim.x * nwarps;
 
     rvl_logtab_fill(rvl_logtab_g); // the only block barrier of the kernel
 
+    // dynamic shared memory: [nwarps] scratch | [nwarps][words] bit rows | [nwarps][2 G stride] float tables (rvl_score_plan)
     RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
-    uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_KSCORE_WARPS);
+    uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + nwarps);
+    float *lfs = reinterpret_cast<float *>(yrows + (size_t)nwarps * P.words);
     rvl_score_phase<false>(P, bits, u_all, xc_all, tg_all, seeds, bcvtab, tt, scores, part, work, ctr, uniq, U, scr[warp],
-                           yrows + (size_t)warp * P.words, slot, nslots, lane);
+                           yrows + (size_t)warp * P.words, lfs + (size_t)warp * 2 * P.G * rvl_lf_stride(P.G), slot, nslots, lane);
 }
 
 // ---- k_search: the whole search in ONE persistent cooperative launch ---------------------------------------
@@ -1456,8 +1489,8 @@ k_search(const RvlSearchArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_last;
     const RvlParams &P = a.P;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * RVL_KSCORE_WARPS + warp, nslots = gridDim.x * RVL_KSCORE_WARPS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int slot = blockIdx.x * nwarps + warp, nslots = gridDim.x * nwarps;
     if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[6] = rvl_globaltimer(); // kernel entry (block 0)
     rvl_logtab_fill(rvl_logtab_g);
     const int nodes = P.dense_x ? 1 : P.tt_nodes;
@@ -1477,10 +1510,12 @@ k_search(const RvlSearchArgs a)
         __syncwarp();
         {
             RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
-            uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + RVL_KSCORE_WARPS);
+            uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + nwarps);
+            float *lfs = reinterpret_cast<float *>(yrows + (size_t)nwarps * P.words);
             rvl_score_phase<RVL_KSEARCH_COH>(P, a.bits, a.u_all, a.xc_all, a.tg_all, seeds_cur, a.bcvtab, a.tt,
                                              a.scores + (size_t)it * P.T * P.F, a.part, a.work + it, a.ctr, a.uniq, a.U, scr[warp],
-                                             yrows + (size_t)warp * P.words, slot, nslots, lane);
+                                             yrows + (size_t)warp * P.words, lfs + (size_t)warp * 2 * P.G * rvl_lf_stride(P.G), slot,
+                                             nslots, lane);
         }
         __threadfence(); // this warp's part[] entries before the block's ticket
         __syncthreads();
@@ -1588,7 +1623,7 @@ __device__ double rvl_assoc_block(const RvlParams &P, const RvlTarget &tg, const
         }
         __syncwarp();
         int nitems, nyz, nfact, ntwo;
-        score = rvl_finish(sh.S, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, 0, lane, &nitems, &nyz, &nfact, &ntwo);
+        score = rvl_finish(sh.S, nullptr, P, RVL_MODE_IC, rho, c, hx, bcvtab[n1], 0.0, 0, lane, &nitems, &nyz, &nfact, &ntwo);
     }
     return score; // valid in warp 0
 }
@@ -1806,20 +1841,28 @@ extern "C" cudaError_t rvl_upload_log_table(void)
     return cudaMemcpyToSymbol(rvl_logtab_g, h, sizeof h);
 }
 
-extern "C" size_t rvl_score_smem_bytes(int n, int words)
+// Block shape of k_score / k_search for bit rows of `words` words and an n_grid of G: the most worker warps (<= 16, one
+// block per SM) whose scratch -- RvlWarpScratch + the bit row + the float table of the soft cells, per warp -- fits in
+// `budget` bytes of dynamic shared memory.  Returns the bytes to request and sets *warps_out; 0 when not even one warp fits.
+extern "C" size_t rvl_score_plan(int words, int G, size_t budget, int *warps_out)
 {
-    (void)n;
-    static_assert(sizeof(RvlAdvanceShared) <= sizeof(RvlWarpScratch) * RVL_KSCORE_WARPS, "k_search overlays the merge workspace on the scratch");
-    return sizeof(RvlWarpScratch) * RVL_KSCORE_WARPS + sizeof(uint64_t) * (size_t)words * RVL_KSCORE_WARPS;
+    const size_t per_warp = sizeof(RvlWarpScratch) + sizeof(uint64_t) * (size_t)words + sizeof(float) * 2 * (size_t)G * rvl_lf_stride(G);
+    int w = (int)(budget / per_warp);
+    if (w > RVL_KSCORE_WARPS) w = RVL_KSCORE_WARPS;
+    *warps_out = w;
+    if (w < 1) return 0;
+    size_t smem = per_warp * (size_t)w;
+    if (smem < sizeof(RvlAdvanceShared)) smem = sizeof(RvlAdvanceShared); // k_search overlays the merge workspace on the scratch
+    return smem;
 }
 
 // Sets the dynamic shared memory limit and returns the persistent grid: SMs x resident CTAs per SM.
-extern "C" cudaError_t rvl_score_configure(size_t smem, int device, int *grid_out)
+extern "C" cudaError_t rvl_score_configure(size_t smem, int warps, int device, int *grid_out)
 {
     cudaError_t e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score, RVL_KSCORE_WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score, warps * 32, smem);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -1828,11 +1871,9 @@ extern "C" cudaError_t rvl_score_configure(size_t smem, int device, int *grid_ou
     return cudaSuccess;
 }
 
-extern "C" int rvl_score_warps(void) { return RVL_KSCORE_WARPS; }
-
 // Persistent grid of k_search for `smem` bytes of dynamic shared memory: SMs x resident blocks (every block must be
 // resident: the launch is cooperative); 0 when the device cannot launch cooperatively.
-extern "C" cudaError_t rvl_search_configure(size_t smem, int device, int *grid_out)
+extern "C" cudaError_t rvl_search_configure(size_t smem, int warps, int device, int *grid_out)
 {
     *grid_out = 0;
     int coop = 0;
@@ -1842,7 +1883,7 @@ extern "C" cudaError_t rvl_search_configure(size_t smem, int device, int *grid_o
     e = cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, RVL_KSCORE_WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, warps * 32, smem);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -1850,19 +1891,19 @@ extern "C" cudaError_t rvl_search_configure(size_t smem, int device, int *grid_o
     return cudaSuccess;
 }
 
-extern "C" cudaError_t rvl_launch_search(const RvlSearchArgs *a, int grid_x, size_t smem, cudaStream_t st)
+extern "C" cudaError_t rvl_launch_search(const RvlSearchArgs *a, int grid_x, int warps, size_t smem, cudaStream_t st)
 {
     void *args[] = {(void *)a};
-    return cudaLaunchCooperativeKernel((const void *)k_search, dim3(grid_x), dim3(RVL_KSCORE_WARPS * 32), args, smem, st);
+    return cudaLaunchCooperativeKernel((const void *)k_search, dim3(grid_x), dim3(warps * 32), args, smem, st);
 }
 
-extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, size_t smem, const uint64_t *bits,
+extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, int warps, size_t smem, const uint64_t *bits,
                                  const double *u_all, const double *xc_all, const RvlTarget *tg,
                                  const uint64_t *seeds, const double *bcvtab, const double *tt, double *scores,
                                  RvlCandHead *part, unsigned long long *work, unsigned long long *ctr,
                                  const int64_t *uniq, int64_t U, cudaStream_t st)
 {
-    k_score<<<grid_x, RVL_KSCORE_WARPS * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, part,
+    k_score<<<grid_x, warps * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, part,
                                                         work, ctr, uniq, U);
 }
 

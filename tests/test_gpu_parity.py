@@ -364,7 +364,7 @@ def test_invalid_inputs_raise_no_fallback():
 def test_sample_count_limit_is_an_error_not_a_crash():
     import revealer_b200 as rb
     from revealer_b200 import _lib
-    n = 200_000                                                  # > the shared-memory budget of k_score
+    n = 1_600_000                                                # one bit row (n / 8 bytes) > the shared-memory budget of a k_score worker warp
     with _ctx() as ctx:
         with pytest.raises(rb.RevealerError) as e:
             ctx.load_matrix(np.zeros((2, n), dtype=np.uint8))
