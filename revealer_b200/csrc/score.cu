@@ -316,24 +316,23 @@ __device__ __forceinline__ unsigned rvl_bits(int lo, int hi)
 //   sum_i Q_i log Q_i = g (log g SX + LX) + E (G log g + LLX)            closed form, pass A's per-k sums of X, X log X, log X
 //                     + E ln2 sum_i (1 + t_i) log2(1 + 1/t_i),           t_i = g X_i / E
 // exactly.  The second line is O(E) per cell whatever t is -- it IS the whole effect of the eps floor on the column --
-// so single precision carries it: a relative error of 1e-5 there moves CMI by < 1e-16 (tools/proto/epilogue_softfloor.py:
-// the column sums come out closer to a long-double evaluation than the cell-by-cell double-precision logs were).
+// so single precision carries it: summed over the cube it is ~2e-14 of CMI (at most 5e-12: G^3 cells at the floor), and a
+// relative error of 4e-4 there moves CMI by ~1e-17, < 2e-15 in the worst case (tools/proto/epilogue_softfloor.py: the
+// column sums come out closer to a long-double evaluation than the cell-by-cell double-precision logs were).
 // With d = log2 t = lf[cls][k][i] + lgf[dist] (float copies of log2 X from pass A and of log2(g / E)), a = |d|, e = 2^-a
-// (one MUFU.EX2) and P(e) = log2(1 + e) / e (degree 5, relative error 8.4e-6):
+// (one MUFU.EX2) and P(e) = log2(1 + e) / e (degree-3 minimax on [0, 1], relative error 3.9e-4):
 //   d > 0  (cell above the floor):   (1 + t) log2(1 + 1/t) = (1 + e) P(e)
 //   d <= 0 (cell at the floor):      (1 + t) log2(1 + 1/t) = (1 + e) (a + e P(e))
-// -- 13 FP32-pipe instructions and one MUFU per cell against 11 FP64 + table gather + I2F for Q = fma(..), log Q, Q log Q.
+// -- 11 FP32-pipe instructions and one MUFU per cell against 11 FP64 + table gather + I2F for Q = fma(..), log Q, Q log Q.
 // A clamped X (pass A takes the log of max(X, 1e-290)) stays consistent: closed form and correction use the same log X.
 __device__ __forceinline__ float rvl_soft_cell(float d)
 {
     const float a = fabsf(d);
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a));
-    float p = fmaf(e, -0.034435972571372986f, 0.14603309333324432f);
-    p = fmaf(p, e, -0.3030364513397217f);
-    p = fmaf(p, e, 0.46917417645454407f);
-    p = fmaf(p, e, -0.7204262018203735f);
-    p = fmaf(p, e, 1.4426828622817993f);
+    float p = fmaf(e, -0.10725461691617966f, 0.3664810359477997f);
+    p = fmaf(p, e, -0.701747477054596f);
+    p = fmaf(p, e, 1.4421281814575195f);
     const bool up = d > 0.f;
     const float r = fmaf(up ? 1.0f : e, p, up ? 0.0f : a);
     return fmaf(e, r, r);
@@ -342,6 +341,7 @@ __device__ __forceinline__ float rvl_soft_cell(float d)
 // stride (in floats) of one k row of the float table lf[class][k][i]: a multiple of 4 (16-byte rows, LDS.128) whose
 // quarter is odd, so that the rows of 8 consecutive k start in 8 distinct 16-byte bank groups
 __host__ __device__ __forceinline__ int rvl_lf_stride(int G) { return (((G + 3) >> 2) | 1) * 4; }
+__host__ __device__ __forceinline__ size_t rvl_lf_bytes(int G) { return sizeof(float) * 2 * (size_t)G * rvl_lf_stride(G); }
 
 // 3-D epilogue, production form.  Same quantity as rvl_cmi_epilogue, organised around the majority
 // y-class `am` (the class holding most samples; a = 0 for the usual sparse alteration row):
@@ -412,11 +412,15 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, float *__restrict__ lf, 
     for (int i = 0; i < G; i++) {
         const double V = fma(S.A[i][M0], gz0, S.A[i][M1] * gz1);
         const double W = fma(S.A[i][m0], gz0, S.A[i][m1] * gz1);
-        minVh = min(minVh, __double2hiint(V));
-        maxVh = max(maxVh, __double2hiint(V));
-        maxWh = max(maxWh, __double2hiint(W));
+        const int Vh = __double2hiint(V), Wh = __double2hiint(W);
+        minVh = min(minVh, Vh);
+        maxVh = max(maxVh, Vh);
+        maxWh = max(maxWh, Wh);
         const double qxz = fma(Gy, V + W, gE);
-        const double Vs = fmax(V, 1e-290), Ws = fmax(W, 1e-290); // keeps the fast log in range (see rvl_soft_cell)
+        // X >= 0 below 2^-963 ~ 1.3e-290 is lifted to at least that by an integer max on its high word: keeps the fast log in
+        // range, and closed form and correction use the same log X (see rvl_soft_cell)
+        const double Vs = __hiloint2double(max(Vh, 0x03c00000), __double2loint(V));
+        const double Ws = __hiloint2double(max(Wh, 0x03c00000), __double2loint(W));
         const double lv = rvl_logq<FAST>(Vs), lw = rvl_logq<FAST>(Ws), lq = rvl_logq<FAST>(qxz);
         SV += V;
         LV = fma(V, lv, LV);
@@ -1410,7 +1414,7 @@ __device__ __forceinline__ void rvl_score_phase(const RvlParams &P, const uint64
                                         : (mode == RVL_MODE_CIC ? (unsigned long long)nitems + 2ull * GG + G : GG + 2ull * G) + 1ull);
                 atomicAdd(&ctr[6], (cols ? 34ull * GG + 10ull * nitems + 2ull * (unsigned long long)ntwo + 70ull * G
                                          : 10ull * (unsigned long long)nitems + 6ull * GG) + (unsigned long long)nexp * G * 6ull);
-                atomicAdd(&ctr[7], (unsigned long long)ntwo * G);  // soft cells (13 FP32 instructions + 1 MUFU each)
+                atomicAdd(&ctr[7], (unsigned long long)ntwo * G);  // soft cells (11 FP32 instructions + 1 MUFU each)
             }
         }
         if (rvl_ahead(score, f, best_v, best_i, P.negative)) { best_v = score; best_i = f; }
@@ -1418,6 +1422,17 @@ __device__ __forceinline__ void rvl_score_phase(const RvlParams &P, const uint64
     }
     // every lane of a warp holds the same best_v / best_i
     if (t >= 0 && lane == 0) { RvlCandHead h; h.score = best_v; h.row = best_i; part[(size_t)t * nslots + slot] = h; }
+}
+
+// This warp's slice of the dynamic shared memory.  Its 32-bit shared-window address is made opaque to the compiler: left
+// alone it recomputes tid / 32 * bytes + base inside the hot loops of the epilogue (6-7 instructions per trip) instead of
+// keeping it; going through the shared window keeps the accesses LDS / STS rather than generic loads.
+__device__ __forceinline__ unsigned char *rvl_warp_smem(unsigned char *smem_raw, int warp, const RvlParams &P)
+{
+    unsigned int off = (unsigned int)__cvta_generic_to_shared(smem_raw) +
+                       (unsigned int)warp * (unsigned int)(sizeof(RvlWarpScratch) + rvl_lf_bytes(P.G) + sizeof(uint64_t) * (size_t)P.words);
+    asm volatile("" : "+r"(off));
+    return reinterpret_cast<unsigned char *>(__cvta_shared_to_generic((size_t)off));
 }
 
 #ifndef RVL_SCORE_MIN_CTAS
@@ -1437,12 +1452,13 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
 
     rvl_logtab_fill(rvl_logtab_g); // the only block barrier of the kernel
 
-    // dynamic shared memory: [nwarps] scratch | [nwarps][words] bit rows | [nwarps][2 G stride] float tables (rvl_score_plan)
-    RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
-    uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + nwarps);
-    float *lfs = reinterpret_cast<float *>(yrows + (size_t)nwarps * P.words);
-    rvl_score_phase<false>(P, bits, u_all, xc_all, tg_all, seeds, bcvtab, tt, scores, part, work, ctr, uniq, U, scr[warp],
-                           yrows + (size_t)warp * P.words, lfs + (size_t)warp * 2 * P.G * rvl_lf_stride(P.G), slot, nslots, lane);
+    // dynamic shared memory, per warp: scratch | float table of the soft cells [2][G][stride] | bit row (rvl_score_plan)
+    unsigned char *base = rvl_warp_smem(smem_raw, warp, P);
+    RvlWarpScratch &S = *reinterpret_cast<RvlWarpScratch *>(base);
+    float *lf = reinterpret_cast<float *>(base + sizeof(RvlWarpScratch));
+    uint64_t *yrow = reinterpret_cast<uint64_t *>(base + sizeof(RvlWarpScratch) + rvl_lf_bytes(P.G));
+    rvl_score_phase<false>(P, bits, u_all, xc_all, tg_all, seeds, bcvtab, tt, scores, part, work, ctr, uniq, U, S, yrow, lf, slot, nslots,
+                           lane);
 }
 
 // ---- k_search: the whole search in ONE persistent cooperative launch ---------------------------------------
@@ -1509,13 +1525,13 @@ k_search(const RvlSearchArgs a)
         }
         __syncwarp();
         {
-            RvlWarpScratch *scr = reinterpret_cast<RvlWarpScratch *>(smem_raw);
-            uint64_t *yrows = reinterpret_cast<uint64_t *>(scr + nwarps);
-            float *lfs = reinterpret_cast<float *>(yrows + (size_t)nwarps * P.words);
+            unsigned char *base = rvl_warp_smem(smem_raw, warp, P);
+            RvlWarpScratch &S = *reinterpret_cast<RvlWarpScratch *>(base);
+            float *lf = reinterpret_cast<float *>(base + sizeof(RvlWarpScratch));
+            uint64_t *yrow = reinterpret_cast<uint64_t *>(base + sizeof(RvlWarpScratch) + rvl_lf_bytes(P.G));
             rvl_score_phase<RVL_KSEARCH_COH>(P, a.bits, a.u_all, a.xc_all, a.tg_all, seeds_cur, a.bcvtab, a.tt,
-                                             a.scores + (size_t)it * P.T * P.F, a.part, a.work + it, a.ctr, a.uniq, a.U, scr[warp],
-                                             yrows + (size_t)warp * P.words, lfs + (size_t)warp * 2 * P.G * rvl_lf_stride(P.G), slot,
-                                             nslots, lane);
+                                             a.scores + (size_t)it * P.T * P.F, a.part, a.work + it, a.ctr, a.uniq, a.U, S, yrow, lf,
+                                             slot, nslots, lane);
         }
         __threadfence(); // this warp's part[] entries before the block's ticket
         __syncthreads();
@@ -1846,7 +1862,7 @@ extern "C" cudaError_t rvl_upload_log_table(void)
 // `budget` bytes of dynamic shared memory.  Returns the bytes to request and sets *warps_out; 0 when not even one warp fits.
 extern "C" size_t rvl_score_plan(int words, int G, size_t budget, int *warps_out)
 {
-    const size_t per_warp = sizeof(RvlWarpScratch) + sizeof(uint64_t) * (size_t)words + sizeof(float) * 2 * (size_t)G * rvl_lf_stride(G);
+    const size_t per_warp = sizeof(RvlWarpScratch) + sizeof(uint64_t) * (size_t)words + rvl_lf_bytes(G);
     int w = (int)(budget / per_warp);
     if (w > RVL_KSCORE_WARPS) w = RVL_KSCORE_WARPS;
     *warps_out = w;
