@@ -579,24 +579,48 @@ class Bench:
             # exp = 25 n + 100, log = 16 900, plain flop = 50 n + 1.8e5  (n = 1000: 25 100 exp, 16 900 log, 2.3e5 flop)
             alg_eval = cnt * t_cnt
             alg_flops = alg_eval * ((G * n + 4 * G) * FLOP_PER_EXP + (G ** 3 + 2 * G * G + G) * FLOP_PER_LOG + 2 * G * n + 1.8e5)
-            traffic = None
-            try:  # DRAM bytes per launch from the committed ncu capture of this workload (1 GPU)
+            traffic, inst_per_eval = None, None
+            try:  # DRAM bytes and warp instructions per launch from the committed ncu capture of this workload (1 GPU)
                 tj = json.load(open(os.path.join(ROOT, "profiles", "k_score_traffic.json")))
-                if tj["workload"] == wl_name and world == 1 and not args.features:
-                    traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+                if tj["workload"] == wl_name and not args.features:
+                    inst_per_eval = tj["warp_instructions_per_launch"] / tj["evaluations_per_launch"]
+                    if world == 1:
+                        traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
             except Exception:
                 pass
-            out["roofline"] = {
-                "kernel": "k_search" if args.fused else "k_score", "bound": "fp64", "achieved": flops / dur / 1e12, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": flops / dur / 1e12 / fp64_peak if fp64_peak else None, "traffic": traffic,
+            fp64_view = {
+                "bound": "fp64", "achieved": flops / dur / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": flops / dur / 1e12 / fp64_peak if fp64_peak else None,
                 "peak_source": "measured live: rvl_measure_fp64_peak (DFMA chain); MEASURED_PEAKS.json has no FP64 figure",
+                "convention": "EXECUTED FP64 work from kernel counters: exp=%d flop, log=%d flop (FP64-pipe SASS instructions x2), "
+                              "+ plain FMA/ADD; the soft cells (%d per launch, 9 FP32 instructions + 1 MUFU each) are not FP64 "
+                              "work" % (FLOP_PER_EXP, FLOP_PER_LOG, int(ctr.get("soft_cells", 0) / k_n)),
+            }
+            # Since the one-class density columns moved to single precision the FP64 pipe is ~30 % busy and the kernel is bound by
+            # INSTRUCTION ISSUE (one warp instruction per clock and scheduler): that is the ceiling the headline frac is quoted
+            # against.  Numerator: warp instructions per evaluation of the committed ncu capture (same workload) x the evaluations
+            # this launch executed; denominator: 4 schedulers x SMs x the SM clock sampled during the timed region.
+            sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            if inst_per_eval and sm_mhz:
+                issue_peak = 4.0 * sms * sm_mhz * 1e6 / 1e9           # G warp-instructions/s
+                issue_ach = inst_per_eval * evals / dur / 1e9
+                top = {"bound": "issue", "achieved": issue_ach, "peak": issue_peak, "unit": "G warp-inst/s",
+                       "frac": issue_ach / issue_peak,
+                       "peak_source": "4 warp schedulers x %d SMs x %.0f MHz (SM clock sampled by NVML during the timed region)" % (sms, sm_mhz),
+                       "convention": "%.0f warp instructions per evaluation (ncu smsp__inst_executed.sum of the committed capture, "
+                                     "profiles/k_score_traffic.json) x %.0f evaluations executed per launch (kernel counter) / launch "
+                                     "duration; the FP64-pipe view of earlier rounds is kept under `fp64`" % (inst_per_eval, evals)}
+            else:
+                top = dict(fp64_view)
+            out["roofline"] = {
+                "kernel": "k_search" if args.fused else "k_score", **top, "traffic": traffic, "fp64": fp64_view,
                 "launch_ms": dur * 1e3, "launches": int(k_n), "share_of_step": k_ms / (ms_prof * nprof),
                 "measured": "CUDA events around every launch of the kernel on its stream, in %d extra searches with the "
                             "profiling switch on (%.3f ms per search there, %.3f ms in the uninstrumented timed region)"
                             % (nprof, ms_prof, ms),
-                "convention": "EXECUTED work from kernel counters: exp=%d flop, log=%d flop (FP64-pipe SASS "
-                              "instructions x2), + plain FMA/ADD" % (FLOP_PER_EXP, FLOP_PER_LOG),
-                "per_launch": {"evaluations": evals, "exp": exps, "log": logs, "flop": flops},
+                "per_launch": {"evaluations": evals, "exp": exps, "log": logs, "flop": flops,
+                               "soft_cells": ctr.get("soft_cells", 0) / k_n},
                 "algorithmic": {"convention": "SURVEY 8(d) literal work per evaluation (25n+100 exp, 16 900 log, 50n+1.8e5 flop) "
                                               "x every row of the shard, same flop weights; > 1 means work the kernel avoids "
                                               "(x-axis table, dead / factorised density columns, duplicate rows), not a fuller pipe",

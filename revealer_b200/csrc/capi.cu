@@ -57,7 +57,7 @@ void rvl_launch_unpack_rows(const uint64_t *src, const int64_t *rows, int64_t k,
 void rvl_launch_bcv_binary_table(int n, double *table, cudaStream_t st);
 void rvl_launch_target_setup(const double *x_all, int n, int T, int G, RvlTarget *tg, double *u_all, double *xc_all,
                              int *bin_all, int *cnt_all, int *nonfinite, int permuted, cudaStream_t st);
-size_t rvl_score_plan(int words, int G, size_t budget, int *warps_out);
+size_t rvl_score_plan(int words, int G, size_t budget, int max_warps, int *warps_out);
 cudaError_t rvl_score_configure(size_t smem, int warps, int device, int *grid_out);
 void rvl_launch_score(const RvlParams *P, int grid_x, int warps, size_t smem, const uint64_t *bits, const double *u_all,
                       const double *xc_all, const RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
@@ -198,6 +198,7 @@ struct rvl_ctx {
     size_t part_cap = 0;
     int score_grid_x = 0; // persistent grid of k_score (SMs x resident CTAs)
     int score_warps = 0;  // worker warps per block (rvl_score_plan)
+    int score_warps_fixed = 0; // > 0: block width forced (environment RVL_SCORE_WARPS, tuning only)
     size_t score_smem = 0;
     unsigned long long *d_work = nullptr; // k_score's item counter
     bool work_dirty = true;
@@ -317,6 +318,7 @@ extern "C" int rvl_create(rvl_ctx **out, int device)
         return RVL_ERR_CUDA;
     }
     ctx->own_stream = true;
+    if (const char *w = getenv("RVL_SCORE_WARPS")) ctx->score_warps_fixed = atoi(w); // tuning: force the block width of k_score
     *out = ctx;
     return RVL_OK;
 }
@@ -572,7 +574,7 @@ static int begin_matrix(rvl_ctx *ctx, int64_t F, int64_t n)
     if (ctx->T > 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "matrix has n=%lld but targets have n=%d", (long long)n, ctx->n);
     {
         int w = 0;
-        if (!rvl_score_plan((int)(((n + 63) / 64 + 1) & ~1ll), RVL_MAX_GRID, RVL_SCORE_DYN_SMEM_MAX, &w))
+        if (!rvl_score_plan((int)(((n + 63) / 64 + 1) & ~1ll), RVL_MAX_GRID, RVL_SCORE_DYN_SMEM_MAX, 0, &w))
             return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (one bit row of n/8 bytes per worker warp; n <= ~1 400 000)", (long long)n);
     }
     free_matrix(ctx);
@@ -1000,7 +1002,7 @@ static int set_targets_impl(rvl_ctx *ctx, const double *targets, int64_t n, int6
     if (ctx->F >= 0 && ctx->n != (int)n) return fail(ctx, RVL_ERR_ARG, "targets have n=%lld but matrix has n=%d", (long long)n, ctx->n);
     {
         int w = 0;
-        if (!rvl_score_plan((int)(((n + 63) / 64 + 1) & ~1ll), RVL_MAX_GRID, RVL_SCORE_DYN_SMEM_MAX, &w))
+        if (!rvl_score_plan((int)(((n + 63) / 64 + 1) & ~1ll), RVL_MAX_GRID, RVL_SCORE_DYN_SMEM_MAX, 0, &w))
             return fail(ctx, RVL_ERR_ARG, "n=%lld samples exceed the score kernel's shared-memory budget (one bit row of n/8 bytes per worker warp; n <= ~1 400 000)", (long long)n);
     }
     free_targets(ctx);
@@ -1082,10 +1084,22 @@ extern "C" int rvl_set_seed(rvl_ctx *ctx, const uint8_t *seed, int64_t n, int pe
 
 // Persistent-grid configuration of k_score for the current (n, T): shared memory, grid = SMs x
 // resident CTAs, the per-warp best slots and the work counter.
+// Worker warps per block of k_score / k_search and the dynamic shared memory they need (0: a bit row does not fit).
+static size_t plan_score(rvl_ctx *ctx, int *warps)
+{
+    size_t smem = rvl_score_plan(ctx->words, ctx->opts.n_grid, RVL_SCORE_DYN_SMEM_MAX, 0, warps);
+    if (!smem) return 0;
+    // (A narrower block for small shards -- fewer, faster warps so that the last round of whole evaluations is fuller --
+    // was measured and loses: 12 500 rows per GPU take 144 us with 16 warps per SM, 150-157 with 15-13, 153 with 12.)
+    const int want = ctx->score_warps_fixed;
+    if (want > 0 && want < *warps) smem = rvl_score_plan(ctx->words, ctx->opts.n_grid, RVL_SCORE_DYN_SMEM_MAX, want, warps);
+    return smem;
+}
+
 static int configure_score(rvl_ctx *ctx)
 {
     int warps = 0;
-    size_t smem = rvl_score_plan(ctx->words, ctx->opts.n_grid, RVL_SCORE_DYN_SMEM_MAX, &warps);
+    size_t smem = plan_score(ctx, &warps);
     if (!smem) return fail(ctx, RVL_ERR_ARG, "n=%d needs more than 194 KB of dynamic shared memory per worker warp", ctx->n);
     if (smem != ctx->score_smem || warps != ctx->score_warps || ctx->score_grid_x <= 0) {
         int grid = 0;
@@ -1442,7 +1456,7 @@ static bool fused_possible(rvl_ctx *ctx)
     if (!ctx->fused || ctx->F < 0 || ctx->T <= 0) return false;
     if (ctx->world > 1 && !ctx->p2p) return false;
     int warps = 0;
-    size_t smem = rvl_score_plan(ctx->words, ctx->opts.n_grid, RVL_SCORE_DYN_SMEM_MAX, &warps);
+    size_t smem = plan_score(ctx, &warps);
     if (!smem) return false;
     if (ctx->search_grid_x < 0 || smem != ctx->search_smem || warps != ctx->search_warps) {
         int grid = 0;

@@ -1863,12 +1863,14 @@ extern "C" cudaError_t rvl_upload_log_table(void)
 
 // Block shape of k_score / k_search for bit rows of `words` words and an n_grid of G: the most worker warps (<= 16, one
 // block per SM) whose scratch -- RvlWarpScratch + the bit row + the float table of the soft cells, per warp -- fits in
-// `budget` bytes of dynamic shared memory.  Returns the bytes to request and sets *warps_out; 0 when not even one warp fits.
-extern "C" size_t rvl_score_plan(int words, int G, size_t budget, int *warps_out)
+// `budget` bytes of dynamic shared memory, at most max_warps when that is > 0.  Returns the bytes to request and sets
+// *warps_out; 0 when not even one warp fits.
+extern "C" size_t rvl_score_plan(int words, int G, size_t budget, int max_warps, int *warps_out)
 {
     const size_t per_warp = sizeof(RvlWarpScratch) + sizeof(uint64_t) * (size_t)words + rvl_lf_bytes(G);
     int w = (int)(budget / per_warp);
     if (w > RVL_KSCORE_WARPS) w = RVL_KSCORE_WARPS;
+    if (max_warps > 0 && w > max_warps) w = max_warps;
     *warps_out = w;
     if (w < 1) return 0;
     size_t smem = per_warp * (size_t)w;
