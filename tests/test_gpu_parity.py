@@ -504,6 +504,33 @@ def test_production_epilogue_equals_literal_cube(oracle):
         assert ok, err
 
 
+@pytest.mark.parametrize("G", [8, 17, 32])
+def test_production_epilogue_other_grids_and_exact_pruning(G):
+    """The column intervals, the float table's row stride (multiple of 4 floats with an odd quarter: 12 / 20 / 36 for these
+    grids) and the soft cells at n_grid != 25, and with the mass-based pruning switched off in BOTH modes (theta = 0: a
+    column is dead only where neither class can change fl(Q) -- the interval ends then meet the visibility bounds)."""
+    n, F = 300, 700
+    w = _workload(n, F)
+    rng = np.random.default_rng(G)
+    m2 = w["m2"].copy()
+    for r, p in zip(range(3, 3 + 5), (0.15, 0.4, 0.6, 0.85, 0.98)):              # dense and complemented rows too
+        m2[r] = rng.random(n) < p
+    with _ctx() as ctx:
+        ctx.set_options(n_grid=G)
+        ctx.load_matrix(m2)
+        ctx.set_targets(w["target"])
+        ctx.set_seed(w["seed"])
+        a = ctx.score_once()[0]
+        ctx.set_prune_theta(0.0)
+        a0 = ctx.score_once()[0]
+        ctx.set_dense_x(True)
+        b0 = ctx.score_once()[0]
+    cmi_a, cmi_a0, cmi_b0 = (-0.5 * np.log1p(-v * v) for v in (a, a0, b0))
+    assert np.max(np.abs(cmi_a0 - cmi_b0)) <= 2e-14, (G, np.max(np.abs(cmi_a0 - cmi_b0)))
+    assert np.max(np.abs(cmi_a - cmi_b0)) <= 1e-12
+    assert np.array_equal(np.sign(a0), np.sign(b0))
+
+
 # ------------------------------------------------------------------ target batches and the permutation null
 
 def test_target_batch_equals_individual_runs():
