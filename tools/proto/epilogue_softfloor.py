@@ -88,6 +88,55 @@ def l3_softfloor(A, g0y, g0z, epsq, hy, am, theta=1e-14, stats=None):
     return tot, Stot
 
 
+def column_errors(A, g0y, g0z, epsq, hy, am, theta=1e-14):
+    """Error of every column kind against a long-double evaluation of the same column, summed per kind, in units of S
+    (i.e. as it enters CMI)."""
+    ld = np.longdouble
+    G = len(g0y)
+    gz = np.stack([g0z, g0z[::-1]])
+    M0, M1, m0, m1 = am * 2, am * 2 + 1, (1 - am) * 2, (1 - am) * 2 + 1
+    V = A[:, M0][:, None] * gz[0][None, :] + A[:, M1][:, None] * gz[1][None, :]
+    W = A[:, m0][:, None] * gz[0][None, :] + A[:, m1][:, None] * gz[1][None, :]
+    t = np.arange(G) / (G - 1) / hy
+    LG = -0.5 * t * t
+    E, lE = epsq, np.log(epsq)
+    Stot = A.sum() * g0y.sum() * g0z.sum() + G ** 3 * epsq
+    dead_thr = max(E * 2.0 ** -55, theta * Stot / G ** 3)
+    err = dict(dead=0.0, fact=0.0, soft=0.0, four=0.0)
+    cnt = dict(dead=0, fact=0, soft=0, four=0)
+    for k in range(G):
+        X = [V[:, k], W[:, k]]
+        lX = [np.log(np.maximum(x, 1e-290)) for x in X]
+        SX = [x.sum() for x in X]
+        LX = [(x * l).sum() for x, l in zip(X, lX)]
+        LLX = [l.sum() for l in lX]
+        lXf = [(l * LOG2E).astype(F32) for l in lX]
+        mx = [x.max() for x in X]
+        mn = [x.min() for x in X]
+        for jp in range(G):
+            g = [g0y[jp], g0y[G - 1 - jp]]
+            lg = [LG[jp], LG[G - 1 - jp]]
+            q = ld(g[0]) * X[0].astype(ld) + ld(g[1]) * X[1].astype(ld) + ld(E)
+            exact = (q * np.log(q)).sum()
+            vis = [g[c] * mx[c] >= 2.0 ** -54 * E for c in (0, 1)]
+            alive = any(g[c] * mx[c] >= 0.5 * dead_thr for c in (0, 1))
+            if not alive:
+                kind, val = "dead", G * E * lE
+            elif vis[0] and vis[1]:
+                qq = g[0] * X[0] + g[1] * X[1] + E
+                kind, val = "four", (qq * np.log(qq)).sum()
+            else:
+                c = 0 if vis[0] else 1
+                closed = g[c] * (lg[c] * SX[c] + LX[c]) + E * (G * lg[c] + LLX[c])
+                if g[c] * mn[c] >= 16 * E:
+                    kind, val = "fact", closed + E * G
+                else:
+                    kind, val = "soft", closed + E * np.log(2.0) * corr_f32(lXf[c], F32((lg[c] - lE) * LOG2E))
+            err[kind] += float(val - exact)
+            cnt[kind] += 1
+    return {k: v / Stot for k, v in err.items()}, cnt
+
+
 if __name__ == "__main__":
     from revealer_b200 import synth
     worst = 0
