@@ -29,7 +29,9 @@
 
 // dynamic shared memory k_score may ask for: 227 KB per block minus its static part (the 32 KB log table
 // of rvl_log_pos + 1 KB of slack)
+#ifndef RVL_SCORE_DYN_SMEM_MAX
 #define RVL_SCORE_DYN_SMEM_MAX ((size_t)(227 - 33) * 1024)
+#endif
 
 // launchers (score.cu, bandwidth.cu)
 extern "C" {

@@ -123,7 +123,11 @@ struct RvlSearchArgs {
 // each = 32 KB per block): the 8 lanes of each quarter-warp of an LDS.128 then hit 8 distinct 16-byte
 // bank groups whatever their entries, so the gather is conflict-free.
 #define RVL_LOGTAB_ENTRIES 256
+#ifndef RVL_LOGTAB_COPIES
 #define RVL_LOGTAB_COPIES 8
+#endif
+// byte offset of table entry (hs >> 12) & 255: entries are RVL_LOGTAB_COPIES * 16 bytes apart
+#define RVL_LOGTAB_OFF(hs) (((hs) >> (RVL_LOGTAB_COPIES == 8 ? 5 : RVL_LOGTAB_COPIES == 4 ? 6 : 7)) & (255 * RVL_LOGTAB_COPIES * 16))
 static __constant__ double RVL_LG[5] = {1.0 / 3, -0.5, 1.0 / 5, -0.25, 0.6931471805599453094};
 
 // The block's copy of the table (one instance per kernel that calls it).
@@ -151,7 +155,7 @@ __device__ __forceinline__ double rvl_log_pos(double q)
     const int hs = __double2hiint(q) + (0x3ff00000 - 0x3fe6a09e);
     const int k = (hs >> 20) - 0x3ff;
     const char *base = reinterpret_cast<const char *>(rvl_logtab_smem()) + (threadIdx.x & (RVL_LOGTAB_COPIES - 1)) * 16;
-    const double2 e = *reinterpret_cast<const double2 *>(base + ((hs >> 5) & 0x7f80)); // entry (hs >> 12) & 255, 128 B apart
+    const double2 e = *reinterpret_cast<const double2 *>(base + RVL_LOGTAB_OFF(hs)); // entry (hs >> 12) & 255, 128 B apart
     const double f = __hiloint2double(__double2hiint(e.x) - (k << 20), __double2loint(e.x));
     const double r = fma(q, f, -1.0);
     const double r2 = r * r;
@@ -172,10 +176,10 @@ __device__ __forceinline__ void rvl_log_pos4(const double q0, const double q1, c
     const char *base = reinterpret_cast<const char *>(rvl_logtab_smem()) + (threadIdx.x & (RVL_LOGTAB_COPIES - 1)) * 16;
     const int s0 = __double2hiint(q0) + (0x3ff00000 - 0x3fe6a09e), s1 = __double2hiint(q1) + (0x3ff00000 - 0x3fe6a09e),
               s2 = __double2hiint(q2) + (0x3ff00000 - 0x3fe6a09e), s3 = __double2hiint(q3) + (0x3ff00000 - 0x3fe6a09e);
-    const double2 e0 = *reinterpret_cast<const double2 *>(base + ((s0 >> 5) & 0x7f80));
-    const double2 e1 = *reinterpret_cast<const double2 *>(base + ((s1 >> 5) & 0x7f80));
-    const double2 e2 = *reinterpret_cast<const double2 *>(base + ((s2 >> 5) & 0x7f80));
-    const double2 e3 = *reinterpret_cast<const double2 *>(base + ((s3 >> 5) & 0x7f80));
+    const double2 e0 = *reinterpret_cast<const double2 *>(base + RVL_LOGTAB_OFF(s0));
+    const double2 e1 = *reinterpret_cast<const double2 *>(base + RVL_LOGTAB_OFF(s1));
+    const double2 e2 = *reinterpret_cast<const double2 *>(base + RVL_LOGTAB_OFF(s2));
+    const double2 e3 = *reinterpret_cast<const double2 *>(base + RVL_LOGTAB_OFF(s3));
     const int k0 = (s0 >> 20) - 0x3ff, k1 = (s1 >> 20) - 0x3ff, k2 = (s2 >> 20) - 0x3ff, k3 = (s3 >> 20) - 0x3ff;
     const double f0 = __hiloint2double(__double2hiint(e0.x) - (k0 << 20), __double2loint(e0.x));
     const double f1 = __hiloint2double(__double2hiint(e1.x) - (k1 << 20), __double2loint(e1.x));

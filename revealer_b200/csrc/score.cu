@@ -40,8 +40,12 @@
 __device__ double2 rvl_logtab_g[RVL_LOGTAB_ENTRIES];
 
 // ---- per-warp scratch in shared memory ----------------------------------------------------
+#ifndef RVL_LIST_MAX
 #define RVL_LIST_MAX 512    // minority-class samples listed per row (longer rows walk their bit words instead)
+#endif
+#ifndef RVL_ITEMS_CAP
 #define RVL_ITEMS_CAP 1024  // direct (j,k) columns: four-term ones from the front, two-term ones from the back
+#endif
 struct __align__(16) RvlWarpScratch {
     double A[RVL_MAXG][4];     // A[i][a*2+b]: x-axis kernel sums of the four (y,z) classes
     double gy[2][RVL_MAXG];    // gy[a][j]
