@@ -434,10 +434,9 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, float *__restrict__ lf, 
         SW += W;
         LW = fma(W, lw, LW);
         LLW += lw;
-        if (active) {
-            lfV[i] = (float)lv * 1.4426950408889634f;
-            lfW[i] = (float)lw * 1.4426950408889634f;
-        }
+        // (lanes >= G repeat lane 0's k and store the same two values to the same two addresses: no branch needed)
+        lfV[i] = (float)lv * 1.4426950408889634f;
+        lfW[i] = (float)lw * 1.4426950408889634f;
         accxz = fma(qxz, lq, accxz);
     }
     const double minV = __hiloint2double(minVh, 0);                 // <= the true minimum
