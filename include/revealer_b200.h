@@ -279,9 +279,11 @@ int64_t rvl_unique_rows(const rvl_ctx *ctx);
 /* Work counters of the score kernel since the last reset: out4[0] evaluations that ran the KDE path,
  * out4[1] live (j,k) density columns (n_grid log() each), out4[2] dense-pass exp() evaluations. */
 int rvl_get_counters(rvl_ctx *ctx, uint64_t *out4, int reset);
-/* The same with more slots (n_out <= 8): out[3] (j,k) columns in the O(1) factorised form, out[4] direct columns
- * evaluated with two of the four class terms (the other y-class cannot change fl(Q) anywhere in the column),
- * out[5] log() evaluations, out[6] FP64 flops outside exp() and log() (an FMA counts 2).  Needs rvl_set_profiling. */
+/* The same with more slots (n_out <= 8): out[1] counts only the columns evaluated cell by cell with a double-precision
+ * log (both y-classes visible), out[3] (j,k) columns in the O(1) factorised form, out[4] one-class columns (the other
+ * y-class cannot change fl(Q) anywhere in the column) whose eps-floor correction is summed cell by cell in single
+ * precision, out[5] log() evaluations, out[6] FP64 flops outside exp() and log() (an FMA counts 2), out[7] single-precision
+ * "soft" cells (out[4] * n_grid).  Needs rvl_set_profiling. */
 int rvl_get_counters_ex(rvl_ctx *ctx, uint64_t *out, int n_out, int reset);
 /* Development aid: nanosecond (globaltimer) stamps of the phases of the last rvl_search_run's k_search launch, out[iters][8]:
  * [0] block 0 starts scoring, [1] block 0 done, [2] every block done, [3] candidate records + stamps published,
