@@ -579,13 +579,14 @@ class Bench:
             # exp = 25 n + 100, log = 16 900, plain flop = 50 n + 1.8e5  (n = 1000: 25 100 exp, 16 900 log, 2.3e5 flop)
             alg_eval = cnt * t_cnt
             alg_flops = alg_eval * ((G * n + 4 * G) * FLOP_PER_EXP + (G ** 3 + 2 * G * G + G) * FLOP_PER_LOG + 2 * G * n + 1.8e5)
-            traffic, inst_per_eval = None, None
+            traffic, inst_per_eval, ncu_view = None, None, None
             try:  # DRAM bytes and warp instructions per launch from the committed ncu capture of this workload (1 GPU)
                 tj = json.load(open(os.path.join(ROOT, "profiles", "k_score_traffic.json")))
                 if tj["workload"] == wl_name and not args.features:
                     inst_per_eval = tj["warp_instructions_per_launch"] / tj["evaluations_per_launch"]
                     if world == 1:
                         traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+                        ncu_view = dict(tj.get("ncu") or {}, source=tj.get("source"))  # the committed capture's own counters
             except Exception:
                 pass
             fp64_view = {
@@ -614,7 +615,7 @@ class Bench:
             else:
                 top = dict(fp64_view)
             out["roofline"] = {
-                "kernel": "k_search" if args.fused else "k_score", **top, "traffic": traffic, "fp64": fp64_view,
+                "kernel": "k_search" if args.fused else "k_score", **top, "traffic": traffic, "fp64": fp64_view, "ncu": ncu_view,
                 "launch_ms": dur * 1e3, "launches": int(k_n), "share_of_step": k_ms / (ms_prof * nprof),
                 "measured": "CUDA events around every launch of the kernel on its stream, in %d extra searches with the "
                             "profiling switch on (%.3f ms per search there, %.3f ms in the uninstrumented timed region)"
