@@ -469,7 +469,7 @@ class RevealerContext:
         out = (C.c_uint64 * 8)()
         self._ck(self._lib.rvl_get_counters_ex(self._h, out, 8, int(reset)))
         return dict(kde_evaluations=int(out[0]), live_columns=int(out[1]), dense_exps=int(out[2]),
-                    factorised_columns=int(out[3]), two_term_columns=int(out[4]), logs=int(out[5]),
+                    factorised_columns=int(out[3]), two_term_columns=int(out[4]), soft_columns=int(out[4]), logs=int(out[5]),
                     plain_flops=int(out[6]), soft_cells=int(out[7]))
 
     def measure_fp64_peak(self):

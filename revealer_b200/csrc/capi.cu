@@ -210,7 +210,7 @@ struct rvl_ctx {
 
     // instrumentation (rvl_set_profiling): work counters of k_score and a CUDA-event pair around each of its launches
     int profiling = 0;
-    unsigned long long *d_ctr = nullptr; // [0] KDE evaluations, [1] direct (j,k) columns, [2] x-axis exps, [3] factorised, [4] two-term
+    unsigned long long *d_ctr = nullptr; // [0] KDE evaluations, [1] four-term (j,k) columns, [2] x-axis exps, [3] factorised, [4] one-class soft columns, [5] logs, [6] flops, [7] soft cells
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_events;

@@ -44,7 +44,7 @@ __device__ double2 rvl_logtab_g[RVL_LOGTAB_ENTRIES];
 #define RVL_LIST_MAX 512    // minority-class samples listed per row (longer rows walk their bit words instead)
 #endif
 #ifndef RVL_ITEMS_CAP
-#define RVL_ITEMS_CAP 1024  // direct (j,k) columns: four-term ones from the front, two-term ones from the back
+#define RVL_ITEMS_CAP 1024  // (j,k) columns of pass C: four-term ones from the front, one-class (soft) ones from the back
 #endif
 struct __align__(16) RvlWarpScratch {
     double A[RVL_MAXG][4];     // A[i][a*2+b]: x-axis kernel sums of the four (y,z) classes
@@ -56,7 +56,7 @@ struct __align__(16) RvlWarpScratch {
     float lgf[RVL_MAXG];       // log2(g[d] / eps') as float: the column constant of the soft-floor cells (pass C)
     union {
         uint32_t list[RVL_LIST_MAX];   // minority-class samples of the row being scored (before the epilogue)
-        uint16_t items[RVL_ITEMS_CAP]; // (j << 5 | k) codes of the density columns evaluated cell by cell (epilogue)
+        uint16_t items[RVL_ITEMS_CAP]; // density columns evaluated cell by cell (epilogue): j << 5 | k, or class << 15 | d << 5 | k
     };
 };
 
