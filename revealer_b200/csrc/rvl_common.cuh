@@ -141,8 +141,11 @@ __device__ __forceinline__ double2 *rvl_logtab_smem()
 __device__ __forceinline__ void rvl_logtab_fill(const double2 *__restrict__ g)
 {
     double2 *tab = rvl_logtab_smem();
-    for (int i = threadIdx.x; i < RVL_LOGTAB_ENTRIES * RVL_LOGTAB_COPIES; i += blockDim.x)
-        tab[i] = g[i / RVL_LOGTAB_COPIES];
+    for (int e = threadIdx.x; e < RVL_LOGTAB_ENTRIES; e += blockDim.x) { // one global load per entry, then its copies
+        const double2 v = g[e];
+#pragma unroll
+        for (int c = 0; c < RVL_LOGTAB_COPIES; c++) tab[e * RVL_LOGTAB_COPIES + c] = v;
+    }
     __syncthreads();
 }
 
