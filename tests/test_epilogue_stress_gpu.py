@@ -6,6 +6,7 @@ import sys
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
@@ -14,3 +15,32 @@ def test_production_epilogue_random_configurations(seed):
     import stress_epilogue
     worst = stress_epilogue.run(ncfg=30, seed=seed, verbose=False)
     assert worst <= 5e-14, worst
+
+
+@pytest.mark.gpu
+def test_random_configurations_match_oracle(oracle):
+    """The same kind of random configurations (sparse, dense and complemented rows, sparse and dense seeds, several grids)
+    through the CUDA path against the CPU oracle, with the suite's score tolerance (tests/parity_tol.py)."""
+    import numpy as np
+    import revealer_b200 as rb
+    from parity_tol import score_close
+    rng = np.random.default_rng(424242)
+    for c in range(14):
+        n = int(rng.choice([40, 82, 129, 200, 333, 500, 1000]))
+        F = 120
+        G = int(rng.choice([8, 17, 25, 25, 32]))
+        x = rng.standard_normal(n) if rng.random() < 0.7 else rng.exponential(size=n)
+        dens = np.exp(rng.uniform(np.log(2.0 / n), np.log(0.98), size=F))
+        m2 = (rng.random((F, n)) < dens[:, None]).astype(np.uint8)
+        z = (rng.random(n) < float(np.exp(rng.uniform(np.log(2.0 / n), np.log(0.9))))).astype(np.uint8)
+        if z.sum() in (0, n):
+            z[0] = 1 - z[0]
+        with rb.RevealerContext(0) as ctx:
+            ctx.set_options(n_grid=G)
+            ctx.load_matrix(m2)
+            ctx.set_targets(x)
+            ctx.set_seed(z)
+            got = ctx.score_once()[0]
+        want = oracle.score_rows(x, m2.astype(float), z.astype(float), n_grid=G)
+        ok, err = score_close(got, want)                 # NaN (round-off-negative CMI, LIB:2614) is handled there
+        assert ok, (c, n, G, err)
