@@ -1359,19 +1359,27 @@ __device__ __forceinline__ void rvl_score_phase(const RvlParams &P, const uint64
                     }
                 }
                 __syncwarp();
-                int q = 0;
-                for (; q + 1 < mc; q += 2) { // two exp chains in flight
-                    const uint32_t e0 = S.list[q], e1 = S.list[q + 1];
-                    const double d0 = gi - u[e0 & 0x7fffffffu], d1 = gi - u[e1 & 0x7fffffffu];
-                    const double x0 = rvl_exp_neg(-beta * d0 * d0), x1 = rvl_exp_neg(-beta * d1 * d1);
-                    if (e0 >> 31) m1 += x0; else m0 += x0;
-                    if (e1 >> 31) m1 += x1; else m0 += x1;
-                }
-                if (q < mc) {
-                    const uint32_t e0 = S.list[q];
-                    const double d0 = gi - u[e0 & 0x7fffffffu];
-                    const double x0 = rvl_exp_neg(-beta * d0 * d0);
-                    if (e0 >> 31) m1 += x0; else m0 += x0;
+                // 32 samples at a time: every lane fetches one entry and its target coordinate (32 independent loads in flight
+                // instead of one dependent global load per sample), then the walk takes them from the lanes by shuffle --
+                // same samples, same order, two exp chains in flight
+                for (int q0 = 0; q0 < mc; q0 += 32) {
+                    const int cnt = min(32, mc - q0);
+                    const uint32_t el = (lane < cnt) ? S.list[q0 + lane] : 0u;
+                    const double ul = (lane < cnt) ? u[el & 0x7fffffffu] : 0.0;
+                    int j = 0;
+                    for (; j + 1 < cnt; j += 2) {
+                        const uint32_t e0 = __shfl_sync(0xffffffffu, el, j), e1 = __shfl_sync(0xffffffffu, el, j + 1);
+                        const double d0 = gi - __shfl_sync(0xffffffffu, ul, j), d1 = gi - __shfl_sync(0xffffffffu, ul, j + 1);
+                        const double x0 = rvl_exp_neg(-beta * d0 * d0), x1 = rvl_exp_neg(-beta * d1 * d1);
+                        if (e0 >> 31) m1 += x0; else m0 += x0;
+                        if (e1 >> 31) m1 += x1; else m0 += x1;
+                    }
+                    if (j < cnt) {
+                        const uint32_t e0 = __shfl_sync(0xffffffffu, el, j);
+                        const double d0 = gi - __shfl_sync(0xffffffffu, ul, j);
+                        const double x0 = rvl_exp_neg(-beta * d0 * d0);
+                        if (e0 >> 31) m1 += x0; else m0 += x0;
+                    }
                 }
                 __syncwarp();
             } else {
