@@ -24,8 +24,11 @@ Extra keys of the JSON line:
                  (column-major doubles in ordinary pageable memory): upload + bit-packing + targets + seed +
                  search + D2H of the scores, wall clock, max over ranks; `pinned` = the same from pinned memory.
   e2e_gct        the same fed from a GCT v1.2 text file through the device tokeniser (single rank).
-  roofline       FP64 work executed / measured DFMA peak (`frac`), the same launch counted by SURVEY 8(d)'s literal
-                 per-evaluation work (`algorithmic`), and the HBM view.
+  roofline       the dominant kernel (k_score) against the resource that binds it -- instruction issue: warp instructions
+                 per evaluation of the committed ncu capture x evaluations executed / launch time, over 4 schedulers x SMs
+                 x the SM clock (`frac`); `fp64` = FP64 work executed / measured DFMA peak (the earlier rounds' headline),
+                 `algorithmic` = the same launch counted by SURVEY 8(d)'s literal per-evaluation work, `hbm` the HBM view,
+                 `ncu` the committed capture's own counters.
   cpu_baseline   restated oracle on the host cores (rank 0, N = 1): all cores, and one core (the reference is
                  serial R).
   configs        short runs of the other named shapes (C2; C5; C4 at 8 GPUs) with their own check blocks.
