@@ -331,3 +331,33 @@ def test_bench_score_checksum_is_independent_of_the_sharding():
     swapped = cmi.copy()
     swapped[0, 0, [3, 4]] = swapped[0, 0, [4, 3]]
     assert bench.score_checksum(swapped, 0, F) != whole
+
+
+def test_score_block_plan_host_logic():
+    """rvl_score_plan (host side of k_score's launch): the most worker warps per block whose per-warp scratch -- struct +
+    float table of the soft cells + one bit row -- fits the dynamic shared-memory budget.  No GPU needed."""
+    import ctypes as C
+    from revealer_b200 import _lib
+    lib = _lib.load()
+    f = lib.rvl_score_plan
+    f.restype = C.c_size_t
+    f.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
+    budget = (227 - 33) * 1024
+
+    def plan(n, G, max_warps=0):
+        words = ((n + 63) // 64 + 1) & ~1
+        w = C.c_int(0)
+        return f(words, G, budget, max_warps, C.byref(w)), w.value, words
+
+    b3, w3, _ = plan(1000, 25)                       # C3: one 16-warp block per SM
+    assert w3 == 16 and 0 < b3 <= budget
+    b4, w4, words4 = plan(10000, 25)                 # C4: the longer bit row costs one warp
+    assert w4 == 15 and b4 <= budget and b4 % 16 == 0
+    assert (b4 // w4) - (b3 // w3) == 8 * (words4 - 16)          # per-warp bytes differ by the bit row only
+    _, w32, _ = plan(1000, 32)                       # n_grid 32: float table 2 x 32 x 36 floats
+    assert 1 <= w32 < 16
+    b, w, _ = plan(1000, 25, max_warps=12)           # tuning override
+    assert w == 12 and b == (b3 // 16) * 12
+    assert plan(1_600_000, 25)[0] == 0               # one bit row alone exceeds the budget: an error upstream, not a crash
+    strides = {G: (((G + 3) >> 2) | 1) * 4 for G in range(2, 33)}
+    assert all(s >= G and s % 4 == 0 and (s // 4) % 2 == 1 for G, s in strides.items())
