@@ -60,6 +60,7 @@ void rvl_launch_bcv_binary_table(int n, double *table, cudaStream_t st);
 void rvl_launch_target_setup(const double *x_all, int n, int T, int G, RvlTarget *tg, double *u_all, double *xc_all,
                              int *bin_all, int *cnt_all, int *nonfinite, int permuted, cudaStream_t st);
 size_t rvl_score_plan(int words, int G, size_t budget, int max_warps, int *warps_out);
+void rvl_set_pdl(int on);
 cudaError_t rvl_score_configure(size_t smem, int warps, int device, int *grid_out);
 void rvl_launch_score(const RvlParams *P, int grid_x, int warps, size_t smem, const uint64_t *bits, const double *u_all,
                       const double *xc_all, const RvlTarget *tg, const uint64_t *seeds, const double *bcvtab,
@@ -321,6 +322,7 @@ extern "C" int rvl_create(rvl_ctx **out, int device)
     }
     ctx->own_stream = true;
     if (const char *w = getenv("RVL_SCORE_WARPS")) ctx->score_warps_fixed = atoi(w); // tuning: force the block width of k_score
+    if (const char *w = getenv("RVL_PDL")) rvl_set_pdl(atoi(w));
     *out = ctx;
     return RVL_OK;
 }

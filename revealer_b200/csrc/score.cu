@@ -80,6 +80,14 @@ __device__ __forceinline__ bool rvl_ahead(double va, int64_t ia, double vb, int6
     return ia < ib;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel of the per-iteration chain k_score -> k_argmax -> k_advance -> k_score
+// may be made resident before its predecessor has finished (launch attribute programmaticStreamSerialization, see
+// rvl_launch_chain); it then does what does not depend on the predecessor (launch latency, block scheduling, the log-table
+// fill) and blocks in rvl_pdl_wait() until the predecessor grid has completed and its writes are visible.  Both are no-ops
+// in a launch without the attribute.
+__device__ __forceinline__ void rvl_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void rvl_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // Loads of data that ANOTHER block of the same launch may have written (k_search: the x-axis table, the seeds, the
 // per-iteration seed state, the candidate records): COH = true goes to L2 (ld.global.cg) instead of a possibly stale
 // L1 line; COH = false is the plain load of the split-phase kernels, whose inputs are constant during a launch.
@@ -1194,6 +1202,8 @@ k_advance(RvlParams P, RvlTarget *tg_all, const double *__restrict__ u_all, cons
           RvlPeerXchg X)
 {
     __shared__ RvlAdvanceShared sh;
+    rvl_pdl_launch_dependents();
+    rvl_pdl_wait();
     rvl_advance_task<false>(P, tg_all, u_all, seeds_in, seeds_out, bcvtab, tt, slots, nslots, work, recv, rec_bytes, iter, iters,
                             first_null, top, top_score, seed_iter, allow_incr, X, blockIdx.y, blockIdx.x, sh);
 }
@@ -1465,7 +1475,9 @@ k_score(RvlParams P, const uint64_t *__restrict__ bits, const double *__restrict
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int slot = blockIdx.x * nwarps + warp, nslots = gridDim.x * nwarps;
 
+    rvl_pdl_launch_dependents();
     rvl_logtab_fill(rvl_logtab_g); // the only block barrier of the kernel
+    rvl_pdl_wait();                // seeds, seed state, table, best slots and the work counter come from k_advance
 
     // dynamic shared memory, per warp: scratch | float table of the soft cells [2][G][stride] | bit row (rvl_score_plan)
     unsigned char *base = rvl_warp_smem(smem_raw, warp, P);
@@ -1685,6 +1697,8 @@ __global__ void k_argmax(RvlParams P, const RvlCandHead *__restrict__ part, int 
                          const uint64_t *__restrict__ bits, unsigned char *__restrict__ send, size_t rec_bytes,
                          RvlPeerXchg X)
 {
+    rvl_pdl_launch_dependents();
+    rvl_pdl_wait();
     rvl_publish_best<false>(P, part + (size_t)blockIdx.x * nparts, nparts, bits, send, rec_bytes, X, blockIdx.x);
 }
 
@@ -1924,6 +1938,23 @@ extern "C" cudaError_t rvl_search_configure(size_t smem, int warps, int device, 
     return cudaSuccess;
 }
 
+// Launch of one kernel of the per-iteration chain, optionally as a programmatic dependent of the kernel before it in the stream.
+static int g_rvl_pdl = 1; // on by default; RVL_PDL=0 in the environment turns it off (A/B: tools/ab_pdl.sh)
+extern "C" void rvl_set_pdl(int on) { g_rvl_pdl = on; }
+template <typename... KArgs, typename... Args>
+static void rvl_launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_rvl_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 extern "C" cudaError_t rvl_launch_search(const RvlSearchArgs *a, int grid_x, int warps, size_t smem, cudaStream_t st)
 {
     void *args[] = {(void *)a};
@@ -1936,8 +1967,8 @@ extern "C" void rvl_launch_score(const RvlParams *P, int grid_x, int warps, size
                                  RvlCandHead *part, unsigned long long *work, unsigned long long *ctr,
                                  const int64_t *uniq, int64_t U, cudaStream_t st)
 {
-    k_score<<<grid_x, warps * 32, smem, st>>>(*P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, part,
-                                                        work, ctr, uniq, U);
+    rvl_launch_chain(k_score, dim3(grid_x), dim3(warps * 32), smem, st, *P, bits, u_all, xc_all, tg, seeds, bcvtab, tt, scores, part,
+                     work, ctr, uniq, U);
 }
 
 extern "C" void rvl_launch_advance(const RvlParams *P, RvlTarget *tg, const double *u_all, const uint64_t *seeds_in,
@@ -1947,9 +1978,8 @@ extern "C" void rvl_launch_advance(const RvlParams *P, RvlTarget *tg, const doub
                                    uint64_t *seed_iter, int allow_incr, const RvlPeerXchg *X, cudaStream_t st)
 {
     dim3 grid(P->dense_x ? 1 : P->tt_nodes, P->T);
-    k_advance<<<grid, RVL_SCORE_WARPS * 32, 0, st>>>(*P, tg, u_all, seeds_in, seeds_out, bcvtab, tt, slots, nslots, work,
-                                                     recv, rec_bytes, iter, iters, first_null, top, top_score, seed_iter,
-                                                     allow_incr, *X);
+    rvl_launch_chain(k_advance, grid, dim3(RVL_SCORE_WARPS * 32), 0, st, *P, tg, u_all, seeds_in, seeds_out, bcvtab, tt, slots, nslots,
+                     work, recv, rec_bytes, iter, iters, first_null, top, top_score, seed_iter, allow_incr, *X);
 }
 
 // FP64 FMA peak micro-benchmark (MEASURED_PEAKS.json has no FP64 figure): 8 independent DFMA chains
@@ -1983,7 +2013,7 @@ extern "C" void rvl_launch_assoc(const RvlParams *P, int npairs, const RvlTarget
 extern "C" void rvl_launch_argmax(const RvlParams *P, const RvlCandHead *part, int nparts, const uint64_t *bits,
                                   unsigned char *send, size_t rec_bytes, const RvlPeerXchg *X, cudaStream_t st)
 {
-    k_argmax<<<P->T, 1024, 0, st>>>(*P, part, nparts, bits, send, rec_bytes, *X);
+    rvl_launch_chain(k_argmax, dim3(P->T), dim3(1024), 0, st, *P, part, nparts, bits, send, rec_bytes, *X);
 }
 
 extern "C" void rvl_launch_pack_f64_colmajor(const double *chunk, int64_t F, int64_t ld, int s0, int ncols,
