@@ -417,7 +417,7 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, float *__restrict__ lf, 
     // min / max of V and max of W are only used in the (conservative) column tests of pass B, so they are
     // tracked on the high words (non-negative doubles order like their bit patterns: one integer min/max
     // instead of a NaN-aware FP64 compare-select) and widened outwards afterwards.
-    double SV = 0.0, LV = 0.0, LLV = 0.0, SW = 0.0, LW = 0.0, LLW = 0.0, accxz = 0.0;
+    double LV = 0.0, LLV = 0.0, LW = 0.0, LLW = 0.0, accxz = 0.0; // (sum_i V and sum_i W are sM and sm below, in closed form)
     int minVh = 0x7ff00000, maxVh = 0, maxWh = 0;
     float *lfV = lf + kk * stride, *lfW = lf + (G + kk) * stride;
     const double2 *pM = reinterpret_cast<const double2 *>(&S.A[0][M0]), *pm = reinterpret_cast<const double2 *>(&S.A[0][m0]);
@@ -436,10 +436,8 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, float *__restrict__ lf, 
         const double Vs = __hiloint2double(max(Vh, 0x03c00000), __double2loint(V));
         const double Ws = __hiloint2double(max(Wh, 0x03c00000), __double2loint(W));
         const double lv = rvl_logq<FAST>(Vs), lw = rvl_logq<FAST>(Ws), lq = rvl_logq<FAST>(qxz);
-        SV += V;
         LV = fma(V, lv, LV);
         LLV += lv;
-        SW += W;
         LW = fma(W, lw, LW);
         LLW += lw;
         // (lanes >= G repeat lane 0's k and store the same two values to the same two addresses: no branch needed)
@@ -480,10 +478,10 @@ __device__ double rvl_cmi_epilogue_f(RvlWarpScratch &S, float *__restrict__ lf, 
     const int ndead = active ? G - __popc(rvl_bits(0, bC) | mMin | m4) : 0;
     double accF = 0.0;
     if (bC >= 0) // closed form over the majority columns: g (log g SV + LV) + eps' (G log g + LLV), + G eps' when factorised
-        accF = fma(SV, S.tab[1][bC], LV * S.tab[0][bC]) +
+        accF = fma(sM, S.tab[1][bC], LV * S.tab[0][bC]) +
                epsq * (fma((double)G, S.tab[2][bC], (double)(bC + 1) * LLV) + (double)((bF + 1) * G));
     if (hm >= 0)
-        accF += fma(SW, S.tab[1][hm], LW * S.tab[0][hm]) + epsq * fma((double)G, S.tab[2][hm], (double)(hm + 1) * LLW);
+        accF += fma(sm, S.tab[1][hm], LW * S.tab[0][hm]) + epsq * fma((double)G, S.tab[2][hm], (double)(hm + 1) * LLW);
     // list offsets: four-term columns (j << 5 | k) from the front of S.items; soft columns (class << 15 | d << 5 | k, d the
     // distance from the class's own end of the axis) from the back, the majority class's first
     int o4 = c4, oM = c2M, om = c2m;
