@@ -188,6 +188,7 @@ __global__ void k_target_stats(const double *__restrict__ x_all, int n, int G, R
         tg[t].xmin = lo;
         tg[t].xmax = hi;
         tg[t].is_const = (hi == lo) ? 1 : 0;
+        tg[t].seed_of = t; // every target is scored against its own seed unless rvl_set_null_targets says otherwise
     }
 }
 
