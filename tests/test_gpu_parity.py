@@ -848,3 +848,25 @@ def test_c3_search_winner_is_consistent(c3):
         assert col[top] == np.nanmax(col) and top == int(np.flatnonzero(col == col[top])[0])
         seed = np.maximum(seed, c3["m2"][top])
         assert np.array_equal(res["seed_iter"][0, it], seed)
+
+
+def test_programmatic_dependent_launch_changes_nothing():
+    """The per-iteration chain k_score -> k_argmax -> k_advance launched as programmatic dependents (default) and as plain
+    stream-ordered launches (RVL_PDL=0, read at rvl_create) must give bit-identical searches."""
+    w = _workload(300, 900)
+    res = {}
+    try:
+        for pdl in ("0", "1"):
+            os.environ["RVL_PDL"] = pdl
+            with _ctx() as ctx:
+                ctx.load_matrix(w["m2"])
+                ctx.set_targets(w["target"])
+                ctx.set_seed(w["seed"])
+                res[pdl] = ctx.search(6)
+    finally:
+        os.environ["RVL_PDL"] = "1"
+        with _ctx():
+            pass                                # the switch is process-wide: leave it on
+        del os.environ["RVL_PDL"]
+    for k in ("cmi", "top", "top_score", "seed_iter", "cmi_seed"):
+        assert np.array_equal(res["0"][k], res["1"][k], equal_nan=True) if res["0"][k].dtype.kind == "f" else np.array_equal(res["0"][k], res["1"][k]), k
